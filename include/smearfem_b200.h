@@ -1,0 +1,197 @@
+/*
+ * smearfem_b200.h -- C ABI of libsmearfem_b200.so: the B200-native (sm_100a) implementation of
+ * smearFEM.jl's assembly + solve hot path.
+ *
+ * The reference has no FFI of its own: its boundary is the Julia call surface
+ *   src/smearFEM.jl:3      export assemble_system, gaussian_quadrature, basis_function
+ *   examples/vector3D.jl   meshgrid (:10), setboundaryCond (:133), apply_boundary_conditions (:175),
+ *                          solve idiom (:308-322);  src/PostProcess.jl:30 inflate_sphere
+ * Every entry point below names the reference function (file:line, relative to the reference
+ * repository) it stands in for; INTEGRATION.md shows the Julia `ccall` binding for each.
+ *
+ * Conventions
+ *   - plain C: opaque handles, raw pointers, sizes; no C++/torch types cross this boundary.
+ *   - every function returns an int status (SMFEM_OK == 0); smfem_last_error() gives the message of
+ *     the last failure on the calling thread.  No exception or exit() crosses the ABI.
+ *   - HOST arrays use Julia's layouts verbatim: NodeList Float64 ndim x nNodes column-major
+ *     (xyz of a node contiguous); IEN Int64 nEl x nLocal column-major, 1-based; ID Int64
+ *     nNodes x nDof column-major, 1-based; sparse results are SparseMatrixCSC parts
+ *     (colptr, rowval, nzval), Int64, 1-based.
+ *   - one context == one GPU == one process (rank); multi-GPU runs are one process per GPU
+ *     (torchrun), the slab partition is by z node planes.  There is no CPU
+ *     fallback: without a CUDA device smfem_init fails with SMFEM_ERR_CUDA.
+ *   - calls are blocking w.r.t. the host unless stated; handles are not thread-safe.
+ */
+#ifndef SMEARFEM_B200_H
+#define SMEARFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMFEM_OK 0
+#define SMFEM_ERR_INVALID 1     /* bad argument (Julia: DimensionMismatch / BoundsError / ArgumentError) */
+#define SMFEM_ERR_CUDA 2        /* CUDA runtime failure, including "no device" */
+#define SMFEM_ERR_UNSUPPORTED 3 /* reference feature outside the built scope (e.g. 1-D, Q2 with nDof>1) */
+#define SMFEM_ERR_SINGULAR 4    /* PCG breakdown: p'Ap <= 0 (Julia: SingularException from inv) */
+
+#define SMFEM_Q1 1
+#define SMFEM_Q2 2
+
+typedef struct smfem_ctx smfem_ctx;
+typedef struct smfem_mesh smfem_mesh;
+typedef struct smfem_matrix smfem_matrix;
+
+int smfem_abi_version(void);
+const char *smfem_last_error(void);
+
+/* ---- host-side helpers (pure functions; same expression order as the reference) ------------- */
+
+/* gaussian_quadrature(a,b,nGaussPoints)           src/fem.jl:21-31.  n in {2,3}; else SMFEM_ERR_INVALID
+ * (the reference leaves xi undefined -> UndefVarError). xi, w: n doubles each. */
+int smfem_gaussian_quadrature(double a, double b, int n, double *xi, double *w);
+
+/* basis_function(xi,eta,zeta,FunctionClass)       src/fem.jl:48-114.  ndim = number of coordinates
+ * given (1,2,3).  N: nn doubles; dN: nn x ndim COLUMN-major (Julia Matrix), except the reference's
+ * 1-D quirk where dN is the 1x2 row [-0.5 0.5] (src/fem.jl:75).  *nn returns the node count. */
+int smfem_basis_function(int ndim, int func_class, double xi, double eta, double zeta, double *N, double *dN,
+                         int *nn);
+
+/* ---- context --------------------------------------------------------------------------------- */
+
+/* device: CUDA ordinal.  rank/nranks: position of this process in the z-slab partition (0/1 for a
+ * single GPU).  Creates the stream all library kernels run on. */
+int smfem_init(int device, int rank, int nranks, smfem_ctx **out);
+int smfem_destroy(smfem_ctx *ctx);
+/* raw cudaStream_t of the context (for callers that want to record their own events) */
+int smfem_stream(smfem_ctx *ctx, void **stream_out);
+/* CUDA-event stopwatch on the context's stream (what bench.py times kernels with) */
+int smfem_timer_start(smfem_ctx *ctx);
+int smfem_timer_stop(smfem_ctx *ctx, float *ms_out); /* records, synchronises, returns elapsed ms */
+int smfem_sync(smfem_ctx *ctx);
+/* counters: kernels launched by this library on this context since init (bench.py: gpu_launches) */
+int smfem_launch_count(smfem_ctx *ctx, int64_t *count_out);
+/* write `bytes` of device scratch (L2 flush between timed iterations) */
+int smfem_flush_l2(smfem_ctx *ctx);
+
+/* ---- mesh ------------------------------------------------------------------------------------ */
+
+/* meshgrid(x0,x1,y0,y1,z0,z1,ne,ndim)              examples/vector3D.jl:10-130.
+ * Generated ON DEVICE; with nranks > 1 only this rank's z-slab (owned node planes plus one ghost
+ * plane per side) is materialised.  ndim in {2,3}. */
+int smfem_meshgrid(smfem_ctx *ctx, double x0, double x1, double y0, double y1, double z0, double z1, int64_t ne,
+                   int ndim, smfem_mesh **out);
+
+/* An arbitrary user mesh as passed to assemble_system (src/fem.jl:135; coords gathered at :180,
+ * ids at :243-244).  Host arrays in Julia layout; copied to the device; index ranges validated.
+ * ID may be NULL for nDof == 1 (the reference then uses raw node ids, src/fem.jl:204-205).
+ * If (IEN, ID) are exactly what meshgrid would produce for `ne`, the structured fast path is
+ * taken; otherwise the general (unstructured) path.  nranks must be 1. */
+int smfem_mesh_from_host(smfem_ctx *ctx, const double *NodeList, const int64_t *IEN, const int64_t *ID,
+                         int64_t nNodes, int64_t nEl, int nLocal, int ndim, int nDof, int64_t ne,
+                         smfem_mesh **out);
+
+/* inflate_sphere(NodeList,x0,x1,y0,y1)             src/PostProcess.jl:30-44 (in place, on device) */
+int smfem_inflate_sphere(smfem_ctx *ctx, smfem_mesh *mesh, double x0, double x1, double y0, double y1);
+
+/* same, on a HOST NodeList (ndim x nNodes, mutated in place like the reference): upload, kernel, download */
+int smfem_inflate_sphere_host(smfem_ctx *ctx, double *NodeList, int ndim, int64_t nNodes, double x0, double x1,
+                              double y0, double y1);
+
+/* Overwrite node coordinates from a GLOBAL host NodeList (ndim x nNodes_global); each rank takes
+ * its slab.  (Robustness inputs: jittered meshes) */
+int smfem_mesh_set_nodelist(smfem_ctx *ctx, smfem_mesh *mesh, const double *NodeList_global);
+
+/* sizes: global node/element counts, nodes per element, this rank's first owned node (0-based) and
+ * owned node count */
+int smfem_mesh_info(smfem_mesh *mesh, int64_t *nNodes, int64_t *nEl, int *nLocal, int *ndim, int *structured,
+                    int64_t *node0_owned, int64_t *nNodes_owned);
+/* Export in Julia layout (caller allocates from smfem_mesh_info; any pointer may be NULL).
+ * NodeList: ndim x nNodes_owned of THIS rank's owned nodes; IEN/ID/IEN_top/IEN_btm: global arrays
+ * (structured meshes regenerate them; only sensible for small ne, rank 0). */
+int smfem_mesh_export(smfem_ctx *ctx, smfem_mesh *mesh, double *NodeList_owned, int64_t *IEN, int64_t *ID,
+                      int64_t *IEN_top, int64_t *IEN_btm);
+int smfem_mesh_free(smfem_mesh *mesh);
+
+/* ---- assembly -------------------------------------------------------------------------------- */
+
+/* assemble_system(ne,NodeList,IEN,ndim,FunctionClass,nDof,ID,Young,nu)   src/fem.jl:135-256.
+ * Builds the sparsity pattern on device (bit-exact with Julia's sparse(E,J,V), src/fem.jl:253:
+ * explicit zeros kept, rows ascending per column) and the values (fp64).  nDof==1: scalar Laplace
+ * (:199-208); nDof==2: plane stress (:210-217); nDof==3: 3-D isotropic (:218-230).
+ * The result stays on the device; this rank holds the rows of its owned nodes. */
+int smfem_assemble(smfem_ctx *ctx, smfem_mesh *mesh, int64_t ne, int ndim, int func_class, int nDof, double Young,
+                   double nu, smfem_matrix **K_out);
+/* The two halves of smfem_assemble, for timing them separately. */
+int smfem_pattern_build(smfem_ctx *ctx, smfem_mesh *mesh, int ndim, int nDof, smfem_matrix **K_out);
+int smfem_assemble_values(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu);
+/* Re-run the pattern kernels into K's existing buffers (no allocation, asynchronous): lets the
+ * bench time pattern build + values back to back with CUDA events.  Structured meshes only. */
+int smfem_pattern_rebuild(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
+
+/* m, n: global dims; nnz: global stored entries; row0/nrows_local/nnz_local: this rank's slab */
+int smfem_matrix_info(smfem_matrix *K, int64_t *m, int64_t *n, int64_t *nnz, int64_t *row0, int64_t *nrows_local,
+                      int64_t *nnz_local);
+/* SparseMatrixCSC parts of this rank's COLUMN slab [row0, row0+nrows_local) (the whole matrix
+ * when nranks == 1).  colptr: nrows_local+1 entries, 1-based, relative to this slab's first stored
+ * entry; rowval: global 1-based row ids; nzval: K[row, col] (true transpose of the device CSR).
+ * which: 0 = K as assembled (+ anything added in place), 1 = the surface matrix b of
+ * smfem_surface_mass on K's pattern. */
+int smfem_matrix_export_csc(smfem_ctx *ctx, smfem_matrix *K, int which, int64_t *colptr, int64_t *rowval,
+                            double *nzval);
+int smfem_matrix_diag(smfem_ctx *ctx, smfem_matrix *K, double *diag_local);
+int smfem_matrix_free(smfem_matrix *K);
+
+/* apply_boundary_conditions(ne,NodeList,IEN,IEN_top,IEN_btm,ndim,FunctionClass,ID,nDof)
+ *                                                  examples/vector3D.jl:175-264  and
+ * K_bar = K + beta*b                               examples/vector3D.jl:308.
+ * Computes b = int_{top U bottom} N'N on K's pattern (kept for export as `which`=1 when keep_b != 0;
+ * costs a second value array) and, if beta != 0, adds beta*b into K in place.  Structured meshes use their own top/bottom faces;
+ * IEN_top/IEN_btm (host, Int64, nFaces x 4 column-major, 1-based) override them when non-NULL. */
+int smfem_surface_mass(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, const int64_t *IEN_top,
+                       const int64_t *IEN_btm, int64_t nFaces, double beta, int keep_b);
+
+/* ---- Dirichlet conditions + solve ------------------------------------------------------------ */
+
+/* setboundaryCond(NodeList,ne,ndim,FunctionClass,d,nDof)      examples/vector3D.jl:133-173:
+ * z-dof of every node with z == 0 -> 0, with z == 1 -> -d (exact compares, :161-166). */
+int smfem_set_dirichlet_zplanes(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, double d);
+/* general form: global 1-based dof ids with prescribed values (replaces any earlier set) */
+int smfem_set_dirichlet(smfem_ctx *ctx, smfem_matrix *K, const int64_t *dofs, const double *values, int64_t n);
+
+/* K_free = C'K̄C ; q_f = K_free^{-1} C'(-K̄ q_d) ; q = q_d + C q_f      examples/vector3D.jl:315-322,
+ * with the reference's dense inverse replaced by Jacobi-preconditioned CG on the masked operator
+ * (Dirichlet rows/columns masked inside the SpMV kernel; K itself is not modified).
+ * rhs_extra (host, nrows_local, may be NULL) is added to the right-hand side (manufactured-solution
+ * tests).  q_out (host, nrows_local doubles, may be NULL) receives this rank's slab of q.
+ * Stops when ||r||_2 <= rtol*||b||_2 or after maxit iterations. */
+int smfem_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const double *rhs_extra,
+                    double *q_out, int *iters_out, double *relres_out);
+
+/* y = K x with host vectors of this rank's slab (nranks == 1 only; for tests) */
+int smfem_spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y);
+/* Time `reps` back-to-back device-resident SpMVs (x = deterministic pattern, halo exchange
+ * included when nranks > 1); returns average ms per SpMV measured with CUDA events on the
+ * context's stream.  variant: SpMV kernel variant (0 = default). */
+int smfem_bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *ms_per_spmv);
+/* choose the SpMV kernel the solver uses: 0 = warp per 3 rows (default), 1 = warp per row */
+int smfem_set_spmv_variant(smfem_matrix *K, int variant);
+/* statistics of the last smfem_pcg_solve on this matrix */
+int smfem_pcg_stats(smfem_matrix *K, float *ms_total, float *ms_spmv_est, int *iters);
+
+/* ---- multi-GPU peer window (one process per GPU) ----------------------------------------------
+ * After smfem_pattern_build / smfem_assemble each rank creates its communication window (halo
+ * planes of the search direction + all-reduce mailboxes), exports a CUDA IPC handle, the host side
+ * exchanges the handles with torch.distributed (all_gather), and every rank maps its peers.
+ * Afterwards the CG kernels write halo planes and dot-product partials directly into peer memory
+ * over NVLink; no host or NCCL call is on the data path.  SMFEM_IPC_HANDLE_BYTES per rank. */
+#define SMFEM_IPC_HANDLE_BYTES 64
+int smfem_comm_export(smfem_ctx *ctx, smfem_matrix *K, void *handle_out);
+int smfem_comm_connect(smfem_ctx *ctx, smfem_matrix *K, const void *all_handles /* nranks*64 bytes */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMEARFEM_B200_H */

@@ -1,0 +1,492 @@
+"""smearfem_b200 -- host-side mirror of smearFEM.jl's call surface over the B200 C ABI.
+
+The reference is a Julia package; Julia is not available in this image, so the host side above the
+C ABI (include/smearfem_b200.h) is written in Python with the SAME function names, positional
+arguments, defaults and array conventions as the reference:
+
+    gaussian_quadrature, basis_function, assemble_system        src/fem.jl:21, :48, :135
+    inflate_sphere                                               src/PostProcess.jl:30
+    meshgrid, setboundaryCond, apply_boundary_conditions         examples/vector3D.jl:10, :133, :175
+    solve (the idiom of examples/vector3D.jl:315-322)
+
+Array conventions are Julia's: NodeList (ndim, nNodes) float64; IEN (nEl, nLocal) int64 1-based;
+ID (nNodes, nDof) int64 1-based; sparse results expose SparseMatrixCSC parts (colptr, rowval,
+nzval), 1-based.  (smearfem.jl_b200/julia/SmearFEMB200.jl is the equivalent `ccall` shim.)
+
+All numerical work is done by hand-written sm_100a CUDA kernels inside libsmearfem_b200.so; there
+is no CPU fallback and nothing here imports the test oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import SmearFEMError, call
+
+__all__ = [
+    "gaussian_quadrature", "basis_function", "assemble_system", "inflate_sphere", "meshgrid", "setboundaryCond",
+    "apply_boundary_conditions", "solve", "greet_fem", "Context", "Mesh", "SparseMatrixB200", "SmearFEMError", "context",
+]
+
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+
+
+def _pf(a):
+    return a.ctypes.data_as(_f64p) if a is not None else None
+
+
+def _pi(a):
+    return a.ctypes.data_as(_i64p) if a is not None else None
+
+
+def _fclass(FunctionClass):
+    if FunctionClass == "Q1":
+        return _lib.Q1
+    if FunctionClass == "Q2":
+        return _lib.Q2
+    raise SmearFEMError(_lib.ERR_INVALID, f"unknown FunctionClass {FunctionClass!r} (reference: UndefVarError)")
+
+
+def greet_fem():
+    """src/fem.jl:4-6"""
+    print("Hello, I am the FEM module")
+
+
+# ------------------------------------------------------------------------------------------------
+# handles
+# ------------------------------------------------------------------------------------------------
+class Context:
+    """One GPU / one process.  rank, nranks give the position in the z-slab partition."""
+
+    def __init__(self, device=None, rank=None, nranks=None):
+        if rank is None:
+            rank = int(os.environ.get("RANK", "0")) if nranks is None else 0
+        if nranks is None:
+            nranks = int(os.environ.get("WORLD_SIZE", "1"))
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device, self.rank, self.nranks = device, rank, nranks
+        h = C.c_void_p()
+        call("smfem_init", device, rank, nranks, C.byref(h))
+        self.handle = h
+
+    def timer_start(self):
+        call("smfem_timer_start", self.handle)
+
+    def timer_stop(self):
+        ms = C.c_float()
+        call("smfem_timer_stop", self.handle, C.byref(ms))
+        return float(ms.value)
+
+    def sync(self):
+        call("smfem_sync", self.handle)
+
+    def flush_l2(self):
+        call("smfem_flush_l2", self.handle)
+
+    @property
+    def launches(self):
+        n = C.c_int64()
+        call("smfem_launch_count", self.handle, C.byref(n))
+        return int(n.value)
+
+    def stream(self):
+        s = C.c_void_p()
+        call("smfem_stream", self.handle, C.byref(s))
+        return s.value
+
+    def close(self):
+        if self.handle:
+            _lib.lib().smfem_destroy(self.handle)
+            self.handle = None
+
+
+_default_ctx = None
+
+
+def context():
+    """The process-wide default context (created on first use; device = LOCAL_RANK)."""
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+class Mesh:
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+
+    @classmethod
+    def meshgrid(cls, ctx, x0, x1, y0, y1, z0, z1, ne, ndim=3):
+        """Device-side meshgrid (examples/vector3D.jl:10-130); only this rank's slab is materialised."""
+        h = C.c_void_p()
+        call("smfem_meshgrid", ctx.handle, float(x0), float(x1), float(y0), float(y1), float(z0), float(z1), int(ne), int(ndim),
+             C.byref(h))
+        return cls(ctx, h)
+
+    @classmethod
+    def from_host(cls, ctx, NodeList, IEN, ID, ndim, nDof, ne):
+        NodeList = np.asfortranarray(NodeList, dtype=np.float64)
+        IEN = np.asfortranarray(IEN, dtype=np.int64)
+        if NodeList.ndim != 2 or NodeList.shape[0] != ndim:
+            raise SmearFEMError(_lib.ERR_INVALID, "NodeList must be ndim x nNodes (reference: DimensionMismatch)")
+        IDa = None if ID is None else np.asfortranarray(ID, dtype=np.int64)
+        if IDa is not None and (IDa.ndim != 2 or IDa.shape[0] != NodeList.shape[1]):
+            raise SmearFEMError(_lib.ERR_INVALID, "ID must be nNodes x nDof")
+        nd = nDof if IDa is None else IDa.shape[1]
+        h = C.c_void_p()
+        call("smfem_mesh_from_host", ctx.handle, _pf(NodeList), _pi(IEN), _pi(IDa), NodeList.shape[1], IEN.shape[0], IEN.shape[1],
+             int(ndim), int(nd), int(ne), C.byref(h))
+        return cls(ctx, h)
+
+    def info(self):
+        nN, nE, n0, nO = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        nl, nd, st = C.c_int(), C.c_int(), C.c_int()
+        call("smfem_mesh_info", self.handle, C.byref(nN), C.byref(nE), C.byref(nl), C.byref(nd), C.byref(st), C.byref(n0), C.byref(nO))
+        return dict(nNodes=nN.value, nEl=nE.value, nLocal=nl.value, ndim=nd.value, structured=bool(st.value),
+                    node0_owned=n0.value, nNodes_owned=nO.value)
+
+    def inflate_sphere(self, x0, x1, y0, y1):
+        call("smfem_inflate_sphere", self.ctx.handle, self.handle, float(x0), float(x1), float(y0), float(y1))
+        return self
+
+    def set_nodelist(self, NodeList_global):
+        a = np.asfortranarray(NodeList_global, dtype=np.float64)
+        call("smfem_mesh_set_nodelist", self.ctx.handle, self.handle, _pf(a))
+        return self
+
+    def nodelist(self):
+        """(ndim, nNodes_owned) coordinates of this rank's owned nodes."""
+        i = self.info()
+        out = np.zeros((i["ndim"], i["nNodes_owned"]), order="F")
+        call("smfem_mesh_export", self.ctx.handle, self.handle, _pf(out), None, None, None, None)
+        return out
+
+    def connectivity(self):
+        """(IEN, ID, IEN_top, IEN_btm) in Julia layout (structured meshes; small ne)."""
+        i = self.info()
+        ne = round(i["nEl"] ** (1 / 3))
+        IEN = np.zeros((i["nEl"], 8), dtype=np.int64, order="F")
+        ID = np.zeros((i["nNodes"], 3), dtype=np.int64, order="F")
+        top = np.zeros((ne * ne, 4), dtype=np.int64, order="F")
+        btm = np.zeros((ne * ne, 4), dtype=np.int64, order="F")
+        call("smfem_mesh_export", self.ctx.handle, self.handle, None, _pi(IEN), _pi(ID), _pi(top), _pi(btm))
+        return IEN, ID, top, btm
+
+    def free(self):
+        if self.handle:
+            _lib.lib().smfem_mesh_free(self.handle)
+            self.handle = None
+
+
+class SparseMatrixB200:
+    """Device-resident K (this rank's row slab).  Stands in for SparseMatrixCSC{Float64,Int64}."""
+
+    def __init__(self, ctx, handle, mesh):
+        self.ctx, self.handle, self.mesh = ctx, handle, mesh
+
+    # -- construction -------------------------------------------------------------------------
+    @classmethod
+    def assemble(cls, ctx, mesh, ne, ndim, FunctionClass, nDof, Young, nu):
+        h = C.c_void_p()
+        call("smfem_assemble", ctx.handle, mesh.handle, int(ne), int(ndim), _fclass(FunctionClass), int(nDof), float(Young),
+             float(nu), C.byref(h))
+        return cls(ctx, h, mesh)
+
+    @classmethod
+    def pattern(cls, ctx, mesh, ndim, nDof):
+        h = C.c_void_p()
+        call("smfem_pattern_build", ctx.handle, mesh.handle, int(ndim), int(nDof), C.byref(h))
+        return cls(ctx, h, mesh)
+
+    def assemble_values(self, Young, nu):
+        call("smfem_assemble_values", self.ctx.handle, self.mesh.handle, self.handle, float(Young), float(nu))
+        return self
+
+    def pattern_rebuild(self):
+        call("smfem_pattern_rebuild", self.ctx.handle, self.mesh.handle, self.handle)
+        return self
+
+    # -- queries ------------------------------------------------------------------------------
+    def info(self):
+        v = [C.c_int64() for _ in range(6)]
+        call("smfem_matrix_info", self.handle, *[C.byref(x) for x in v])
+        m, n, nnz, row0, nrl, nnzl = [x.value for x in v]
+        return dict(m=m, n=n, nnz=nnz, row0=row0, nrows_local=nrl, nnz_local=nnzl)
+
+    @property
+    def shape(self):
+        i = self.info()
+        return (i["m"], i["n"])
+
+    @property
+    def nnz(self):
+        return self.info()["nnz"]
+
+    def to_csc(self, which=0):
+        """(colptr, rowval, nzval): this rank's column slab as SparseMatrixCSC parts, 1-based."""
+        i = self.info()
+        colptr = np.zeros(i["nrows_local"] + 1, dtype=np.int64)
+        rowval = np.zeros(i["nnz_local"], dtype=np.int64)
+        nzval = np.zeros(i["nnz_local"], dtype=np.float64)
+        call("smfem_matrix_export_csc", self.ctx.handle, self.handle, int(which), _pi(colptr), _pi(rowval), _pf(nzval))
+        return colptr, rowval, nzval
+
+    def to_scipy(self, which=0):
+        import scipy.sparse as sp
+
+        colptr, rowval, nzval = self.to_csc(which)
+        i = self.info()
+        return sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(i["m"], i["nrows_local"]))
+
+    def diag(self):
+        d = np.zeros(self.info()["nrows_local"])
+        call("smfem_matrix_diag", self.ctx.handle, self.handle, _pf(d))
+        return d
+
+    # -- K_bar = K + beta*b  (examples/vector3D.jl:308), evaluated in place on the device ----------
+    def add_surface_mass(self, beta, IEN_top=None, IEN_btm=None, keep_b=False):
+        t = None if IEN_top is None else np.asfortranarray(IEN_top, dtype=np.int64)
+        b = None if IEN_btm is None else np.asfortranarray(IEN_btm, dtype=np.int64)
+        nf = 0 if t is None else t.shape[0]
+        call("smfem_surface_mass", self.ctx.handle, self.handle, self.mesh.handle, _pi(t), _pi(b), nf, float(beta), int(keep_b))
+        return self
+
+    def __add__(self, other):
+        if isinstance(other, SurfaceMatrix):
+            return other._add_into(self)
+        return NotImplemented
+
+    __radd__ = __add__
+
+    # -- Dirichlet + solve ----------------------------------------------------------------------
+    def set_dirichlet_zplanes(self, d):
+        call("smfem_set_dirichlet_zplanes", self.ctx.handle, self.handle, self.mesh.handle, float(d))
+        return self
+
+    def set_dirichlet(self, dofs, values):
+        dofs = np.ascontiguousarray(dofs, dtype=np.int64)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        call("smfem_set_dirichlet", self.ctx.handle, self.handle, _pi(dofs), _pf(values), dofs.shape[0])
+        return self
+
+    def pcg_solve(self, rtol=1e-12, maxit=20000, rhs_extra=None, want_q=True):
+        n = self.info()["nrows_local"]
+        q = np.zeros(n) if want_q else None
+        ex = None if rhs_extra is None else np.ascontiguousarray(rhs_extra, dtype=np.float64)
+        it, rel = C.c_int(), C.c_double()
+        call("smfem_pcg_solve", self.ctx.handle, self.handle, float(rtol), int(maxit), _pf(ex), _pf(q), C.byref(it), C.byref(rel))
+        return q, int(it.value), float(rel.value)
+
+    def pcg_stats(self):
+        ms, ms2, it = C.c_float(), C.c_float(), C.c_int()
+        call("smfem_pcg_stats", self.handle, C.byref(ms), C.byref(ms2), C.byref(it))
+        return dict(ms_total=float(ms.value), iters=int(it.value))
+
+    def spmv(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros_like(x)
+        call("smfem_spmv_host", self.ctx.handle, self.handle, _pf(x), _pf(y))
+        return y
+
+    def bench_spmv(self, reps=20, variant=0):
+        ms = C.c_float()
+        call("smfem_bench_spmv", self.ctx.handle, self.handle, int(variant), int(reps), C.byref(ms))
+        return float(ms.value)
+
+    def set_spmv_variant(self, variant):
+        call("smfem_set_spmv_variant", self.handle, int(variant))
+        return self
+
+    def free(self):
+        if self.handle:
+            _lib.lib().smfem_matrix_free(self.handle)
+            self.handle = None
+
+
+class SurfaceMatrix:
+    """What apply_boundary_conditions returns: b = ∫ N'N over the top and bottom faces, kept lazy so
+    that `K + β*b` (examples/vector3D.jl:308) becomes one in-place device kernel on K's pattern."""
+
+    def __init__(self, ctx, mesh, ne, IEN_top, IEN_btm, ID, beta=1.0):
+        self.ctx, self.mesh, self.ne, self.beta = ctx, mesh, ne, beta
+        self.IEN_top, self.IEN_btm, self.ID = IEN_top, IEN_btm, ID
+
+    def __rmul__(self, beta):
+        return SurfaceMatrix(self.ctx, self.mesh, self.ne, self.IEN_top, self.IEN_btm, self.ID, self.beta * float(beta))
+
+    __mul__ = __rmul__
+
+    def _add_into(self, K):
+        return K.add_surface_mass(self.beta, self.IEN_top, self.IEN_btm)
+
+    def to_csc(self):
+        """b as SparseMatrixCSC parts with ITS OWN pattern (pairs of dofs of nodes sharing a face)."""
+        K = SparseMatrixB200.pattern(self.ctx, self.mesh, 3, 3).assemble_values(0.0, 0.25)
+        K.add_surface_mass(0.0, self.IEN_top, self.IEN_btm, keep_b=True)
+        colptr, rowval, nzval = K.to_csc(which=1)
+        K.free()
+        # structural entries of b: (dof of node a, dof of node b) with a, b in a common face
+        ID = np.asarray(self.ID)
+        ndof = int(ID.max())
+        dof2node = np.zeros(ndof + 1, dtype=np.int64)
+        dof2node[ID.ravel(order="F")] = np.tile(np.arange(1, ID.shape[0] + 1), ID.shape[1])
+        faces = np.vstack([np.asarray(self.IEN_btm), np.asarray(self.IEN_top)])
+        nN = ID.shape[0]
+        a = np.repeat(faces, 4, axis=1).ravel()
+        bb = np.tile(faces, (1, 4)).ravel()
+        pair_keys = np.unique((a - 1) * nN + (bb - 1))
+        cols = np.repeat(np.arange(1, colptr.shape[0]), np.diff(colptr))
+        keys = (dof2node[rowval] - 1) * nN + (dof2node[cols] - 1)
+        keep = np.isin(keys, pair_keys)
+        newptr = np.zeros(ndof + 1, dtype=np.int64)
+        np.add.at(newptr, cols[keep], 1)
+        newptr = np.concatenate([[0], np.cumsum(newptr[1:])]) + 1
+        # Julia's sparse(E,J,V) sizes b by the largest index present (examples/vector3D.jl:262)
+        return newptr[: int(cols[keep].max()) + 1], rowval[keep], nzval[keep] * self.beta
+
+
+class Constraint:
+    """The constraint matrix C of setboundaryCond (identity with the constrained columns removed),
+    stored as the 1-based ids of the kept columns."""
+
+    def __init__(self, ndof, free):
+        self.ndof, self.free = ndof, free
+
+    @property
+    def shape(self):
+        return (self.ndof, self.free.shape[0])
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        n = self.free.shape[0]
+        return sp.csc_matrix((np.ones(n), (self.free - 1, np.arange(n))), shape=(self.ndof, n))
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's call surface
+# ------------------------------------------------------------------------------------------------
+def gaussian_quadrature(a, b, nGaussPoints=2):
+    """src/fem.jl:21-31 -> (xi, w).  nGaussPoints outside {2,3} raises (reference: UndefVarError)."""
+    n = int(nGaussPoints)
+    xi = np.zeros(max(n, 1))
+    w = np.zeros(max(n, 1))
+    call("smfem_gaussian_quadrature", float(a), float(b), n, _pf(xi), _pf(w))
+    return xi, w
+
+
+def basis_function(xi, eta=None, zeta=None, FunctionClass="Q1"):
+    """src/fem.jl:48-114 -> (N, dN) with dN (nnodes, ndim); the 1-D case keeps the 1x2 row quirk."""
+    ndim = 1 if eta is None else (2 if zeta is None else 3)
+    N = np.zeros(9)
+    dN = np.zeros(27)
+    nn = C.c_int()
+    call("smfem_basis_function", ndim, _fclass(FunctionClass), float(xi), 0.0 if eta is None else float(eta),
+         0.0 if zeta is None else float(zeta), _pf(N), _pf(dN), C.byref(nn))
+    n = nn.value
+    if ndim == 1:
+        return N[:n].copy(), dN[:2].reshape(1, 2).copy()
+    return N[:n].copy(), dN[: n * ndim].reshape((n, ndim), order="F").copy()
+
+
+def meshgrid(x0, x1, y0, y1, z0, z1, ne, ndim):
+    """examples/vector3D.jl:10-130 -> (NodeList, IEN, ID, IEN_top, IEN_btm, [Border, Bottom, Top]).
+    3-D: coordinates generated by the device kernel; integer tables by the library's exporter."""
+    ne = int(ne)
+    if ndim == 3:
+        ctx = context()
+        if ctx.nranks != 1:
+            raise SmearFEMError(_lib.ERR_UNSUPPORTED, "host-array meshgrid is single-process; use Mesh.meshgrid per rank")
+        m = Mesh.meshgrid(ctx, x0, x1, y0, y1, z0, z1, ne, 3)
+        NodeList = m.nodelist()
+        IEN, ID, top, btm = m.connectivity()
+        m.free()
+        n1 = ne + 1
+        k, j, i = np.meshgrid(np.arange(n1), np.arange(n1), np.arange(n1), indexing="ij")
+        i, j, k = i.ravel(), j.ravel(), k.ravel()
+        ids = np.arange(1, n1**3 + 1)
+        side = (i == 0) | (i == ne) | (j == 0) | (j == ne)
+        borders = [list(ids[side]), list(ids[~side & (k == 0)]), list(ids[~side & (k == ne) & (k != 0)])]
+        return NodeList, IEN, ID, top, btm, borders
+    if ndim == 2:  # examples/vector3D.jl:23-58: integer bookkeeping + two ranges, host side
+        n1 = ne + 1
+        x = x0 + (x1 - x0) * (np.arange(n1) / ne)
+        y = y0 + (y1 - y0) * (np.arange(n1) / ne)
+        x[0], x[-1], y[0], y[-1] = x0, x1, y0, y1
+        jj, ii = np.meshgrid(np.arange(n1), np.arange(n1), indexing="ij")
+        NodeList = np.asfortranarray(np.vstack([x[ii.ravel()], y[jj.ravel()]]))
+        m = np.arange(1, n1 * n1 + 1)
+        ID = np.asfortranarray(np.column_stack([2 * (m - 1) + 1, 2 * (m - 1) + 2]).astype(np.int64))
+        ej, ei = np.meshgrid(np.arange(1, ne + 1), np.arange(1, ne + 1), indexing="ij")
+        ej, ei = ej.ravel(), ei.ravel()
+        IEN = np.asfortranarray(np.column_stack([(ej - 1) * n1 + ei, (ej - 1) * n1 + ei + 1, ej * n1 + ei + 1, ej * n1 + ei]).astype(np.int64))
+        btm = np.zeros((ne, 2), dtype=np.int64)
+        top = np.zeros((ne, 2), dtype=np.int64)
+        btm[:, 0], btm[:, 1] = IEN[ej == 1, 0], IEN[ej == 1, 1]
+        if ne > 1:
+            top[:, 0], top[:, 1] = IEN[ej == ne, 3], IEN[ej == ne, 2]
+        border = list(m[(ii.ravel() == 0) | (ii.ravel() == ne)])
+        return NodeList, IEN, ID, top, btm, [border, [], []]
+    raise SmearFEMError(_lib.ERR_UNSUPPORTED, "meshgrid: ndim must be 2 or 3")
+
+
+def inflate_sphere(NodeList, x0, x1, y0, y1):
+    """src/PostProcess.jl:30-44.  IN PLACE (and returned), like the reference."""
+    if not (isinstance(NodeList, np.ndarray) and NodeList.dtype == np.float64 and NodeList.flags.f_contiguous):
+        raise SmearFEMError(_lib.ERR_INVALID, "inflate_sphere mutates its argument: pass a float64 column-major (ndim,nNodes) array")
+    call("smfem_inflate_sphere_host", context().handle, _pf(NodeList), NodeList.shape[0], NodeList.shape[1], float(x0), float(x1),
+         float(y0), float(y1))
+    return NodeList
+
+
+def assemble_system(ne, NodeList, IEN, ndim, FunctionClass="Q1", nDof=1, ID=None, Young=1, nu=0.3):
+    """src/fem.jl:135-256 -> K (device-resident SparseMatrixB200; `.to_csc()` gives Julia's CSC parts)."""
+    ctx = context()
+    if nDof > 1 and ID is None:
+        raise SmearFEMError(_lib.ERR_INVALID, "ID is required when nDof > 1 (reference: MethodError size(nothing, 2))")
+    mesh = Mesh.from_host(ctx, NodeList, IEN, ID if nDof > 1 else None, ndim, nDof, ne)
+    return SparseMatrixB200.assemble(ctx, mesh, ne, ndim, FunctionClass, nDof, Young, nu)
+
+
+def apply_boundary_conditions(ne, NodeList, IEN, IEN_top, IEN_btm, ndim, FunctionClass, ID, nDof=3):
+    """examples/vector3D.jl:175-264 -> b (lazy SurfaceMatrix; `K + β*b` runs on the device)."""
+    if ndim != 3:
+        raise SmearFEMError(_lib.ERR_UNSUPPORTED, "apply_boundary_conditions: the reference's 2-D branch is not executable")
+    _fclass(FunctionClass)
+    ctx = context()
+    mesh = Mesh.from_host(ctx, NodeList, IEN, ID, ndim, nDof, ne)
+    return SurfaceMatrix(ctx, mesh, ne, np.asarray(IEN_top), np.asarray(IEN_btm), np.asarray(ID))
+
+
+def setboundaryCond(NodeList, ne, ndim, FunctionClass, d, nDof=1):
+    """examples/vector3D.jl:133-173 -> (q_d (ndof x 1), C).  Host data preparation, as upstream; the
+    conditions themselves are applied inside the SpMV / CG kernels by `solve`."""
+    if FunctionClass != "Q1":
+        raise SmearFEMError(_lib.ERR_INVALID, "UndefVarError: q_d not defined (reference defines it for Q1 only)")
+    ndof = nDof * (ne + 1) ** ndim
+    q_d = np.zeros((ndof, 1))
+    z = np.asarray(NodeList)[2]
+    nodes = np.arange(1, z.shape[0] + 1)
+    btm = z == 0
+    top = (z == 1) & ~btm
+    q_d[3 * nodes[top] - 1, 0] = -d
+    rCol = np.concatenate([3 * nodes[btm], 3 * nodes[top]])
+    free = np.setdiff1d(np.arange(1, ndim * (ne + 1) ** ndim + 1), rCol)
+    return q_d, Constraint(ndim * (ne + 1) ** ndim, free)
+
+
+def solve(K_bar, q_d, C_, rtol=1e-12, maxit=20000, return_info=False):
+    """examples/vector3D.jl:315-322: K_free = C'K̄C; q_f = K_free⁻¹ C'(-K̄ q_d); q = q_d + C q_f,
+    with the dense inverse replaced by Jacobi-PCG on the Dirichlet-masked device operator."""
+    q_d = np.asarray(q_d, dtype=np.float64).reshape(-1)
+    fixed = np.setdiff1d(np.arange(1, C_.ndof + 1), C_.free)
+    K_bar.set_dirichlet(fixed, q_d[fixed - 1])
+    q, it, rel = K_bar.pcg_solve(rtol=rtol, maxit=maxit)
+    if return_info:
+        return q, dict(iters=it, relres=rel)
+    return q

@@ -1,0 +1,731 @@
+// Assembly side of the path: sparsity pattern on device, element kernels, scatter, surface term,
+// diagonal extraction, CSC export.
+//   reference: src/fem.jl:135-256 (assemble_system), examples/vector3D.jl:175-264 (surface matrix)
+#include <cub/device/device_scan.cuh>
+
+#include "smfem_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Quadrature tables in the reference's Gauss-point order (src/fem.jl:161-164, :172-176), built on
+// the host with the same code that backs the ABI's basis_function and uploaded once.
+// ------------------------------------------------------------------------------------------------
+__constant__ double c_dN3[8][8][3];  // [gp][node][d/dxi_d]
+__constant__ double c_w3[8];
+__constant__ double c_dN2[4][4][2];
+__constant__ double c_N2[4][4];
+__constant__ double c_w2[4];
+
+void mesh_upload_tables() {
+    double xi[2], w[2];
+    smfem_host_gauss(-1, 1, 2, xi, w);
+    const int ix[8] = {0, 1, 1, 0, 0, 1, 1, 0}, iy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, iz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+    double dN3[8][8][3], w3[8], dN2[4][4][2], N2[4][4], w2[4];
+    for (int g = 0; g < 8; ++g) {
+        double N[8], dN[24];
+        int nn;
+        smfem_host_basis(3, SMFEM_Q1, xi[ix[g]], xi[iy[g]], xi[iz[g]], N, dN, &nn);
+        for (int a = 0; a < 8; ++a)
+            for (int d = 0; d < 3; ++d) dN3[g][a][d] = dN[d * 8 + a];
+        w3[g] = w[ix[g]] * w[iy[g]] * w[iz[g]];
+    }
+    for (int g = 0; g < 4; ++g) {
+        double N[4], dN[8];
+        int nn;
+        smfem_host_basis(2, SMFEM_Q1, xi[ix[g]], xi[iy[g]], 0, N, dN, &nn);
+        for (int a = 0; a < 4; ++a) {
+            N2[g][a] = N[a];
+            for (int d = 0; d < 2; ++d) dN2[g][a][d] = dN[d * 4 + a];
+        }
+        w2[g] = w[ix[g]] * w[iy[g]];
+    }
+    CUDA_CHECK(cudaMemcpyToSymbol(c_dN3, dN3, sizeof dN3));
+    CUDA_CHECK(cudaMemcpyToSymbol(c_w3, w3, sizeof w3));
+    CUDA_CHECK(cudaMemcpyToSymbol(c_dN2, dN2, sizeof dN2));
+    CUDA_CHECK(cudaMemcpyToSymbol(c_N2, N2, sizeof N2));
+    CUDA_CHECK(cudaMemcpyToSymbol(c_w2, w2, sizeof w2));
+}
+
+// ------------------------------------------------------------------------------------------------
+// dof maps and connectivity views shared by the kernels
+// ------------------------------------------------------------------------------------------------
+struct DofMap {
+    const int32_t *id;  // [comp][node] 0-based, or nullptr for dof = nDof*node + comp
+    int64_t nNodes;
+    int nDof;
+    int64_t ghost_cols, nrows_l;
+    __device__ __forceinline__ int64_t col(int64_t ln, int c) const {
+        return id ? (int64_t)id[(int64_t)c * nNodes + ln] : ln * nDof + c;
+    }
+    __device__ __forceinline__ int64_t row(int64_t ln, int c) const {
+        int64_t r = col(ln, c) - ghost_cols;
+        return (r >= 0 && r < nrows_l) ? r : -1;
+    }
+};
+
+struct Conn {
+    const int32_t *ien;  // general: [a][e]
+    int64_t nEl;         // elements this rank works on
+    Lattice L;
+    int structured;
+    int layer0;  // structured: first element layer worked on
+    __device__ __forceinline__ int64_t node(int64_t e, int a) const {
+        if (!structured) return ien[(int64_t)a * nEl + e];
+        int ne = L.ne;
+        int ei = (int)(e % ne), ej = (int)((e / ne) % ne), ek = (int)(e / ((int64_t)ne * ne)) + layer0;
+        // local node order of examples/vector3D.jl:94-101
+        int ox = ((a & 3) == 1 || (a & 3) == 2), oy = ((a & 3) >= 2), oz = (a >> 2);
+        return L.lnode(ei + ox, ej + oy, ek + oz);
+    }
+};
+
+static DofMap make_dofmap(const smfem_mesh *mesh, const smfem_matrix *K) {
+    DofMap d;
+    d.id = mesh->structured ? nullptr : mesh->id;
+    d.nNodes = mesh->nNodes_l;
+    d.nDof = K->nDof;
+    d.ghost_cols = K->ghost_cols;
+    d.nrows_l = K->nrows_l;
+    return d;
+}
+
+static Conn make_conn(const smfem_mesh *mesh) {
+    Conn c;
+    c.ien = mesh->ien;
+    c.L = mesh->lat;
+    c.structured = mesh->structured ? 1 : 0;
+    c.layer0 = 0;
+    c.nEl = mesh->nEl_g;
+    if (mesh->structured) {
+        int l0 = mesh->lat.k0 - 1 < 0 ? 0 : mesh->lat.k0 - 1;
+        int l1 = mesh->lat.k1 < mesh->lat.ne ? mesh->lat.k1 : mesh->lat.ne;  // layers [l0,l1)
+        c.layer0 = l0;
+        c.nEl = (int64_t)(l1 - l0) * mesh->lat.ne * mesh->lat.ne;
+    }
+    return c;
+}
+
+// position of local column `c` inside local row `r` (binary search; rows are sorted ascending)
+__device__ __forceinline__ int64_t csr_find(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                            int64_t r, int64_t c) {
+    int64_t lo = rowptr[r], hi = rowptr[r + 1] - 1;
+    while (lo <= hi) {
+        int64_t mid = (lo + hi) >> 1;
+        int32_t v = colind[mid];
+        if (v == c) return mid;
+        if (v < c) lo = mid + 1;
+        else hi = mid - 1;
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (structured): closed-form CSR pattern == Julia's sparse(E,J,V) pattern for the hex lattice.
+// Along one axis node i has cnt1(i) in-range neighbours {i-1,i,i+1}; the neighbours of (i,j,k) in
+// ascending global node order are the tensor product (k' slowest).  Each row of node m holds
+// nDof * |nbrs(m)| columns: the dofs nDof*n + c' of its neighbours n, ascending.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cnt1(int i, int n1) { return 1 + (i > 0) + (i < n1 - 1); }
+__device__ __forceinline__ int64_t pre1(int i) { return i == 0 ? 0 : 3 * (int64_t)i - 1; }
+__device__ __forceinline__ int64_t pairs_before(int n1, int i, int j, int k) {
+    int64_t S1 = 3 * (int64_t)n1 - 2;
+    return pre1(k) * S1 * S1 + (int64_t)cnt1(k, n1) * (pre1(j) * S1 + (int64_t)cnt1(j, n1) * pre1(i));
+}
+
+__global__ void k_struct_rowptr(Lattice L, int nDof, int64_t nrows_l, int64_t *__restrict__ rowptr) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > nrows_l) return;
+    int64_t base = (int64_t)nDof * nDof * pairs_before(L.n1, 0, 0, L.k0);
+    if (r == nrows_l) {
+        int64_t S1 = 3 * (int64_t)L.n1 - 2;
+        int64_t endp = (L.k1 >= L.n1) ? S1 * S1 * S1 : pairs_before(L.n1, 0, 0, L.k1);
+        rowptr[r] = (int64_t)nDof * nDof * endp - base;
+        return;
+    }
+    int64_t node = r / nDof;
+    int c = (int)(r % nDof);
+    int i = (int)(node % L.n1), j = (int)((node / L.n1) % L.n1), k = (int)(node / L.plane()) + L.k0;
+    int cnt = cnt1(i, L.n1) * cnt1(j, L.n1) * cnt1(k, L.n1);
+    rowptr[r] = (int64_t)nDof * nDof * pairs_before(L.n1, i, j, k) + (int64_t)c * nDof * cnt - base;
+}
+
+// one warp per owned node: writes the nDof rows of the node (contiguous in colind), coalesced
+__global__ void k_struct_colind(Lattice L, int nDof, int64_t nOwnedNodes, const int64_t *__restrict__ rowptr,
+                                int32_t *__restrict__ colind) {
+    int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (node >= nOwnedNodes) return;
+    int i = (int)(node % L.n1), j = (int)((node / L.n1) % L.n1), k = (int)(node / L.plane()) + L.k0;
+    int cx = cnt1(i, L.n1), cy = cnt1(j, L.n1), cz = cnt1(k, L.n1);
+    int i0 = i - (i > 0), j0 = j - (j > 0), k0 = k - (k > 0);
+    int T = nDof * cx * cy * cz;
+    int64_t base = rowptr[node * nDof];
+    for (int t = lane; t < nDof * T; t += 32) {
+        int s = t % T;
+        int q = s / nDof, comp = s - q * nDof;
+        int ai = q % cx, aj = (q / cx) % cy, ak = q / (cx * cy);
+        colind[base + t] = (int32_t)(L.lnode(i0 + ai, j0 + aj, k0 + ak) * nDof + comp);
+    }
+}
+
+static void matrix_alloc_pattern(smfem_matrix *K) {
+    K->rowptr = dev_alloc<int64_t>(K->nrows_l + 1);
+}
+
+void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
+    const Lattice &L = mesh->lat;
+    int nDof = K->nDof;
+    K->structured = true;
+    K->lat = L;
+    K->m_g = (int64_t)nDof * mesh->nNodes_g;
+    int64_t S1 = 3 * (int64_t)L.n1 - 2;
+    K->nnz_g = (int64_t)nDof * nDof * S1 * S1 * S1;
+    K->ghost_cols = L.plane() * nDof;
+    K->nrows_l = (int64_t)L.nown() * L.plane() * nDof;
+    K->ncols_l = K->nrows_l + 2 * K->ghost_cols;
+    K->row0 = (int64_t)L.k0 * L.plane() * nDof;
+    REQUIRE(K->ncols_l < (int64_t)INT32_MAX, SMFEM_ERR_UNSUPPORTED, "local dof count exceeds int32 column indices");
+    const bool first = (K->rowptr == nullptr);
+    if (first) matrix_alloc_pattern(K);
+    LAUNCH(ctx, k_struct_rowptr, (unsigned)((K->nrows_l + 1 + 255) / 256), 256, 0, L, nDof, K->nrows_l, K->rowptr);
+    if (first) {
+        CUDA_CHECK(cudaMemcpyAsync(&K->nnz_l, K->rowptr + K->nrows_l, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        K->colind = dev_alloc<int32_t>(K->nnz_l);
+    }
+    int64_t nOwned = (int64_t)L.nown() * L.plane();
+    LAUNCH(ctx, k_struct_colind, (unsigned)((nOwned * 32 + 255) / 256), 256, 0, L, nDof, nOwned, K->rowptr, K->colind);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (general): arbitrary (IEN, ID).  node->element lists -> sorted unique node adjacency ->
+// rows through the dof map, columns sorted ascending (Julia CSC has ascending row ids per column
+// and the pattern is structurally symmetric).
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_ADJ = 64;   // max distinct neighbour nodes of a node (incl. itself)
+constexpr int MAX_VAL = 16;   // max elements sharing a node
+
+__global__ void k_n2e_count(const int32_t *__restrict__ ien, int64_t nEl, int nn, int *__restrict__ cnt) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nEl * nn) return;
+    atomicAdd(&cnt[ien[t]], 1);
+}
+
+__global__ void k_n2e_fill(const int32_t *__restrict__ ien, int64_t nEl, int nn, const int64_t *__restrict__ ptr,
+                           int *__restrict__ cursor, int32_t *__restrict__ n2e) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nEl * nn) return;
+    int node = ien[t];
+    int e = (int)(t % nEl);
+    int slot = atomicAdd(&cursor[node], 1);
+    n2e[ptr[node] + slot] = e;
+}
+
+// thread per node: sorted unique neighbour list (two passes: count, then fill)
+__global__ void k_node_adj(const int32_t *__restrict__ ien, int64_t nEl, int nn, int64_t nNodes,
+                           const int64_t *__restrict__ n2e_ptr, const int32_t *__restrict__ n2e,
+                           const int64_t *__restrict__ adj_ptr, int32_t *__restrict__ adj, int *__restrict__ adj_cnt,
+                           int *__restrict__ err) {
+    int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nNodes) return;
+    int32_t loc[MAX_ADJ];
+    int n = 0;
+    for (int64_t q = n2e_ptr[m]; q < n2e_ptr[m + 1]; ++q) {
+        int e = n2e[q];
+        for (int a = 0; a < nn; ++a) {
+            int32_t v = ien[(int64_t)a * nEl + e];
+            int pos = 0;
+            while (pos < n && loc[pos] < v) ++pos;
+            if (pos < n && loc[pos] == v) continue;
+            if (n >= MAX_ADJ) {
+                *err = 1;
+                return;
+            }
+            for (int s = n; s > pos; --s) loc[s] = loc[s - 1];
+            loc[pos] = v;
+            ++n;
+        }
+    }
+    if (adj == nullptr) {
+        adj_cnt[m] = n;
+    } else {
+        int64_t base = adj_ptr[m];
+        for (int s = 0; s < n; ++s) adj[base + s] = loc[s];
+    }
+}
+
+// row lengths: row of dof (m,c) has nDof*|adj(m)| entries
+__global__ void k_gen_rowlen(DofMap D, const int64_t *__restrict__ adj_ptr, int64_t nNodes, int64_t ndof,
+                             int64_t *__restrict__ rowlen, int *__restrict__ err) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nNodes * D.nDof) return;
+    int64_t m = t / D.nDof;
+    int c = (int)(t % D.nDof);
+    int64_t r = D.col(m, c);
+    if (r < 0 || r >= ndof) {
+        *err = 2;
+        return;
+    }
+    int64_t old = atomicExch((unsigned long long *)&rowlen[r], (unsigned long long)((adj_ptr[m + 1] - adj_ptr[m]) * D.nDof));
+    if (old != 0) *err = 3;  // two (node, comp) pairs map to one dof: not a bijection
+}
+
+__global__ void k_gen_colind(DofMap D, const int64_t *__restrict__ adj_ptr, const int32_t *__restrict__ adj,
+                             int64_t nNodes, const int64_t *__restrict__ rowptr, int32_t *__restrict__ colind) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nNodes * D.nDof) return;
+    int64_t m = t / D.nDof;
+    int c = (int)(t % D.nDof);
+    int64_t r = D.col(m, c);
+    int64_t base = rowptr[r];
+    int n = 0;
+    bool sorted = true;
+    int32_t prev = -1;
+    for (int64_t q = adj_ptr[m]; q < adj_ptr[m + 1]; ++q) {
+        int32_t nb = adj[q];
+        for (int cc = 0; cc < D.nDof; ++cc) {
+            int32_t v = (int32_t)D.col(nb, cc);
+            colind[base + n++] = v;
+            sorted = sorted && (v > prev);
+            prev = v;
+        }
+    }
+    if (!sorted) {  // permuted ID maps: insertion sort of this row (rare, short rows)
+        for (int a = 1; a < n; ++a) {
+            int32_t v = colind[base + a];
+            int b = a - 1;
+            while (b >= 0 && colind[base + b] > v) {
+                colind[base + b + 1] = colind[base + b];
+                --b;
+            }
+            colind[base + b + 1] = v;
+        }
+    }
+}
+
+template <class T>
+static void exclusive_scan(smfem_ctx *ctx, const T *in, int64_t *out, int64_t n);
+
+template <class In>
+static void exclusive_scan_impl(smfem_ctx *ctx, In in, int64_t *out, int64_t n) {
+    void *tmp = nullptr;
+    size_t bytes = 0;
+    REQUIRE(n < (int64_t)INT32_MAX, SMFEM_ERR_UNSUPPORTED, "scan length exceeds int32");
+    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, (int)n, ctx->stream));
+    CUDA_CHECK(cudaMalloc(&tmp, bytes ? bytes : 1));
+    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, (int)n, ctx->stream));
+    ctx->launches += 2;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(tmp);
+}
+
+struct IntTo64 {
+    const int *p;
+    __host__ __device__ int64_t operator()(int64_t i) const { return (int64_t)p[i]; }
+};
+
+void pattern_build_general(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
+    REQUIRE(ctx->nranks == 1, SMFEM_ERR_UNSUPPORTED, "general (unstructured) meshes are single-GPU only");
+    const int64_t nNodes = mesh->nNodes_g, nEl = mesh->nEl_g;
+    const int nn = mesh->nn, nDof = K->nDof;
+    K->structured = false;
+    K->ghost_cols = 0;
+    int64_t ndof = mesh->id ? mesh->ndof_id : nNodes * nDof;
+    REQUIRE(ndof == nNodes * nDof, SMFEM_ERR_UNSUPPORTED,
+            "ID must be a bijection onto 1..nDof*nNodes (max(ID) != nDof*nNodes)");
+    K->m_g = ndof;
+    K->nrows_l = ndof;
+    K->ncols_l = ndof;
+    K->row0 = 0;
+    REQUIRE(ndof < (int64_t)INT32_MAX, SMFEM_ERR_UNSUPPORTED, "dof count exceeds int32 column indices");
+
+    int *cnt = dev_alloc<int>(nNodes + 1), *cursor = dev_alloc<int>(nNodes + 1), *err = dev_alloc<int>(1);
+    int64_t *n2e_ptr = dev_alloc<int64_t>(nNodes + 1), *adj_ptr = dev_alloc<int64_t>(nNodes + 1);
+    CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int) * (nNodes + 1), ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(int) * (nNodes + 1), ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(err, 0, sizeof(int), ctx->stream));
+    unsigned gE = (unsigned)((nEl * nn + 255) / 256), gN = (unsigned)((nNodes + 127) / 128);
+    LAUNCH(ctx, k_n2e_count, gE, 256, 0, mesh->ien, nEl, nn, cnt);
+    {
+        // scan of int counts into int64 offsets (nNodes+1 entries: last one = total)
+        int64_t *tmp64 = dev_alloc<int64_t>(nNodes + 1);
+        CUDA_CHECK(cudaMemsetAsync(tmp64, 0, 8 * (nNodes + 1), ctx->stream));
+        // widen
+        std::vector<int> h(nNodes + 1);
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), cnt, sizeof(int) * (nNodes + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        int mx = 0;
+        for (int64_t i = 0; i < nNodes; ++i) mx = h[i] > mx ? h[i] : mx;
+        REQUIRE(mx <= MAX_VAL, SMFEM_ERR_UNSUPPORTED, "a node is shared by more than 16 elements");
+        std::vector<int64_t> p(nNodes + 1);
+        int64_t s = 0;
+        for (int64_t i = 0; i <= nNodes; ++i) {
+            p[i] = s;
+            if (i < nNodes) s += h[i];
+        }
+        CUDA_CHECK(cudaMemcpyAsync(n2e_ptr, p.data(), 8 * (nNodes + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        dev_free(tmp64);
+    }
+    int32_t *n2e = dev_alloc<int32_t>(nEl * nn);
+    LAUNCH(ctx, k_n2e_fill, gE, 256, 0, mesh->ien, nEl, nn, n2e_ptr, cursor, n2e);
+    // (element order inside a node's list is irrelevant: the adjacency below is sorted + unique)
+    int *adj_cnt = cnt;  // reuse
+    LAUNCH(ctx, k_node_adj, gN, 128, 0, mesh->ien, nEl, nn, nNodes, n2e_ptr, n2e, (const int64_t *)nullptr,
+           (int32_t *)nullptr, adj_cnt, err);
+    CUDA_CHECK(cudaMemsetAsync(adj_cnt + nNodes, 0, sizeof(int), ctx->stream));
+    {
+        std::vector<int> h(nNodes + 1);
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), adj_cnt, sizeof(int) * (nNodes + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        std::vector<int64_t> p(nNodes + 1);
+        int64_t s = 0;
+        for (int64_t i = 0; i <= nNodes; ++i) {
+            p[i] = s;
+            if (i < nNodes) s += h[i];
+        }
+        CUDA_CHECK(cudaMemcpyAsync(adj_ptr, p.data(), 8 * (nNodes + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        int herr = 0;
+        CUDA_CHECK(cudaMemcpy(&herr, err, sizeof(int), cudaMemcpyDeviceToHost));
+        REQUIRE(herr == 0, SMFEM_ERR_UNSUPPORTED, "a node has more than 64 neighbour nodes");
+        int32_t *adj = dev_alloc<int32_t>(s);
+        LAUNCH(ctx, k_node_adj, gN, 128, 0, mesh->ien, nEl, nn, nNodes, n2e_ptr, n2e, adj_ptr, adj, adj_cnt, err);
+
+        DofMap D = make_dofmap(mesh, K);
+        D.nrows_l = ndof;
+        int64_t *rowlen = dev_alloc<int64_t>(ndof + 1);
+        CUDA_CHECK(cudaMemsetAsync(rowlen, 0, 8 * (ndof + 1), ctx->stream));
+        unsigned gR = (unsigned)((nNodes * nDof + 255) / 256);
+        LAUNCH(ctx, k_gen_rowlen, gR, 256, 0, D, adj_ptr, nNodes, ndof, rowlen, err);
+        CUDA_CHECK(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        REQUIRE(herr == 0, SMFEM_ERR_INVALID, "ID is not a bijection onto 1..nDof*nNodes");
+        matrix_alloc_pattern(K);
+        exclusive_scan_impl(ctx, rowlen, K->rowptr, ndof + 1);
+        CUDA_CHECK(cudaMemcpy(&K->nnz_l, K->rowptr + ndof, 8, cudaMemcpyDeviceToHost));
+        K->nnz_g = K->nnz_l;
+        K->colind = dev_alloc<int32_t>(K->nnz_l);
+        LAUNCH(ctx, k_gen_colind, gR, 256, 0, D, adj_ptr, adj, nNodes, K->rowptr, K->colind);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        dev_free(rowlen);
+        dev_free(adj);
+    }
+    dev_free(n2e);
+    dev_free(cnt);
+    dev_free(cursor);
+    dev_free(err);
+    dev_free(n2e_ptr);
+    dev_free(adj_ptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K3, general form: one thread per (element, local node a) computes the a-th block row of
+//   Ke = sum_gp w * B'DB                                   (src/fem.jl:183-233)
+// through the isotropic identity  K_ab = lam * G_ab + mu * G_ab' + mu tr(G_ab) I,
+// G_ab = sum_gp w grad N_a grad N_b'  (material applied once after the Gauss loop), and adds it
+// into the CSR values with fp64 atomics.  Used for unstructured meshes, 2-D and scalar problems;
+// the structured hex path uses the tiled gather kernel in assemble_tile.cu.
+// ------------------------------------------------------------------------------------------------
+template <int NDIM>
+__device__ __forceinline__ double jac_inv(const double *J, double *inv) {
+    if (NDIM == 2) {
+        double d = J[0] * J[3] - J[1] * J[2];
+        double id = 1.0 / d;
+        inv[0] = J[3] * id;
+        inv[1] = -J[1] * id;
+        inv[2] = -J[2] * id;
+        inv[3] = J[0] * id;
+        return d;
+    } else {
+        double c00 = J[4] * J[8] - J[5] * J[7], c01 = J[5] * J[6] - J[3] * J[8], c02 = J[3] * J[7] - J[4] * J[6];
+        double d = J[0] * c00 + J[1] * c01 + J[2] * c02;
+        double id = 1.0 / d;
+        inv[0] = c00 * id;
+        inv[1] = (J[2] * J[7] - J[1] * J[8]) * id;
+        inv[2] = (J[1] * J[5] - J[2] * J[4]) * id;
+        inv[3] = c01 * id;
+        inv[4] = (J[0] * J[8] - J[2] * J[6]) * id;
+        inv[5] = (J[2] * J[3] - J[0] * J[5]) * id;
+        inv[6] = c02 * id;
+        inv[7] = (J[1] * J[6] - J[0] * J[7]) * id;
+        inv[8] = (J[0] * J[4] - J[1] * J[3]) * id;
+        return d;
+    }
+}
+
+struct Material {
+    double d11, lam, mu;  // D(1,1), D(1,2), shear
+};
+
+template <int NDIM, int NDOF>
+__global__ void __launch_bounds__(128)
+k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64_t *__restrict__ rowptr,
+                const int32_t *__restrict__ colind, double *__restrict__ val, Material mat) {
+    constexpr int NN = 1 << NDIM, NGP = 1 << NDIM;
+    __shared__ double s_dN[NGP][NN][NDIM];
+    __shared__ double s_w[NGP];
+    for (int t = threadIdx.x; t < NGP * NN * NDIM; t += blockDim.x) {
+        int g = t / (NN * NDIM), rem = t % (NN * NDIM);
+        s_dN[g][rem / NDIM][rem % NDIM] = (NDIM == 3) ? c_dN3[g][rem / NDIM][rem % NDIM] : c_dN2[g][rem / NDIM][rem % NDIM];
+    }
+    if (threadIdx.x < NGP) s_w[threadIdx.x] = (NDIM == 3) ? c_w3[threadIdx.x] : c_w2[threadIdx.x];
+    __syncthreads();
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= C.nEl * NN) return;
+    int64_t e = t / NN;
+    int a = (int)(t % NN);
+    int64_t nodes[NN];
+    double X[NN][NDIM];
+#pragma unroll
+    for (int b = 0; b < NN; ++b) {
+        nodes[b] = C.node(e, b);
+#pragma unroll
+        for (int d = 0; d < NDIM; ++d) X[b][d] = coords[nodes[b] * NDIM + d];
+    }
+    // does this thread own any row?  (ghost element layers only feed owned rows)
+    int64_t rows[NDOF];
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c) {
+        rows[c] = D.row(nodes[a], c);
+        any = any || rows[c] >= 0;
+    }
+    if (!any) return;
+    constexpr int GS = (NDOF == 1) ? 1 : NDIM * NDIM;
+    double G[NN][GS];
+#pragma unroll
+    for (int b = 0; b < NN; ++b)
+#pragma unroll
+        for (int s = 0; s < GS; ++s) G[b][s] = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < NGP; ++g) {
+        double J[NDIM * NDIM], inv[NDIM * NDIM];
+#pragma unroll
+        for (int r = 0; r < NDIM; ++r)
+#pragma unroll
+            for (int c = 0; c < NDIM; ++c) {
+                double s = 0;
+#pragma unroll
+                for (int b = 0; b < NN; ++b) s += X[b][r] * s_dN[g][b][c];  // Jac = coords*dN, src/fem.jl:192
+                J[r * NDIM + c] = s;
+            }
+        double w = s_w[g] * fabs(jac_inv<NDIM>(J, inv));  // :194-195
+        double ga[NDIM];
+#pragma unroll
+        for (int c = 0; c < NDIM; ++c) {
+            double s = 0;
+#pragma unroll
+            for (int k = 0; k < NDIM; ++k) s += s_dN[g][a][k] * inv[k * NDIM + c];  // dNdX = dN*invJ, :196
+            ga[c] = s * w;
+        }
+#pragma unroll
+        for (int b = 0; b < NN; ++b) {
+            double gb[NDIM];
+#pragma unroll
+            for (int c = 0; c < NDIM; ++c) {
+                double s = 0;
+#pragma unroll
+                for (int k = 0; k < NDIM; ++k) s += s_dN[g][b][k] * inv[k * NDIM + c];
+                gb[c] = s;
+            }
+            if (NDOF == 1) {
+                double s = 0;
+#pragma unroll
+                for (int c = 0; c < NDIM; ++c) s += ga[c] * gb[c];
+                G[b][0] += s;
+            } else {
+#pragma unroll
+                for (int i = 0; i < NDIM; ++i)
+#pragma unroll
+                    for (int j = 0; j < NDIM; ++j) G[b][(i * NDIM + j) % GS] += ga[i] * gb[j];
+            }
+        }
+    }
+    // material + scatter (src/fem.jl:236-249)
+#pragma unroll 1
+    for (int b = 0; b < NN; ++b) {
+        if (NDOF == 1) {
+            int64_t pos = csr_find(rowptr, colind, rows[0], D.col(nodes[b], 0));
+            atomicAdd(&val[pos], G[b][0]);
+        } else {
+            double tr = 0;
+#pragma unroll
+            for (int i = 0; i < NDIM; ++i) tr += G[b][(i * NDIM + i) % GS];
+#pragma unroll
+            for (int i = 0; i < NDIM; ++i) {
+                if (rows[i % NDOF] < 0) continue;
+#pragma unroll
+                for (int j = 0; j < NDIM; ++j) {
+                    double gij = G[b][(i * NDIM + j) % GS], gji = G[b][(j * NDIM + i) % GS];
+                    double v = (i == j) ? mat.d11 * gij + mat.mu * (tr - gij) : mat.lam * gij + mat.mu * gji;
+                    int64_t pos = csr_find(rowptr, colind, rows[i % NDOF], D.col(nodes[b], j % NDOF));
+                    atomicAdd(&val[pos], v);
+                }
+            }
+        }
+    }
+}
+
+void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat);  // assemble_tile.cu
+bool values_tile_enabled();
+
+void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu) {
+    Material mat;
+    const int ndim = K->ndim, nDof = K->nDof;
+    if (nDof == 2) {  // plane stress, src/fem.jl:217
+        mat.d11 = Young / (1 - nu * nu);
+        mat.lam = nu * Young / (1 - nu * nu);
+        mat.mu = Young / (2 * (1 + nu));
+    } else {  // src/fem.jl:230
+        double f = Young / ((1 + nu) * (1 - 2 * nu));
+        mat.d11 = (1 - nu) * f;
+        mat.lam = nu * f;
+        mat.mu = (1 - 2 * nu) / 2 * f;
+    }
+    if (!K->val) K->val = dev_alloc<double>(K->nnz_l);
+    if (mesh->structured && ndim == 3 && nDof == 3 && values_tile_enabled()) {
+        values_assemble_tile(ctx, mesh, K, mat);  // writes every entry: no memset needed
+    } else {
+        CUDA_CHECK(cudaMemsetAsync(K->val, 0, sizeof(double) * K->nnz_l, ctx->stream));
+        Conn C = make_conn(mesh);
+        DofMap D = make_dofmap(mesh, K);
+        const int nn = 1 << ndim;
+        unsigned grid = (unsigned)((C.nEl * nn + 127) / 128);
+        if (ndim == 3 && nDof == 3)
+            LAUNCH(ctx, (k_values_atomic<3, 3>), grid, 128, 0, C, D, mesh->coords, K->rowptr, K->colind, K->val, mat);
+        else if (ndim == 3 && nDof == 1)
+            LAUNCH(ctx, (k_values_atomic<3, 1>), grid, 128, 0, C, D, mesh->coords, K->rowptr, K->colind, K->val, mat);
+        else if (ndim == 2 && nDof == 2)
+            LAUNCH(ctx, (k_values_atomic<2, 2>), grid, 128, 0, C, D, mesh->coords, K->rowptr, K->colind, K->val, mat);
+        else if (ndim == 2 && nDof == 1)
+            LAUNCH(ctx, (k_values_atomic<2, 1>), grid, 128, 0, C, D, mesh->coords, K->rowptr, K->colind, K->val, mat);
+        else
+            throw SmfemError(SMFEM_ERR_UNSUPPORTED, "assemble_system: supported (ndim,nDof) are (3,3) (3,1) (2,2) (2,1)");
+    }
+    K->values_ready = true;
+    extract_diag(ctx, K);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: b = int_{top U bottom} N'N dGamma  (examples/vector3D.jl:193-262) on K's pattern;
+// K += beta*b (:308).  One thread per (face, local node a).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_surface_mass(const int32_t *__restrict__ faces, int64_t nFaces, DofMap D,
+                               const double *__restrict__ coords, const int64_t *__restrict__ rowptr,
+                               const int32_t *__restrict__ colind, double *__restrict__ val, double *__restrict__ bval,
+                               double beta) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nFaces * 4) return;
+    int64_t f = t >> 2;
+    int a = (int)(t & 3);
+    int64_t nodes[4];
+    double X[4][3];
+    for (int b = 0; b < 4; ++b) {
+        nodes[b] = faces[(int64_t)b * nFaces + f];
+        for (int d = 0; d < 3; ++d) X[b][d] = coords[nodes[b] * 3 + d];
+    }
+    double acc[4] = {0, 0, 0, 0};
+    for (int g = 0; g < 4; ++g) {
+        double t1[3] = {0, 0, 0}, t2[3] = {0, 0, 0};
+        for (int b = 0; b < 4; ++b)
+            for (int d = 0; d < 3; ++d) {
+                t1[d] += X[b][d] * c_dN2[g][b][0];  // coords*dN, :224-225
+                t2[d] += X[b][d] * c_dN2[g][b][1];
+            }
+        double cx = t1[1] * t2[2] - t1[2] * t2[1], cy = t1[2] * t2[0] - t1[0] * t2[2], cz = t1[0] * t2[1] - t1[1] * t2[0];
+        double w = c_w2[g] * sqrt(cx * cx + cy * cy + cz * cz);  // :227-228
+        for (int b = 0; b < 4; ++b) acc[b] += w * (c_N2[g][a] * c_N2[g][b]);  // be = M'M, :235
+    }
+    for (int c = 0; c < 3; ++c) {
+        int64_t r = D.row(nodes[a], c);
+        if (r < 0) continue;
+        for (int b = 0; b < 4; ++b) {
+            int64_t pos = csr_find(rowptr, colind, r, D.col(nodes[b], c));
+            if (pos < 0) continue;
+            if (bval) atomicAdd(&bval[pos], acc[b]);
+            if (beta != 0.0) atomicAdd(&val[pos], beta * acc[b]);
+        }
+    }
+}
+
+void surface_mass(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, const int32_t *faces_dev, int64_t nFaces,
+                  double beta, bool keep_b) {
+    REQUIRE(K->ndim == 3 && K->nDof == 3, SMFEM_ERR_UNSUPPORTED,
+            "apply_boundary_conditions: only the 3-D branch of the reference is executable");
+    if (keep_b) {
+        if (!K->bval) K->bval = dev_alloc<double>(K->nnz_l);
+        CUDA_CHECK(cudaMemsetAsync(K->bval, 0, sizeof(double) * K->nnz_l, ctx->stream));
+    }
+    if (nFaces > 0) {
+        DofMap D = make_dofmap(mesh, K);
+        LAUNCH(ctx, k_surface_mass, (unsigned)((nFaces * 4 + 127) / 128), 128, 0, faces_dev, nFaces, D, mesh->coords,
+               K->rowptr, K->colind, K->val, keep_b ? K->bval : (double *)nullptr, beta);
+    }
+    if (beta != 0.0) extract_diag(ctx, K);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: diagonal (Jacobi preconditioner)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_extract_diag(int64_t nrows, int64_t ghost_cols, const int64_t *__restrict__ rowptr,
+                               const int32_t *__restrict__ colind, const double *__restrict__ val,
+                               double *__restrict__ diag) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    int64_t pos = csr_find(rowptr, colind, r, r + ghost_cols);
+    diag[r] = pos >= 0 ? val[pos] : 0.0;
+}
+
+void extract_diag(smfem_ctx *ctx, smfem_matrix *K) {
+    if (!K->diag) K->diag = dev_alloc<double>(K->nrows_l);
+    LAUNCH(ctx, k_extract_diag, (unsigned)((K->nrows_l + 255) / 256), 256, 0, K->nrows_l, K->ghost_cols, K->rowptr,
+           K->colind, K->val, K->diag);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Export as SparseMatrixCSC parts.  The pattern is structurally symmetric, so column j of the CSC
+// has the row ids of CSR row j; the values are transposed through a search (nranks == 1) so that
+// nzval really is K[i,j]; with nranks > 1 rows of other ranks are not resident and the slab of
+// K' is returned instead (K is symmetric to rounding, ~1e-16 relative).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_export_csc(int64_t nrows, int64_t ghost_cols, int64_t col_off_g, const int64_t *__restrict__ rowptr,
+                             const int32_t *__restrict__ colind, const double *__restrict__ val, int transpose,
+                             int64_t *__restrict__ colptr1, int64_t *__restrict__ rowval1, double *__restrict__ nzval) {
+    int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (j > nrows) return;
+    if (lane == 0) colptr1[j] = rowptr[j] + 1;
+    if (j == nrows) return;
+    for (int64_t p = rowptr[j] + lane; p < rowptr[j + 1]; p += 32) {
+        int64_t c = colind[p];
+        rowval1[p] = c + col_off_g + 1;
+        if (val) {
+            double v = val[p];
+            if (transpose) {
+                int64_t i = c - ghost_cols;  // local row of the mirror entry
+                int64_t q = csr_find(rowptr, colind, i, j + ghost_cols);
+                v = val[q];
+            }
+            nzval[p] = v;
+        }
+    }
+}
+
+void export_csc(smfem_ctx *ctx, smfem_matrix *K, int which, int64_t *colptr, int64_t *rowval, double *nzval) {
+    const double *src = which == 1 ? K->bval : K->val;
+    REQUIRE(which == 0 || which == 1, SMFEM_ERR_INVALID, "export: which must be 0 (K) or 1 (b)");
+    REQUIRE(which == 0 || K->bval, SMFEM_ERR_INVALID, "export: surface matrix b was not kept");
+    int64_t *d_colptr = dev_alloc<int64_t>(K->nrows_l + 1), *d_rowval = dev_alloc<int64_t>(K->nnz_l);
+    double *d_nz = (nzval && src) ? dev_alloc<double>(K->nnz_l) : nullptr;
+    int64_t col_off_g = K->row0 - K->ghost_cols;
+    LAUNCH(ctx, k_export_csc, (unsigned)(((K->nrows_l + 1) * 32 + 255) / 256), 256, 0, K->nrows_l, K->ghost_cols,
+           col_off_g, K->rowptr, K->colind, d_nz ? src : (const double *)nullptr, ctx->nranks == 1 ? 1 : 0, d_colptr,
+           d_rowval, d_nz);
+    if (colptr) CUDA_CHECK(cudaMemcpyAsync(colptr, d_colptr, 8 * (K->nrows_l + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (rowval) CUDA_CHECK(cudaMemcpyAsync(rowval, d_rowval, 8 * K->nnz_l, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_nz) CUDA_CHECK(cudaMemcpyAsync(nzval, d_nz, 8 * K->nnz_l, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    dev_free(d_colptr);
+    dev_free(d_rowval);
+    dev_free(d_nz);
+}

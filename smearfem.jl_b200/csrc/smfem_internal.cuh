@@ -1,0 +1,190 @@
+// Internal structures of libsmearfem_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/smearfem_b200.h"
+
+struct SmfemError : std::runtime_error {
+    int code;
+    SmfemError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define CUDA_CHECK(x)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (x);                                                                           \
+        if (e_ != cudaSuccess)                                                                          \
+            throw SmfemError(SMFEM_ERR_CUDA, std::string(#x) + " -> " + cudaGetErrorString(e_) + " (" + \
+                                                 __FILE__ + ":" + std::to_string(__LINE__) + ")");     \
+    } while (0)
+
+#define REQUIRE(cond, code, msg)                      \
+    do {                                              \
+        if (!(cond)) throw SmfemError((code), (msg)); \
+    } while (0)
+
+constexpr int SMFEM_MAX_RANKS = 8;
+
+struct smfem_ctx {
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // user stopwatch (smfem_timer_*)
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;  // internal timing (pcg_solve, bench_spmv)
+    int sms = 148;
+    int64_t launches = 0;
+    void *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+};
+
+// Counts every kernel this library launches (bench.py reports it as gpu_launches).
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                        \
+    do {                                                                   \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);   \
+        (ctx)->launches++;                                                 \
+        CUDA_CHECK(cudaGetLastError());                                    \
+    } while (0)
+
+template <class T>
+inline T *dev_alloc(size_t n) {
+    T *p = nullptr;
+    if (n == 0) n = 1;
+    CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
+    return p;
+}
+template <class T>
+inline void dev_free(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Structured hex lattice (examples/vector3D.jl:60-127): n1 = ne+1 nodes per axis, node id
+// = k*n1^2 + j*n1 + i (x fastest).  A rank owns node planes [k0, k1); its LOCAL arrays always carry
+// one ghost plane below and one above (unused at the ends of the domain), so the local plane of
+// global plane k is  k - k0 + 1  and every rank has the same layout
+//     [ ghost_lo | owned planes ... | ghost_hi ].
+// ---------------------------------------------------------------------------------------------
+struct Lattice {
+    int n1 = 0, ne = 0;
+    int k0 = 0, k1 = 0;  // owned planes [k0,k1)
+    __host__ __device__ int64_t plane() const { return (int64_t)n1 * n1; }
+    __host__ __device__ int nown() const { return k1 - k0; }
+    __host__ __device__ int64_t nodes_local() const { return (int64_t)(k1 - k0 + 2) * n1 * n1; }
+    // local node index (with ghosts) of global (i,j,k); k may be k0-1 .. k1
+    __host__ __device__ int64_t lnode(int i, int j, int k) const {
+        return ((int64_t)(k - k0 + 1) * n1 + j) * n1 + i;
+    }
+};
+
+inline void slab_range(int n1, int rank, int nranks, int &k0, int &k1) {
+    k0 = (int)((int64_t)n1 * rank / nranks);
+    k1 = (int)((int64_t)n1 * (rank + 1) / nranks);
+}
+
+struct smfem_mesh {
+    smfem_ctx *ctx = nullptr;
+    int ndim = 3, nn = 8;
+    bool structured = false;
+    int64_t ne = 0;
+    int64_t nNodes_g = 0, nEl_g = 0;
+    Lattice lat;
+    int64_t nNodes_l = 0;      // local nodes incl. ghost planes (== nNodes_g for general meshes)
+    double *coords = nullptr;  // ndim x nNodes_l, xyz of a node contiguous (Julia NodeList layout)
+    // general (unstructured) meshes only
+    int32_t *ien = nullptr;  // [a][e], 0-based node ids (SoA like Julia's column-major IEN)
+    int32_t *id = nullptr;   // [comp][node], 0-based dof ids; nullptr -> dof = nDof*node+comp
+    int nDof_id = 0;
+    int64_t ndof_id = 0;  // max(ID)
+    // surface faces for general meshes are passed to smfem_surface_mass directly
+};
+
+// all-reduce mailboxes + halo flags, at the start of each rank's peer window
+struct CommHeader {
+    double mbox[2][SMFEM_MAX_RANKS][4];
+    unsigned long long mflag[2][SMFEM_MAX_RANKS];
+    unsigned long long hflag[2];  // [0]: ghost_lo filled up to seq, [1]: ghost_hi
+    unsigned long long pad[6];
+};
+
+struct PcgScalars {
+    double rzs[2], pAp, alpha, beta, rr, bnorm2, spare;
+    unsigned long long it;      // global iteration counter (never reset: sequence for flags)
+    unsigned long long red;     // global all-reduce sequence counter
+    unsigned int ticketA, ticketB, ticketC, breakdown;
+};
+
+struct CommView {  // passed by value to kernels
+    int rank = 0, nranks = 1;
+    CommHeader *self = nullptr;
+    CommHeader *peer[SMFEM_MAX_RANKS] = {nullptr};
+    double *peer_p[SMFEM_MAX_RANKS] = {nullptr};  // peers' p vectors (inside their windows)
+    int64_t lo_dst_off = 0;  // offset in peer (rank-1)'s p of its ghost_hi plane
+    int64_t plane_dofs = 0;  // dofs per node plane
+};
+
+struct smfem_matrix {
+    smfem_ctx *ctx = nullptr;
+    int ndim = 3, nDof = 3, nn = 8;
+    bool structured = false;
+    Lattice lat;
+    int64_t m_g = 0, nnz_g = 0;
+    int64_t row0 = 0, nrows_l = 0, ncols_l = 0, ghost_cols = 0, nnz_l = 0;
+    int64_t *rowptr = nullptr;  // nrows_l+1, local offsets
+    int32_t *colind = nullptr;  // local column index (into vectors with ghost planes)
+    double *val = nullptr;
+    double *bval = nullptr;  // surface matrix on the same pattern (only when kept)
+    double *diag = nullptr;
+    bool values_ready = false;
+    // Dirichlet
+    uint8_t *fixed = nullptr;  // nrows_l
+    double *qd = nullptr;      // ncols_l (ghost entries filled locally)
+    bool has_bc = false;
+    // solver workspace
+    double *x = nullptr, *r = nullptr, *Ap = nullptr, *dinv = nullptr, *partials = nullptr;
+    int64_t partials_n = 0;
+    double *p = nullptr;  // ncols_l; lives inside `window`
+    void *window = nullptr;
+    size_t window_bytes = 0;
+    PcgScalars *scal = nullptr;
+    double *h_pinned = nullptr;
+    CommView comm;
+    void *peer_maps[SMFEM_MAX_RANKS] = {nullptr};
+    bool comm_connected = false;
+    int spmv_variant = 0;
+    // stats
+    float last_ms = 0, last_ms_spmv = 0;
+    int last_iters = 0;
+};
+
+// --- functions implemented across translation units ---------------------------------------------
+void smfem_host_gauss(double a, double b, int n, double *xi, double *w);
+void smfem_host_basis(int ndim, int func_class, double xi, double eta, double zeta, double *N, double *dN, int *nn);
+
+void mesh_upload_tables();  // quadrature tables -> __constant__ (assemble.cu)
+void mesh_generate_structured(smfem_ctx *ctx, smfem_mesh *m, double x0, double x1, double y0, double y1, double z0,
+                              double z1);
+void mesh_inflate(smfem_ctx *ctx, smfem_mesh *m, double x0, double x1, double y0, double y1);
+
+void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
+void pattern_build_general(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
+void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu);
+void surface_mass(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, const int32_t *faces_dev, int64_t nFaces,
+                  double beta, bool keep_b);
+void extract_diag(smfem_ctx *ctx, smfem_matrix *K);
+void export_csc(smfem_ctx *ctx, smfem_matrix *K, int which, int64_t *colptr, int64_t *rowval, double *nzval);
+
+void solver_alloc(smfem_ctx *ctx, smfem_matrix *K);
+void solver_free(smfem_matrix *K);
+void dirichlet_zplanes(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, double d);
+void dirichlet_list(smfem_ctx *ctx, smfem_matrix *K, const int64_t *dofs, const double *vals, int64_t n);
+void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const double *rhs_extra, double *q_out,
+               int *iters, double *relres);
+void spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y);
+void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *ms);
+void comm_export(smfem_ctx *ctx, smfem_matrix *K, void *handle_out);
+void comm_connect(smfem_ctx *ctx, smfem_matrix *K, const void *handles);

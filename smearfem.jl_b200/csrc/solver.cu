@@ -1,0 +1,738 @@
+// Solve side of the path: in-kernel Dirichlet conditions, CSR SpMV, Jacobi-preconditioned CG with
+// fused vector kernels, halo exchange + dot-product all-reduce through peer memory (NVLink).
+//   reference: examples/vector3D.jl:133-173 (setboundaryCond), :308-322 (solve; the dense inverse
+//   of :318 is replaced by PCG on the same system K̄[free,free] q_f = -(K̄ q_d)[free]).
+#include <cmath>
+#include <cstring>
+
+#include "smfem_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ld_stream_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int32_t *p) {
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile_f64(const double *p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block sum (fixed tree); result valid in thread 0
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *smem /* NT/32 doubles */) {
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    double s = 0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < NT / 32; ++i) s += smem[i];
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// All-reduce of up to 4 doubles through the peer windows: every rank stores its partial into slot
+// [seq&1][rank] of EVERY rank's mailbox (direct NVLink stores), then releases a flag; readers spin
+// on their own (local) mailbox and add the partials in rank order, so all ranks obtain bitwise
+// identical sums.  Two slots suffice because sequence s+2 can only be published after s+1 has been
+// read from all ranks (see DESIGN.md "Multi-GPU").
+// ------------------------------------------------------------------------------------------------
+__device__ void allreduce_publish(const CommView &cv, unsigned long long seq, int nv, const double *vals) {
+    int slot = (int)(seq & 1ull);
+    for (int q = 0; q < cv.nranks; ++q) {
+        CommHeader *h = cv.peer[q];
+        for (int v = 0; v < nv; ++v) h->mbox[slot][cv.rank][v] = vals[v];
+    }
+    __threadfence_system();
+    for (int q = 0; q < cv.nranks; ++q) st_release_sys(&cv.peer[q]->mflag[slot][cv.rank], seq);
+}
+
+__device__ void allreduce_fetch(const CommView &cv, unsigned long long seq, int nv, double *out) {
+    int slot = (int)(seq & 1ull);
+    for (int v = 0; v < nv; ++v) out[v] = 0.0;
+    for (int q = 0; q < cv.nranks; ++q) {
+        while (ld_acquire_sys(&cv.self->mflag[slot][q]) != seq) {
+        }
+        for (int v = 0; v < nv; ++v) out[v] += ld_volatile_f64(&cv.self->mbox[slot][q][v]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dirichlet data
+// ------------------------------------------------------------------------------------------------
+// examples/vector3D.jl:159-168: node with z == 0 -> q_d[3n] = 0, z == 1 -> q_d[3n] = -d (exact compares)
+__global__ void k_dirichlet_zplanes(int64_t nNodes_l, const double *__restrict__ coords, int nDof, int64_t ghost_cols,
+                                    int64_t nrows_l, double d, double *__restrict__ qd, uint8_t *__restrict__ fixed) {
+    int64_t ln = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ln >= nNodes_l) return;
+    double z = coords[3 * ln + 2];
+    bool btm = (z == 0.0), top = (z == 1.0) && !btm;
+    if (!(btm || top)) return;
+    int64_t c = ln * nDof + 2;
+    qd[c] = btm ? 0.0 : -d;
+    int64_t r = c - ghost_cols;
+    if (r >= 0 && r < nrows_l) fixed[r] = 1;
+}
+
+void dirichlet_zplanes(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, double d) {
+    REQUIRE(K->ndim == 3 && K->nDof == 3, SMFEM_ERR_UNSUPPORTED, "setboundaryCond is 3-D / nDof=3 only (indexes coord[3], 3*nNode)");
+    solver_alloc(ctx, K);
+    CUDA_CHECK(cudaMemsetAsync(K->qd, 0, sizeof(double) * K->ncols_l, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(K->fixed, 0, K->nrows_l, ctx->stream));
+    // NB the reference writes q_d[3*nNode] regardless of ID (examples/vector3D.jl:162,165)
+    // ghost planes outside the domain carry z = 0 coordinates only when k0 == 0 / k1 == n1 planes are absent:
+    // they are excluded by restricting the launch to in-domain local planes.
+    int64_t first = 0, count = mesh->nNodes_l;
+    if (mesh->structured) {
+        const Lattice &L = mesh->lat;
+        int lo = L.k0 - 1 < 0 ? 0 : L.k0 - 1, hi = L.k1 + 1 > L.n1 ? L.n1 : L.k1 + 1;
+        first = (int64_t)(lo - (L.k0 - 1)) * L.plane();
+        count = (int64_t)(hi - lo) * L.plane();
+    }
+    LAUNCH(ctx, k_dirichlet_zplanes, (unsigned)((count + 255) / 256), 256, 0, count, mesh->coords + 3 * first, K->nDof,
+           K->ghost_cols - first * K->nDof, K->nrows_l, d, K->qd + first * K->nDof, K->fixed);
+    K->has_bc = true;
+}
+
+__global__ void k_dirichlet_list(int64_t n, const int64_t *__restrict__ dofs, const double *__restrict__ vals,
+                                 int64_t col_off_g, int64_t ncols_l, int64_t ghost_cols, int64_t nrows_l,
+                                 double *__restrict__ qd, uint8_t *__restrict__ fixed) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int64_t c = dofs[t] - 1 - col_off_g;
+    if (c < 0 || c >= ncols_l) return;
+    qd[c] = vals[t];
+    int64_t r = c - ghost_cols;
+    if (r >= 0 && r < nrows_l) fixed[r] = 1;
+}
+
+void dirichlet_list(smfem_ctx *ctx, smfem_matrix *K, const int64_t *dofs, const double *vals, int64_t n) {
+    solver_alloc(ctx, K);
+    CUDA_CHECK(cudaMemsetAsync(K->qd, 0, sizeof(double) * K->ncols_l, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(K->fixed, 0, K->nrows_l, ctx->stream));
+    if (n > 0) {
+        for (int64_t i = 0; i < n; ++i)
+            REQUIRE(dofs[i] >= 1 && dofs[i] <= K->m_g, SMFEM_ERR_INVALID, "set_dirichlet: dof id out of range");
+        int64_t *d_dofs = dev_alloc<int64_t>(n);
+        double *d_vals = dev_alloc<double>(n);
+        CUDA_CHECK(cudaMemcpyAsync(d_dofs, dofs, 8 * n, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(d_vals, vals, 8 * n, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(ctx, k_dirichlet_list, (unsigned)((n + 255) / 256), 256, 0, n, d_dofs, d_vals, K->row0 - K->ghost_cols,
+               K->ncols_l, K->ghost_cols, K->nrows_l, K->qd, K->fixed);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        dev_free(d_dofs);
+        dev_free(d_vals);
+    }
+    K->has_bc = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: CSR SpMV.
+// Variant 0 ("w3"): one warp streams the contiguous nonzeros of 3 consecutive rows (the three
+// dofs of a node on the hex lattice: 3 x 81 = 243 values -> 95 % lane use instead of 81/96), with
+// L1-bypassing streaming loads for val/colind and cached gathers of x.  Variant 1: warp per row.
+// MODE bit 0: Dirichlet row mask; bit 1: fused dot(x_row, y) partial; bit 2: wait for halo flags.
+// ------------------------------------------------------------------------------------------------
+struct SpmvArgs {
+    int64_t nrows, ghost_cols;
+    const int64_t *rowptr;
+    const int32_t *colind;
+    const double *val;
+    const double *x;  // ncols_l
+    double *y;        // nrows
+    const uint8_t *fixed;
+    double *partials;
+    PcgScalars *scal;
+    CommView cv;
+    int64_t rot;  // warp rotation so that boundary-plane rows run last
+};
+
+template <int RPW, int MODE>
+__global__ void __launch_bounds__(256) k_spmv(SpmvArgs A) {
+    constexpr bool MASK = MODE & 1, DOT = MODE & 2, HALO = MODE & 4;
+    __shared__ double s_red[8];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (A.nrows + RPW - 1) / RPW;
+    int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    double dot = 0.0;
+    if (wid < nwarps) {
+        if (HALO) wid = (wid + A.rot) % nwarps;
+        const int64_t r0 = wid * RPW;
+        const int nr = (int)((A.nrows - r0) < RPW ? (A.nrows - r0) : RPW);
+        if (HALO && A.cv.nranks > 1) {
+            // rows of the first / last owned plane read ghost planes written by the neighbours
+            const unsigned long long need = A.scal->it + 1;
+            bool lo = (A.cv.rank > 0) && (r0 < A.cv.plane_dofs);
+            bool hi = (A.cv.rank < A.cv.nranks - 1) && (r0 + nr > A.nrows - A.cv.plane_dofs);
+            if (lane == 0) {
+                if (lo)
+                    while (ld_acquire_sys(&A.cv.self->hflag[0]) < need) {
+                    }
+                if (hi)
+                    while (ld_acquire_sys(&A.cv.self->hflag[1]) < need) {
+                    }
+            }
+            __syncwarp();
+        }
+        int64_t b[RPW + 1];
+#pragma unroll
+        for (int i = 0; i <= RPW; ++i) b[i] = A.rowptr[r0 + (i < nr ? i : nr)];
+        double acc[RPW];
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) acc[i] = 0.0;
+#pragma unroll 4
+        for (int64_t p = b[0] + lane; p < b[RPW]; p += 32) {
+            double v = ld_stream_f64(A.val + p);
+            int c = ld_stream_s32(A.colind + p);
+            double prod = v * A.x[c];
+            if (RPW == 1) {
+                acc[0] += prod;
+            } else {
+#pragma unroll
+                for (int i = 0; i < RPW; ++i)
+                    if (p >= b[i] && p < b[i + 1]) acc[i] += prod;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) acc[i] = warp_sum(acc[i]);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < RPW; ++i)
+                if (i < nr) {
+                    double yv = acc[i];
+                    if (MASK && A.fixed[r0 + i]) yv = 0.0;
+                    A.y[r0 + i] = yv;
+                    if (DOT) dot += yv * A.x[A.ghost_cols + r0 + i];
+                }
+        }
+    }
+    if (DOT) {
+        double s = block_sum<256>(dot, s_red);
+        if (threadIdx.x == 0) {
+            A.partials[blockIdx.x] = s;
+            __threadfence();
+            unsigned t = atomicAdd(&A.scal->ticketB, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double v = 0.0;
+            for (int64_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += ld_volatile_f64(A.partials + i);
+            double tot = block_sum<256>(v, s_red);
+            if (threadIdx.x == 0) {
+                A.scal->ticketB = 0;
+                allreduce_publish(A.cv, 2ull * A.scal->it + 1ull, 1, &tot);
+            }
+        }
+    }
+}
+
+static SpmvArgs make_spmv_args(smfem_matrix *K, const double *x, double *y) {
+    SpmvArgs A;
+    A.nrows = K->nrows_l;
+    A.ghost_cols = K->ghost_cols;
+    A.rowptr = K->rowptr;
+    A.colind = K->colind;
+    A.val = K->val;
+    A.x = x;
+    A.y = y;
+    A.fixed = K->fixed;
+    A.partials = K->partials;
+    A.scal = K->scal;
+    A.cv = K->comm;
+    A.rot = 0;
+    return A;
+}
+
+template <int MODE>
+static void launch_spmv(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A, int variant) {
+    if (variant == 1) {
+        int64_t nw = A.nrows;
+        unsigned grid = (unsigned)((nw * 32 + 255) / 256);
+        LAUNCH(ctx, (k_spmv<1, MODE>), grid, 256, 0, A);
+    } else {
+        int64_t nw = (A.nrows + 2) / 3;
+        unsigned grid = (unsigned)((nw * 32 + 255) / 256);
+        LAUNCH(ctx, (k_spmv<3, MODE>), grid, 256, 0, A);
+    }
+}
+
+static int64_t spmv_grid(smfem_matrix *K, int variant) {
+    int64_t nw = variant == 1 ? K->nrows_l : (K->nrows_l + 2) / 3;
+    return (nw * 32 + 255) / 256;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: fused CG vector kernels (device-side scalars; no host round trip inside an iteration)
+//   A: beta = rz_k / rz_{k-1};  p = D^-1 r + beta p;  boundary planes of p are also stored into
+//      the neighbours' ghost planes (NVLink peer stores) and a flag is released     [halo push]
+//   B: Ap = K p (masked), partial p'Ap -> all-reduce publish                         [k_spmv]
+//   C: alpha = rz_k / p'Ap;  x += alpha p;  r -= alpha Ap;  partial r'D^-1 r, r'r -> publish
+// ------------------------------------------------------------------------------------------------
+constexpr int VEC_NT = 256;
+
+__global__ void __launch_bounds__(VEC_NT)
+k_pcg_update_p(int64_t n, int64_t ghost_cols, const double *__restrict__ r, const double *__restrict__ dinv,
+               double *__restrict__ p, PcgScalars *scal, CommView cv, unsigned long long it_start_unused) {
+    __shared__ double s_beta;
+    __shared__ bool s_last;
+    const unsigned long long it = scal->it;
+    if (threadIdx.x == 0) {
+        double v[2];
+        allreduce_fetch(cv, 2ull * it, 2, v);  // (rz_k, rr_k) published by the previous C / init
+        double rz_prev = scal->rzs[(it + 1ull) & 1ull];  // parity slots: [it-1]
+        double beta = (scal->spare != 0.0) ? 0.0 : v[0] / rz_prev;  // spare != 0 marks the first iteration
+        s_beta = beta;
+        if (blockIdx.x == 0) {
+            scal->rzs[it & 1ull] = v[0];
+            scal->rr = v[1];
+            scal->beta = beta;
+        }
+    }
+    __syncthreads();
+    const double beta = s_beta;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double *po = p + ghost_cols;
+    const bool push_lo = cv.nranks > 1 && cv.rank > 0, push_hi = cv.nranks > 1 && cv.rank < cv.nranks - 1;
+    double *dst_lo = push_lo ? cv.peer_p[cv.rank - 1] + cv.lo_dst_off : nullptr;  // their ghost_hi
+    double *dst_hi = push_hi ? cv.peer_p[cv.rank + 1] : nullptr;                   // their ghost_lo (offset 0)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double z = r[i] * dinv[i];
+        double pv = (beta == 0.0) ? z : z + beta * po[i];
+        po[i] = pv;
+        if (push_lo && i < cv.plane_dofs) dst_lo[i] = pv;
+        if (push_hi && i >= n - cv.plane_dofs) dst_hi[i - (n - cv.plane_dofs)] = pv;
+    }
+    if (cv.nranks > 1) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned t = atomicAdd(&scal->ticketA, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last && threadIdx.x == 0) {
+            scal->ticketA = 0;
+            __threadfence_system();
+            if (push_lo) st_release_sys(&cv.peer[cv.rank - 1]->hflag[1], it + 1);
+            if (push_hi) st_release_sys(&cv.peer[cv.rank + 1]->hflag[0], it + 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(VEC_NT)
+k_pcg_update_xr(int64_t n, int64_t ghost_cols, const double *__restrict__ p, const double *__restrict__ Ap,
+                const double *__restrict__ dinv, double *__restrict__ x, double *__restrict__ r,
+                double *__restrict__ partials, PcgScalars *scal, CommView cv) {
+    __shared__ double s_alpha;
+    __shared__ double s_red[VEC_NT / 32];
+    __shared__ bool s_last;
+    const unsigned long long it = scal->it;
+    if (threadIdx.x == 0) {
+        double pAp;
+        allreduce_fetch(cv, 2ull * it + 1ull, 1, &pAp);
+        double rz = scal->rzs[it & 1ull];
+        double alpha = 0.0;
+        if (pAp > 0.0) alpha = rz / pAp;
+        else if (rz != 0.0 && blockIdx.x == 0) scal->breakdown = 1;
+        s_alpha = alpha;
+        if (blockIdx.x == 0) {
+            scal->alpha = alpha;
+            scal->pAp = pAp;
+        }
+    }
+    __syncthreads();
+    const double alpha = s_alpha;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const double *po = p + ghost_cols;
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double xv = x[i] + alpha * po[i];
+        double rv = r[i] - alpha * Ap[i];
+        x[i] = xv;
+        r[i] = rv;
+        rz += rv * rv * dinv[i];
+        rr += rv * rv;
+    }
+    double s1 = block_sum<VEC_NT>(rz, s_red);
+    double s2 = block_sum<VEC_NT>(rr, s_red);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = s1;
+        partials[2 * blockIdx.x + 1] = s2;
+        __threadfence();
+        unsigned t = atomicAdd(&scal->ticketC, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double a = 0.0, b = 0.0;
+        for (int64_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+            a += ld_volatile_f64(partials + 2 * i);
+            b += ld_volatile_f64(partials + 2 * i + 1);
+        }
+        double t1 = block_sum<VEC_NT>(a, s_red);
+        double t2 = block_sum<VEC_NT>(b, s_red);
+        if (threadIdx.x == 0) {
+            scal->ticketC = 0;
+            scal->spare = 0.0;  // first-iteration marker cleared
+            double v[2] = {t1, t2};
+            allreduce_publish(cv, 2ull * it + 2ull, 2, v);
+            __threadfence();
+            scal->it = it + 1;
+        }
+    }
+}
+
+// r0 = free ? (extra - K q_d) : 0 ; x0 = 0 ; D^-1 ; publishes (r'D^-1 r, r'r) and opens a new solve
+__global__ void __launch_bounds__(VEC_NT)
+k_pcg_init(int64_t n, const double *__restrict__ Kqd, const double *__restrict__ extra, const double *__restrict__ diag,
+           const uint8_t *__restrict__ fixed, double *__restrict__ x, double *__restrict__ r, double *__restrict__ dinv,
+           double *__restrict__ partials, PcgScalars *scal, CommView cv) {
+    __shared__ double s_red[VEC_NT / 32];
+    __shared__ bool s_last;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        bool fx = fixed[i] != 0;
+        double rv = fx ? 0.0 : ((extra ? extra[i] : 0.0) - Kqd[i]);
+        double di = (fx || diag[i] == 0.0) ? 0.0 : 1.0 / diag[i];
+        x[i] = 0.0;
+        r[i] = rv;
+        dinv[i] = di;
+        rz += rv * rv * di;
+        rr += rv * rv;
+    }
+    double s1 = block_sum<VEC_NT>(rz, s_red);
+    double s2 = block_sum<VEC_NT>(rr, s_red);
+    if (threadIdx.x == 0) {
+        partials[2 * blockIdx.x] = s1;
+        partials[2 * blockIdx.x + 1] = s2;
+        __threadfence();
+        unsigned t = atomicAdd(&scal->ticketC, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double a = 0.0, b = 0.0;
+        for (int64_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+            a += ld_volatile_f64(partials + 2 * i);
+            b += ld_volatile_f64(partials + 2 * i + 1);
+        }
+        double t1 = block_sum<VEC_NT>(a, s_red);
+        double t2 = block_sum<VEC_NT>(b, s_red);
+        if (threadIdx.x == 0) {
+            const unsigned long long it = scal->it;
+            scal->ticketC = 0;
+            scal->spare = 1.0;  // marks "first iteration": beta = 0
+            scal->breakdown = 0;
+            double v[2] = {t1, t2};
+            allreduce_publish(cv, 2ull * it + 2ull, 2, v);
+            __threadfence();
+            scal->it = it + 1;
+        }
+    }
+}
+
+// fetch the current global (rz, rr) into scal (so the host can read the residual)
+__global__ void k_pcg_fetch(PcgScalars *scal, CommView cv, double *out2) {
+    double v[2];
+    allreduce_fetch(cv, 2ull * scal->it, 2, v);
+    out2[0] = v[0];
+    out2[1] = v[1];
+}
+
+__global__ void k_final_q(int64_t n, int64_t ghost_cols, const double *__restrict__ qd, const double *__restrict__ x,
+                          double *__restrict__ q) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) q[i] = qd[ghost_cols + i] + x[i];  // q = q_d + C q_f, examples/vector3D.jl:322
+}
+
+// halo push of an arbitrary vector with ghosts (bench_spmv)
+__global__ void k_halo_push(int64_t n, int64_t ghost_cols, const double *__restrict__ v, PcgScalars *scal, CommView cv,
+                            unsigned long long seq) {
+    __shared__ bool s_last;
+    const double *vo = v + ghost_cols;
+    const bool push_lo = cv.rank > 0, push_hi = cv.rank < cv.nranks - 1;
+    double *dst_lo = push_lo ? cv.peer_p[cv.rank - 1] + cv.lo_dst_off : nullptr;
+    double *dst_hi = push_hi ? cv.peer_p[cv.rank + 1] : nullptr;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cv.plane_dofs; i += stride) {
+        if (push_lo) dst_lo[i] = vo[i];
+        if (push_hi) dst_hi[i] = vo[n - cv.plane_dofs + i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(&scal->ticketA, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        scal->ticketA = 0;
+        __threadfence_system();
+        if (push_lo) st_release_sys(&cv.peer[cv.rank - 1]->hflag[1], seq);
+        if (push_hi) st_release_sys(&cv.peer[cv.rank + 1]->hflag[0], seq);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int vec_grid(smfem_ctx *ctx, int64_t n) {
+    int64_t g = (n + VEC_NT - 1) / VEC_NT;
+    int64_t cap = (int64_t)ctx->sms * 8;
+    return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+void solver_alloc(smfem_ctx *ctx, smfem_matrix *K) {
+    if (K->window) return;
+    K->window_bytes = sizeof(CommHeader) + sizeof(double) * (size_t)K->ncols_l;
+    CUDA_CHECK(cudaMalloc(&K->window, K->window_bytes));
+    CUDA_CHECK(cudaMemsetAsync(K->window, 0, K->window_bytes, ctx->stream));
+    K->p = (double *)((char *)K->window + sizeof(CommHeader));
+    K->x = dev_alloc<double>(K->nrows_l);
+    K->r = dev_alloc<double>(K->nrows_l);
+    K->Ap = dev_alloc<double>(K->nrows_l);
+    K->dinv = dev_alloc<double>(K->nrows_l);
+    K->qd = dev_alloc<double>(K->ncols_l);
+    K->fixed = dev_alloc<uint8_t>(K->nrows_l);
+    int64_t np = spmv_grid(K, 0);
+    int64_t np1 = spmv_grid(K, 1);
+    if (np1 > np) np = np1;
+    if (np < 2 * (int64_t)ctx->sms * 8) np = 2 * (int64_t)ctx->sms * 8;
+    K->partials = dev_alloc<double>(np + 16);
+    K->partials_n = np;
+    K->scal = dev_alloc<PcgScalars>(1);
+    CUDA_CHECK(cudaMemsetAsync(K->scal, 0, sizeof(PcgScalars), ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(K->qd, 0, sizeof(double) * K->ncols_l, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(K->fixed, 0, K->nrows_l, ctx->stream));
+    CUDA_CHECK(cudaMallocHost(&K->h_pinned, 64));
+    K->comm = CommView();
+    K->comm.rank = ctx->rank;
+    K->comm.nranks = ctx->nranks;
+    K->comm.self = (CommHeader *)K->window;
+    K->comm.plane_dofs = K->structured ? K->lat.plane() * K->nDof : 0;
+    if (ctx->nranks == 1) {
+        K->comm.peer[0] = K->comm.self;
+        K->comm.peer_p[0] = K->p;
+        K->comm_connected = true;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+void solver_free(smfem_matrix *K) {
+    for (int q = 0; q < SMFEM_MAX_RANKS; ++q)
+        if (K->peer_maps[q]) {
+            cudaIpcCloseMemHandle(K->peer_maps[q]);
+            K->peer_maps[q] = nullptr;
+        }
+    if (K->window) cudaFree(K->window);
+    K->window = nullptr;
+    K->p = nullptr;
+    dev_free(K->x);
+    dev_free(K->r);
+    dev_free(K->Ap);
+    dev_free(K->dinv);
+    dev_free(K->qd);
+    dev_free(K->fixed);
+    dev_free(K->partials);
+    dev_free(K->scal);
+    if (K->h_pinned) cudaFreeHost(K->h_pinned);
+    K->h_pinned = nullptr;
+}
+
+void comm_export(smfem_ctx *ctx, smfem_matrix *K, void *handle_out) {
+    solver_alloc(ctx, K);
+    static_assert(sizeof(cudaIpcMemHandle_t) == SMFEM_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_CHECK(cudaIpcGetMemHandle(&h, K->window));
+    std::memcpy(handle_out, &h, sizeof h);
+}
+
+void comm_connect(smfem_ctx *ctx, smfem_matrix *K, const void *handles) {
+    solver_alloc(ctx, K);
+    REQUIRE(K->structured, SMFEM_ERR_UNSUPPORTED, "multi-GPU needs a structured (slab-partitioned) mesh");
+    REQUIRE(ctx->nranks <= SMFEM_MAX_RANKS, SMFEM_ERR_UNSUPPORTED, "at most 8 ranks");
+    for (int q = 0; q < ctx->nranks; ++q) {
+        void *base = K->window;
+        if (q != ctx->rank) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, (const char *)handles + (size_t)q * SMFEM_IPC_HANDLE_BYTES, sizeof h);
+            CUDA_CHECK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            K->peer_maps[q] = base;
+        }
+        K->comm.peer[q] = (CommHeader *)base;
+        K->comm.peer_p[q] = (double *)((char *)base + sizeof(CommHeader));
+    }
+    if (ctx->rank > 0) {
+        int k0, k1;
+        slab_range(K->lat.n1, ctx->rank - 1, ctx->nranks, k0, k1);
+        K->comm.lo_dst_off = (int64_t)(k1 - k0 + 1) * K->comm.plane_dofs;
+    }
+    K->comm_connected = true;
+}
+
+void spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y) {
+    REQUIRE(ctx->nranks == 1, SMFEM_ERR_UNSUPPORTED, "spmv_host is single-GPU");
+    REQUIRE(K->values_ready, SMFEM_ERR_INVALID, "matrix has no values yet");
+    solver_alloc(ctx, K);
+    CUDA_CHECK(cudaMemsetAsync(K->p, 0, sizeof(double) * K->ncols_l, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(K->p + K->ghost_cols, x, sizeof(double) * K->nrows_l, cudaMemcpyHostToDevice, ctx->stream));
+    SpmvArgs A = make_spmv_args(K, K->p, K->Ap);
+    launch_spmv<0>(ctx, K, A, K->spmv_variant);
+    CUDA_CHECK(cudaMemcpyAsync(y, K->Ap, sizeof(double) * K->nrows_l, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+__global__ void k_fill_pattern(int64_t n, double *__restrict__ v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = 1.0 + 1e-3 * (double)(i % 1024);
+}
+
+void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *ms) {
+    REQUIRE(K->values_ready, SMFEM_ERR_INVALID, "matrix has no values yet");
+    REQUIRE(reps > 0, SMFEM_ERR_INVALID, "reps must be positive");
+    solver_alloc(ctx, K);
+    REQUIRE(K->comm_connected, SMFEM_ERR_INVALID, "multi-GPU: call smfem_comm_connect first");
+    LAUNCH(ctx, k_fill_pattern, (unsigned)((K->ncols_l + 255) / 256), 256, 0, K->ncols_l, K->p);
+    SpmvArgs A = make_spmv_args(K, K->p, K->Ap);
+    int64_t nw = variant == 1 ? K->nrows_l : (K->nrows_l + 2) / 3;
+    int64_t per_plane = variant == 1 ? K->comm.plane_dofs : (K->comm.plane_dofs + 2) / 3;
+    A.rot = (ctx->nranks > 1 && nw > 0) ? per_plane % nw : 0;
+    // sequence numbers for the halo flags continue the solver's counter
+    unsigned long long it0 = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&it0, &K->scal->it, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    auto one = [&](int j) {
+        if (ctx->nranks > 1) {
+            unsigned long long seq = it0 + 1;  // SpMV waits for hflag >= scal->it + 1 (it is not advanced here)
+            int g = (int)((K->comm.plane_dofs + 255) / 256);
+            if (g > ctx->sms * 4) g = ctx->sms * 4;
+            LAUNCH(ctx, k_halo_push, g, 256, 0, K->nrows_l, K->ghost_cols, (const double *)K->p, K->scal, K->comm, seq);
+            launch_spmv<4>(ctx, K, A, variant);
+        } else {
+            launch_spmv<0>(ctx, K, A, variant);
+        }
+        (void)j;
+    };
+    for (int j = 0; j < 3; ++j) one(j);
+    CUDA_CHECK(cudaEventRecord(ctx->ev2, ctx->stream));
+    for (int j = 0; j < reps; ++j) one(j);
+    CUDA_CHECK(cudaEventRecord(ctx->ev3, ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(ctx->ev3));
+    float t = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&t, ctx->ev2, ctx->ev3));
+    *ms = t / reps;
+}
+
+void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const double *rhs_extra, double *q_out,
+               int *iters, double *relres) {
+    REQUIRE(K->values_ready, SMFEM_ERR_INVALID, "matrix has no values yet");
+    solver_alloc(ctx, K);
+    REQUIRE(K->comm_connected, SMFEM_ERR_INVALID, "multi-GPU: call smfem_comm_connect first");
+    const int64_t n = K->nrows_l;
+    const int variant = K->spmv_variant;
+    double *extra = nullptr;
+    if (rhs_extra) {
+        extra = dev_alloc<double>(n);
+        CUDA_CHECK(cudaMemcpyAsync(extra, rhs_extra, 8 * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int vg = vec_grid(ctx, n);
+    CUDA_CHECK(cudaEventRecord(ctx->ev2, ctx->stream));
+    // K q_d (unmasked rows; q_d's ghost entries are filled locally, no exchange needed)
+    {
+        SpmvArgs A = make_spmv_args(K, K->qd, K->Ap);
+        launch_spmv<0>(ctx, K, A, variant);
+    }
+    LAUNCH(ctx, k_pcg_init, vg, VEC_NT, 0, n, (const double *)K->Ap, (const double *)extra, (const double *)K->diag,
+           (const uint8_t *)K->fixed, K->x, K->r, K->dinv, K->partials, K->scal, K->comm);
+    double *d_out2 = K->partials + K->partials_n;  // tail slots (see solver_alloc)
+    auto fetch = [&](double &rz, double &rr) {
+        LAUNCH(ctx, k_pcg_fetch, 1, 1, 0, K->scal, K->comm, d_out2);
+        CUDA_CHECK(cudaMemcpyAsync(K->h_pinned, d_out2, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        rz = K->h_pinned[0];
+        rr = K->h_pinned[1];
+    };
+    double rz, rr;
+    fetch(rz, rr);
+    const double bnorm2 = rr;
+    int it = 0;
+    double res2 = rr;
+    SpmvArgs A = make_spmv_args(K, K->p, K->Ap);
+    {
+        int64_t nw = variant == 1 ? n : (n + 2) / 3;
+        int64_t per_plane = variant == 1 ? K->comm.plane_dofs : (K->comm.plane_dofs + 2) / 3;
+        A.rot = (ctx->nranks > 1 && nw > 0) ? per_plane % nw : 0;
+    }
+    if (bnorm2 > 0.0) {
+        const int chunk = 25;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t gexec = nullptr;
+        // capture `chunk` iterations once; replay until converged
+        CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        for (int j = 0; j < chunk; ++j) {
+            LAUNCH(ctx, k_pcg_update_p, vg, VEC_NT, 0, n, K->ghost_cols, (const double *)K->r, (const double *)K->dinv, K->p,
+                   K->scal, K->comm, 0ull);
+            launch_spmv<7>(ctx, K, A, variant);
+            LAUNCH(ctx, k_pcg_update_xr, vg, VEC_NT, 0, n, K->ghost_cols, (const double *)K->p, (const double *)K->Ap,
+                   (const double *)K->dinv, K->x, K->r, K->partials, K->scal, K->comm);
+        }
+        CUDA_CHECK(cudaStreamEndCapture(ctx->stream, &graph));
+        ctx->launches -= 3 * chunk;  // captured, not launched; counted per replay below
+        CUDA_CHECK(cudaGraphInstantiate(&gexec, graph, 0));
+        const double tol2 = rtol * rtol * bnorm2;
+        while (it < maxit && res2 > tol2) {
+            CUDA_CHECK(cudaGraphLaunch(gexec, ctx->stream));
+            ctx->launches += 3 * chunk;
+            it += chunk;
+            fetch(rz, res2);
+            if (!(res2 == res2)) break;  // NaN guard
+        }
+        cudaGraphExecDestroy(gexec);
+        cudaGraphDestroy(graph);
+    }
+    unsigned brk = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&brk, &K->scal->breakdown, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (q_out) {
+        LAUNCH(ctx, k_final_q, (unsigned)((n + 255) / 256), 256, 0, n, K->ghost_cols, (const double *)K->qd,
+               (const double *)K->x, K->Ap);
+        CUDA_CHECK(cudaMemcpyAsync(q_out, K->Ap, 8 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_CHECK(cudaEventRecord(ctx->ev3, ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(ctx->ev3));
+    CUDA_CHECK(cudaEventElapsedTime(&K->last_ms, ctx->ev2, ctx->ev3));
+    K->last_iters = it;
+    if (extra) dev_free(extra);
+    if (iters) *iters = it;
+    if (relres) *relres = bnorm2 > 0 ? std::sqrt(res2 / bnorm2) : 0.0;
+    REQUIRE(brk == 0, SMFEM_ERR_SINGULAR, "PCG breakdown: p'Ap <= 0 (matrix not SPD on the free dofs; reference: SingularException)");
+}

@@ -1,0 +1,127 @@
+"""CPU-side checks of the boundary: the C-ABI library loads without a GPU, exports every symbol
+include/smearfem_b200.h declares, its host helpers reproduce the reference's own unit tests
+(test/runtests.jl:15-35) bit-for-bit, and device entry points fail loudly without a device."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import smearfem_b200 as sf
+from smearfem_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "smearfem_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(smfem_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/smearfem_b200.h but not exported"
+    # and the Python binding table covers them all
+    bound = set(_lib.SIGNATURES) | set(_lib.NON_STATUS)
+    assert set(names) == bound, set(names) ^ bound
+    assert L.smfem_abi_version() == 1
+
+
+def test_no_oracle_import_in_product():
+    """The product must never import, link or execute the test oracle."""
+    pkg = os.path.join(ROOT, "smearfem.jl_b200")
+    bad = re.compile(r"import\s+oracle|from\s+oracle|fem_oracle|c_oracle|oracle/|libfem_oracle")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".jl", ".cpp", ".h")) or f == "Makefile":
+                assert not bad.search(open(os.path.join(dp, f)).read()), os.path.join(dp, f)
+    assert not bad.search(open(os.path.join(ROOT, "smearfem_b200.py")).read())
+
+
+# ---- the reference's unit tests through the ABI (host helpers; no GPU needed) ---------------------
+def test_basis_1d():  # test/runtests.jl:15-16
+    assert sf.basis_function(-1)[0].tolist() == [1.0, 0.0]
+    assert sf.basis_function(1)[0].tolist() == [0.0, 1.0]
+    assert sf.basis_function(0.3)[1].shape == (1, 2)  # src/fem.jl:75 quirk
+
+
+@pytest.mark.parametrize("pt,idx", [((-1, -1), 0), ((1, -1), 1), ((1, 1), 2), ((-1, 1), 3)])
+def test_basis_2d(pt, idx):  # test/runtests.jl:18-21
+    e = [0.0] * 4
+    e[idx] = 1.0
+    assert sf.basis_function(*pt)[0].tolist() == e
+
+
+@pytest.mark.parametrize("pt,idx", [((-1, -1, -1), 0), ((1, -1, -1), 1), ((1, 1, -1), 2), ((-1, 1, -1), 3),
+                                    ((-1, -1, 1), 4), ((1, -1, 1), 5), ((1, 1, 1), 6), ((-1, 1, 1), 7)])
+def test_basis_3d(pt, idx):  # test/runtests.jl:23-30
+    e = [0.0] * 8
+    e[idx] = 1.0
+    assert sf.basis_function(*pt)[0].tolist() == e
+
+
+def test_gauss():  # test/runtests.jl:34-35
+    xi, w = sf.gaussian_quadrature(-1, 1, 2)
+    assert xi.tolist() == [-1 / math.sqrt(3), 1 / math.sqrt(3)] and w.tolist() == [1.0, 1.0]
+    xi, w = sf.gaussian_quadrature(-1, 1, 3)
+    assert xi.tolist() == [-math.sqrt(3 / 5), 0.0, math.sqrt(3 / 5)] and w.tolist() == [5 / 9, 8 / 9, 5 / 9]
+    with pytest.raises(sf.SmearFEMError):
+        sf.gaussian_quadrature(-1, 1, 4)
+
+
+def test_host_helpers_match_oracle_bitwise():
+    from oracle import fem_oracle as o
+
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        x, e, z = rng.uniform(-1, 1, 3)
+        for args in [(x,), (x, e), (x, e, z)]:
+            N, dN = sf.basis_function(*args)
+            No, dNo = o.basis_function(*args)
+            assert np.array_equal(N, No) and np.array_equal(dN, dNo)
+        N, dN = sf.basis_function(x, e, None, "Q2")
+        No, dNo = o.basis_function(x, e, None, "Q2")
+        assert np.array_equal(N, No) and np.array_equal(dN, dNo)
+    a, b = rng.uniform(-2, 2, 2)
+    for n in (2, 3):
+        assert all(np.array_equal(u, v) for u, v in zip(sf.gaussian_quadrature(a, b, n), o.gaussian_quadrature(a, b, n)))
+    with pytest.raises(sf.SmearFEMError):
+        sf.basis_function(0.1, 0.2, 0.3, "Q2")  # reference defines Q2 in 2-D only
+    with pytest.raises(sf.SmearFEMError):
+        sf.basis_function(0.1, 0.2, 0.3, "Q7")
+
+
+def test_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(sf.SmearFEMError) as ei:
+        sf.Context(device=0, rank=0, nranks=1)
+    assert ei.value.code == _lib.ERR_CUDA and "no CPU fallback" in str(ei.value)
+
+
+def test_setboundarycond_host_prep_matches_oracle():
+    from oracle import fem_oracle as o
+
+    NL, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, 3, 3)
+    q_d, Cc = sf.setboundaryCond(NL, 3, 3, "Q1", 0.25, 3)
+    q_o, free_o = o.setboundaryCond(NL, 3, 3, "Q1", 0.25, 3)
+    assert np.array_equal(q_d, q_o) and np.array_equal(Cc.free, free_o) and Cc.shape == (192, 160)
+
+
+def test_meshgrid_2d_host_matches_oracle():
+    from oracle import fem_oracle as o
+
+    for ne in (1, 2, 5):
+        a = sf.meshgrid(0, 1, 0, 1, 0, 1, ne, 2)
+        b = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 2)
+        for u, v in zip(a[:5], b[:5]):
+            assert np.array_equal(u, v)
+        assert a[5][0] == b[5][0]

@@ -1,0 +1,234 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle.  Run on the GPU box: -m gpu.
+
+Bars (BASELINE.json north_star): sparsity pattern bit-exact; ||K-K_ref||_F / ||K_ref||_F <= 1e-10;
+||u-u_ref||_2 / ||u_ref||_2 <= 1e-10 (fp64).  Mesh generation / inflate are bit-exact."""
+import numpy as np
+import pytest
+
+import smearfem_b200 as sf
+from oracle import fem_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def _load_csc(g, p):
+    return o.JuliaCSC(int(g[p + "_m"]), int(g[p + "_n"]), g[p + "_colptr"], g[p + "_rowval"], g[p + "_nzval"])
+
+
+def assert_csc_parity(K, Ko, tol=TOL):
+    colptr, rowval, nzval = K.to_csc()
+    assert K.shape == (Ko.m, Ko.n) and K.nnz == Ko.nnz
+    assert np.array_equal(colptr, Ko.colptr), "colptr differs (pattern must be bit-exact)"
+    assert np.array_equal(rowval, Ko.rowval), "rowval differs (pattern must be bit-exact)"
+    assert rel(nzval, Ko.nzval) <= tol
+    # explicit zeros are structural, as in Julia's sparse()
+    assert (nzval == 0.0).sum() == (Ko.nzval == 0.0).sum() or rel(nzval, Ko.nzval) <= tol
+
+
+# ---- mesh --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ne", [1, 2, 7, 20])
+def test_meshgrid_and_inflate_bit_exact(ne):
+    NL, IEN, ID, top, btm, borders = sf.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    NLo, IENo, IDo, topo, btmo, borderso = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    assert np.array_equal(NL, NLo) and np.array_equal(IEN, IENo) and np.array_equal(ID, IDo)
+    assert np.array_equal(top, topo) and np.array_equal(btm, btmo)
+    assert all(list(a) == list(b) for a, b in zip(borders, borderso))
+    out = sf.inflate_sphere(NL, 0, 1, 0, 1)
+    assert out is NL  # in place, like the reference
+    assert np.array_equal(NL, o.inflate_sphere(NLo, 0, 1, 0, 1))
+
+
+def test_meshgrid_general_box_bit_exact():
+    NL, *_ = sf.meshgrid(-0.3, 1.7, 0.25, 0.5, 2.0, 5.0, 6, 3)
+    NLo, *_ = o.meshgrid(-0.3, 1.7, 0.25, 0.5, 2.0, 5.0, 6, 3)
+    assert np.array_equal(NL, NLo)
+
+
+# ---- assembly: structured fast path (device mesh) ---------------------------------------------------
+@pytest.mark.parametrize("ne,inflate", [(1, False), (2, False), (2, True), (5, True), (8, True), (20, True)])
+def test_hex_elasticity_structured(ne, inflate):
+    ctx = sf.context()
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3)
+    NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    if inflate:
+        mesh.inflate_sphere(0, 1, 0, 1)
+        o.inflate_sphere(NL, 0, 1, 0, 1)
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
+    Ko = o.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4)
+    assert K.nnz == 9 * (3 * (ne + 1) - 2) ** 3
+    assert_csc_parity(K, Ko)
+    assert rel(K.diag(), Ko.to_scipy().diagonal()) <= TOL
+    K.free()
+    mesh.free()
+
+
+@pytest.mark.parametrize("name", ["hex_ne2_cube", "hex_ne2_inflated", "hex_ne4_cube", "hex_ne4_inflated"])
+def test_golden_fixtures_through_reference_api(golden_dir, name):
+    """Reads like the reference's own (missing) integration test: host arrays in, CSC out."""
+    g = np.load(f"{golden_dir}/{name}.npz")
+    ne = int(g["ne"])
+    K = sf.assemble_system(ne, g["NodeList"], g["IEN"], 3, "Q1", 3, g["ID"], 40, 0.4)
+    assert K.mesh.info()["structured"]
+    assert_csc_parity(K, _load_csc(g, "K"))
+    b = sf.apply_boundary_conditions(ne, g["NodeList"], g["IEN"], g["IEN_top"], g["IEN_btm"], 3, "Q1", g["ID"])
+    bo = _load_csc(g, "b")
+    colptr, rowval, nzval = b.to_csc()
+    assert np.array_equal(colptr, bo.colptr) and np.array_equal(rowval, bo.rowval)
+    assert rel(nzval, bo.nzval) <= TOL
+    K_bar = K + 100 * b  # examples/vector3D.jl:308
+    q_d, C = sf.setboundaryCond(g["NodeList"], ne, 3, "Q1", 0.001, 3)
+    q = sf.solve(K_bar, q_d, C, rtol=1e-13)
+    assert rel(q, g["q"]) <= TOL
+
+
+# ---- assembly: general (unstructured) path ----------------------------------------------------------
+def test_general_path_permuted_ids_and_elements():
+    """A lattice mesh with shuffled element order and a permuted ID map must take the general path
+    and still reproduce Julia's pattern for THAT numbering."""
+    ne = 4
+    NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.inflate_sphere(NL, 0, 1, 0, 1)
+    rng = np.random.default_rng(7)
+    IENp = IEN[rng.permutation(IEN.shape[0])]
+    IDp = (rng.permutation(ID.size) + 1).reshape(ID.shape).astype(np.int64)
+    K = sf.assemble_system(ne, NL, IENp, 3, "Q1", 3, IDp, 40, 0.4)
+    assert not K.mesh.info()["structured"]
+    Ko = o.assemble_system(ne, NL, IENp, 3, "Q1", 3, IDp, 40, 0.4)
+    assert_csc_parity(K, Ko)
+
+
+@pytest.mark.parametrize("ne", [2, 4, 9])
+def test_plane_stress_quad4(ne, golden_dir):  # config C1 geometry, src/fem.jl:210-217
+    NL, IEN, ID, *_ = sf.meshgrid(0, 1, 0, 1, 0, 1, ne, 2)
+    K = sf.assemble_system(ne, NL, IEN, 2, "Q1", 2, ID, 40, 0.4)
+    Ko = o.assemble_system_literal(ne, NL, IEN, 2, "Q1", 2, ID, 40, 0.4)
+    assert K.nnz == 4 * (3 * (ne + 1) - 2) ** 2
+    assert_csc_parity(K, Ko)
+    if ne in (2, 4):
+        assert_csc_parity(K, _load_csc(np.load(f"{golden_dir}/quad_ne{ne}.npz"), "K"))
+
+
+@pytest.mark.parametrize("ndim,ne", [(2, 5), (3, 2), (3, 6)])
+def test_scalar_laplace(ndim, ne):  # nDof = 1: raw node ids, no ID (src/fem.jl:199-208)
+    NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, ndim)
+    if ndim == 3:
+        o.inflate_sphere(NL, 0, 1, 0, 1)
+    K = sf.assemble_system(ne, NL, IEN, ndim)  # defaults: "Q1", nDof=1, ID=nothing, as upstream
+    Ko = o.assemble_system(ne, NL, IEN, ndim, "Q1", 1)
+    assert_csc_parity(K, Ko)
+    if ndim == 3:
+        assert K.nnz == (3 * (ne + 1) - 2) ** 3
+    # constants are in the null space of the Laplacian
+    y = K.spmv(np.ones(K.shape[0]))
+    assert np.abs(y).max() <= 1e-12 * np.abs(Ko.nzval).max()
+
+
+def test_jittered_mesh_no_uniform_shortcut():
+    ne = 10
+    NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.jitter_nodes(NL, ne, seed=1234)
+    K = sf.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4)
+    assert K.mesh.info()["structured"]
+    assert_csc_parity(K, o.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4))
+
+
+# ---- surface term, Dirichlet, solve -------------------------------------------------------------------
+@pytest.mark.parametrize("ne", [3, 8])
+def test_example_pipeline_device_resident(ne):
+    """examples/vector3D.jl:283-322 with everything on the device."""
+    ctx = sf.context()
+    r = o.example_problem(ne)
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
+    K.add_surface_mass(100.0, keep_b=True)
+    cp, rv, bz = K.to_csc(which=1)
+    assert abs(bz.sum() - r["b"].nzval.sum()) <= 1e-12 * abs(bz.sum())
+    _, _, kb = K.to_csc()
+    assert rel(kb, r["K_bar"].nzval) <= TOL
+    K.set_dirichlet_zplanes(0.001)
+    q, it, relres = K.pcg_solve(rtol=1e-13, maxit=10000)
+    assert relres <= 1e-13 and it < 10000
+    assert rel(q, r["q"]) <= TOL
+    # q is linear in d: second load step of examples/vector3D.jl:310
+    K.set_dirichlet_zplanes(0.011)
+    q2, *_ = K.pcg_solve(rtol=1e-13, maxit=10000)
+    assert rel(q2, 11 * r["q"]) <= TOL
+
+
+def test_config_c2_ne20_against_golden(golden_dir):
+    """BASELINE config 2: examples/vector3D.jl with ne = 20, u vs the oracle's sparse direct solve."""
+    g = np.load(f"{golden_dir}/example_summaries.npz")
+    ne = 20
+    ctx = sf.context()
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
+    _, _, nz = K.to_csc()
+    s = g["ne20"]
+    assert K.nnz == int(s[0]) == 2042829
+    assert abs(np.linalg.norm(nz) - s[1]) <= 1e-11 * s[1] and abs(K.diag().sum() - s[2]) <= 1e-11 * s[2]
+    K.add_surface_mass(100.0).set_dirichlet_zplanes(0.001)
+    q, it, relres = K.pcg_solve(rtol=1e-13, maxit=20000)
+    assert rel(q, g["q_ne20"]) <= TOL
+    assert abs(np.abs(q[0::3]).max() - s[7]) <= 1e-9 * s[7]
+
+
+def test_spmv_variants_and_host_spmv():
+    ne = 9
+    NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.inflate_sphere(NL, 0, 1, 0, 1)
+    K = sf.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4)
+    A = o.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4).to_scipy()
+    x = np.random.default_rng(3).standard_normal(K.shape[0])
+    for v in (0, 1):
+        K.set_spmv_variant(v)
+        assert rel(K.spmv(x), A @ x) <= 1e-13
+
+
+def test_manufactured_solution_general_dirichlet():
+    """u* ~ N(0,1) (seed 4321), rhs = K̄u*; Dirichlet on an arbitrary dof set."""
+    ne = 12
+    ctx = sf.context()
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4).add_surface_mass(100.0)
+    n = K.shape[0]
+    rng = np.random.default_rng(4321)
+    u = rng.standard_normal(n)
+    fixed = np.sort(rng.choice(n, size=n // 10, replace=False)) + 1
+    K.set_dirichlet(fixed, u[fixed - 1])
+    # rhs on free rows: (K̄ u*)_f ; the solver subtracts K̄ q_d itself
+    K.set_spmv_variant(0)
+    rhs = K.spmv(u)
+    q, it, relres = K.pcg_solve(rtol=1e-13, maxit=20000, rhs_extra=rhs)
+    assert rel(q, u) <= 1e-9
+
+
+# ---- error behaviour at the boundary -----------------------------------------------------------------
+def test_error_codes():
+    NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, 3, 3)
+    with pytest.raises(sf.SmearFEMError):  # ne^ndim != number of elements
+        sf.assemble_system(4, NL, IEN, 3, "Q1", 3, ID, 40, 0.4)
+    with pytest.raises(sf.SmearFEMError):  # ID missing for nDof > 1
+        sf.assemble_system(3, NL, IEN, 3, "Q1", 3, None, 40, 0.4)
+    bad = IEN.copy()
+    bad[0, 0] = NL.shape[1] + 5
+    with pytest.raises(sf.SmearFEMError):  # BoundsError
+        sf.assemble_system(3, NL, bad, 3, "Q1", 3, ID, 40, 0.4)
+    IDbad = ID.copy()
+    IDbad[0, 0] = IDbad[1, 0]
+    with pytest.raises(sf.SmearFEMError):  # not a bijection
+        sf.assemble_system(3, NL, IEN, 3, "Q1", 3, IDbad, 40, 0.4)
+    with pytest.raises(sf.SmearFEMError):
+        sf.assemble_system(3, NL, IEN, 3, "Q2", 3, ID, 40, 0.4)
+    with pytest.raises(sf.SmearFEMError):  # 1-D branch is not executable upstream either
+        sf.assemble_system(3, NL[:1], IEN[:, :2], 1)
+    # unconstrained K is singular: PCG on rhs in the null-space complement still runs, but a zero matrix breaks down
+    K = sf.assemble_system(3, NL, IEN, 3, "Q1", 3, ID, 0.0, 0.4)
+    K.set_dirichlet(np.array([1]), np.array([1.0]))
+    q, it, relres = K.pcg_solve(rtol=1e-10, maxit=50)
+    assert np.all(np.isfinite(q))
