@@ -148,22 +148,31 @@ __global__ void k_struct_rowptr(Lattice L, int nDof, int64_t nrows_l, int64_t *_
     rowptr[r] = (int64_t)nDof * nDof * pairs_before(L.n1, i, j, k) + (int64_t)c * nDof * cnt - base;
 }
 
-// one warp per owned node: writes the nDof rows of the node (contiguous in colind), coalesced
-__global__ void k_struct_colind(Lattice L, int nDof, int64_t nOwnedNodes, const int64_t *__restrict__ rowptr,
-                                int32_t *__restrict__ colind) {
+// one warp per owned node: lanes 0..26 compute the first column of one neighbour node each (the only
+// div/mod work), park it in shared memory, then the warp streams the node's nDof rows (contiguous in
+// colind) with coalesced stores.
+template <int NDOF>
+__global__ void __launch_bounds__(256) k_struct_colind(Lattice L, int64_t nOwnedNodes, const int64_t *__restrict__ rowptr,
+                                                       int32_t *__restrict__ colind) {
+    __shared__ int32_t s_nb[8][28];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int64_t node = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
     if (node >= nOwnedNodes) return;
     int i = (int)(node % L.n1), j = (int)((node / L.n1) % L.n1), k = (int)(node / L.plane()) + L.k0;
     int cx = cnt1(i, L.n1), cy = cnt1(j, L.n1), cz = cnt1(k, L.n1);
     int i0 = i - (i > 0), j0 = j - (j > 0), k0 = k - (k > 0);
-    int T = nDof * cx * cy * cz;
-    int64_t base = rowptr[node * nDof];
-    for (int t = lane; t < nDof * T; t += 32) {
-        int s = t % T;
-        int q = s / nDof, comp = s - q * nDof;
-        int ai = q % cx, aj = (q / cx) % cy, ak = q / (cx * cy);
-        colind[base + t] = (int32_t)(L.lnode(i0 + ai, j0 + aj, k0 + ak) * nDof + comp);
+    const int cnt = cx * cy * cz;
+    if (lane < cnt) {
+        int ai = lane % cx, aj = (lane / cx) % cy, ak = lane / (cx * cy);
+        s_nb[w][lane] = (int32_t)(L.lnode(i0 + ai, j0 + aj, k0 + ak) * NDOF);
+    }
+    __syncwarp();
+    const int T = NDOF * cnt;
+    int32_t *dst = colind + rowptr[node * NDOF];
+    for (int t = lane; t < NDOF * T; t += 32) {
+        int s = t - ((t >= T) ? T : 0) - ((t >= 2 * T) ? T : 0);  // position inside its row (NDOF <= 3)
+        int q = s / NDOF;
+        dst[t] = s_nb[w][q] + (s - q * NDOF);
     }
 }
 
@@ -193,7 +202,10 @@ void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K)
         K->colind = dev_alloc<int32_t>(K->nnz_l);
     }
     int64_t nOwned = (int64_t)L.nown() * L.plane();
-    LAUNCH(ctx, k_struct_colind, (unsigned)((nOwned * 32 + 255) / 256), 256, 0, L, nDof, nOwned, K->rowptr, K->colind);
+    if (nDof == 3)
+        LAUNCH(ctx, (k_struct_colind<3>), (unsigned)((nOwned * 32 + 255) / 256), 256, 0, L, nOwned, (const int64_t *)K->rowptr, K->colind);
+    else
+        LAUNCH(ctx, (k_struct_colind<1>), (unsigned)((nOwned * 32 + 255) / 256), 256, 0, L, nOwned, (const int64_t *)K->rowptr, K->colind);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -584,7 +596,9 @@ void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Y
     }
     if (!K->val) K->val = dev_alloc<double>(K->nnz_l);
     if (mesh->structured && ndim == 3 && nDof == 3 && values_tile_enabled()) {
-        values_assemble_tile(ctx, mesh, K, mat);  // writes every entry: no memset needed
+        values_assemble_tile(ctx, mesh, K, mat);  // writes every entry and the diagonal: no memset, no extract_diag
+        K->values_ready = true;
+        return;
     } else {
         CUDA_CHECK(cudaMemsetAsync(K->val, 0, sizeof(double) * K->nnz_l, ctx->stream));
         Conn C = make_conn(mesh);

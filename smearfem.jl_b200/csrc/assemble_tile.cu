@@ -1,5 +1,20 @@
-// Structured-hex value kernel (tiled gather).  Placeholder until the tile kernel lands: the
-// general atomic kernel in assemble.cu is used for every mesh.
+// K1 + K3 for the structured hex lattice, nDof = 3: tiled, atomic-free, deterministic gather assembly.
+//   replaces src/fem.jl:179-249 (element loop + COO scatter) and the value side of sparse(E,J,V) (:253)
+//
+// A CTA owns a tile of TX x TY node columns and marches up the z planes of its chunk.
+//   phase 1  (thread = element x Gauss point of the (TX+1)x(TY+1) element footprint of one layer):
+//            Jacobian, inverse, |det| and the physical gradients of the 8 shape functions, scaled by
+//            sqrt(w):  g_b = sqrt(w_gp |det J|) * dN_b J^-1   -> shared memory ring of two layers.
+//            Every element layer is computed once per tile column (redundancy (TX+1)(TY+1)/(TX TY)).
+//   phase 2  (thread = node x element slot s in 0..7): for the element at offset -s of the node (local
+//            node a(s)) accumulate the 8 blocks  G_ab = sum_gp g_a g_b'  (72 fp64 accumulators, 9 FMA
+//            per 6 shared loads... see DESIGN.md) in registers.
+//   combine  8 conflict-free rounds (round b: the 8 slot-threads of a node hit 8 distinct neighbour
+//            blocks) add the G blocks into a per-node staging area [27 neighbours][3x3] in shared memory.
+//   output   lanes 0..26 of the warp own one neighbour each: apply the material once,
+//            K_ab = lam G + mu G' + mu tr(G) I   (D(1,1) on the diagonal, src/fem.jl:230), and store the
+//            node's three CSR rows; every stored entry of K is written exactly once (no memset, no
+//            atomics, fold order fixed -> bit-reproducible).
 #include <cstdlib>
 
 #include "smfem_internal.cuh"
@@ -8,8 +23,240 @@ struct Material {
     double d11, lam, mu;
 };
 
-bool values_tile_enabled() { return false; }
+namespace {
 
-void values_assemble_tile(smfem_ctx *, smfem_mesh *, smfem_matrix *, Material) {
-    throw SmfemError(SMFEM_ERR_UNSUPPORTED, "tile kernel not built");
+constexpr int TX = 8, TY = 4, NTH = 256;
+constexpr int EX = TX + 1, EY = TY + 1, NEL = EX * EY;  // 45 footprint elements per layer
+constexpr int LAYER = 8 * 8 * 3 * NEL + 3;               // doubles per layer in the ring; +3: the two layers a half-warp
+                                                         // reads (sz = 0/1) land in disjoint banks (ncu: 2x excess wavefronts without)
+constexpr int STAGE_NODE = 27 * 9;                       // doubles per node in the staging area
+constexpr size_t SMEM_BYTES = sizeof(double) * (2 * LAYER + TX * TY * STAGE_NODE + 8 * 8 * 3 + 8);
+
+struct TileArgs {
+    Lattice L;
+    const double *coords;
+    const int64_t *rowptr;
+    double *val;
+    double *diag;
+    Material mat;
+    int tiles_x, tiles_y, nchunks, chunk;
+    double dN[8][8][3];  // reference gradients at the 8 Gauss points (src/fem.jl:63, :174-176)
+    double w[8];
+};
+
+__device__ __forceinline__ double inv3(const double *J, double *inv) {
+    double c00 = J[4] * J[8] - J[5] * J[7], c01 = J[5] * J[6] - J[3] * J[8], c02 = J[3] * J[7] - J[4] * J[6];
+    double d = J[0] * c00 + J[1] * c01 + J[2] * c02;
+    double id = 1.0 / d;
+    inv[0] = c00 * id;
+    inv[1] = (J[2] * J[7] - J[1] * J[8]) * id;
+    inv[2] = (J[1] * J[5] - J[2] * J[4]) * id;
+    inv[3] = c01 * id;
+    inv[4] = (J[0] * J[8] - J[2] * J[6]) * id;
+    inv[5] = (J[2] * J[3] - J[0] * J[5]) * id;
+    inv[6] = c02 * id;
+    inv[7] = (J[1] * J[6] - J[0] * J[7]) * id;
+    inv[8] = (J[0] * J[4] - J[1] * J[3]) * id;
+    return d;
+}
+
+// element layer `layer` of the footprint -> ring slot
+__device__ __forceinline__ void phase1(const TileArgs &A, const double *s_dN, const double *s_w, double *S, int layer, int X0,
+                                       int Y0) {
+    const Lattice &L = A.L;
+    double *dst = S + (layer & 1) * LAYER;
+    for (int q = threadIdx.x; q < 8 * NEL; q += NTH) {
+        const int gp = q / NEL, e = q - gp * NEL;
+        const int fy = e / EX, fx = e - fy * EX;
+        const int ex = X0 - 1 + fx, ey = Y0 - 1 + fy;
+        if (ex < 0 || ey < 0 || ex >= L.ne || ey >= L.ne) continue;
+        double X[8][3];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int ox = ((b & 3) == 1 || (b & 3) == 2), oy = ((b & 3) >= 2), oz = (b >> 2);
+            const double *p = A.coords + 3 * L.lnode(ex + ox, ey + oy, layer + oz);
+            X[b][0] = p[0];
+            X[b][1] = p[1];
+            X[b][2] = p[2];
+        }
+        const double *dN = s_dN + gp * 24;
+        double J[9], inv[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) s += X[b][r] * dN[b * 3 + c];  // Jac = coords*dN, src/fem.jl:192
+                J[r * 3 + c] = s;
+            }
+        const double det = inv3(J, inv);
+        const double sw = sqrt(s_w[gp] * fabs(det));  // w = wp*|det J|, src/fem.jl:194
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double s = dN[b * 3] * inv[c] + dN[b * 3 + 1] * inv[3 + c] + dN[b * 3 + 2] * inv[6 + c];  // dNdX, :196
+                dst[((gp * 8 + b) * 3 + c) * NEL + e] = s * sw;
+            }
+    }
+}
+
+__global__ void __launch_bounds__(NTH, 1) k_values_tile(const __grid_constant__ TileArgs A) {
+    extern __shared__ double smem[];
+    double *S = smem;                             // [2][gp][b][c][e]
+    double *stage = smem + 2 * LAYER;             // [node][27][9]
+    double *s_dN = stage + TX * TY * STAGE_NODE;  // [gp][b][c]
+    double *s_w = s_dN + 8 * 8 * 3;
+    const Lattice &L = A.L;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = tid; t < 8 * 8 * 3; t += NTH) s_dN[t] = (&A.dN[0][0][0])[t];
+    if (tid < 8) s_w[tid] = A.w[tid];
+
+    int bid = blockIdx.x;
+    const int tix = bid % A.tiles_x;
+    bid /= A.tiles_x;
+    const int tiy = bid % A.tiles_y;
+    const int chunk_id = bid / A.tiles_y;
+    const int X0 = tix * TX, Y0 = tiy * TY;
+    const int zs = L.k0 + chunk_id * A.chunk;
+    const int ze = min(zs + A.chunk, L.k1);
+
+    // phase-2 identity of this thread
+    const int s = lane & 7, nt = warp * 4 + (lane >> 3);
+    const int sx = s & 1, sy = (s >> 1) & 1, sz = s >> 2;
+    const int tx = nt % TX, ty = nt / TX;
+    const int ix = X0 + tx, iy = Y0 + ty;
+    const bool node_ok = ix < L.n1 && iy < L.n1;
+    const int ex = ix - sx, ey = iy - sy;
+    const bool el_xy_ok = node_ok && ex >= 0 && ey >= 0 && ex < L.ne && ey < L.ne;
+    const int e = (ty - sy + 1) * EX + (tx - sx + 1);
+    const int a = sz * 4 + ((sy << 1) | (sx ^ sy));  // local node number of this node inside element -s
+    double *my_stage = stage + nt * STAGE_NODE;
+    double *warp_stage = stage + warp * 4 * STAGE_NODE;
+    __syncthreads();
+
+    for (int k = zs; k < ze; ++k) {
+        if (k == zs && k - 1 >= 0) phase1(A, s_dN, s_w, S, k - 1, X0, Y0);
+        if (k < L.ne) phase1(A, s_dN, s_w, S, k, X0, Y0);
+        for (int t = lane; t < 4 * STAGE_NODE; t += 32) warp_stage[t] = 0.0;
+        __syncthreads();
+
+        // ---- phase 2: G_ab for b = 0..7 -------------------------------------------------------
+        const int layer = k - sz;
+        const bool el_ok = el_xy_ok && layer >= 0 && layer < L.ne;
+        double G[8][9];
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+#pragma unroll
+            for (int m = 0; m < 9; ++m) G[b][m] = 0.0;
+        if (el_ok) {
+            const double *Sb = S + (layer & 1) * LAYER + e;
+#pragma unroll 2
+            for (int gp = 0; gp < 8; ++gp) {
+                const double *Sg = Sb + gp * (8 * 3 * NEL);
+                const double ga0 = Sg[(a * 3 + 0) * NEL], ga1 = Sg[(a * 3 + 1) * NEL], ga2 = Sg[(a * 3 + 2) * NEL];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const double gb0 = Sg[(b * 3 + 0) * NEL], gb1 = Sg[(b * 3 + 1) * NEL], gb2 = Sg[(b * 3 + 2) * NEL];
+                    G[b][0] += ga0 * gb0;
+                    G[b][1] += ga0 * gb1;
+                    G[b][2] += ga0 * gb2;
+                    G[b][3] += ga1 * gb0;
+                    G[b][4] += ga1 * gb1;
+                    G[b][5] += ga1 * gb2;
+                    G[b][6] += ga2 * gb0;
+                    G[b][7] += ga2 * gb1;
+                    G[b][8] += ga2 * gb2;
+                }
+            }
+        }
+        // ---- combine: round b -> neighbour offset d = o(b) - s, distinct for the 8 slot threads -------
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int obx = ((b & 3) == 1 || (b & 3) == 2), oby = ((b & 3) >= 2), obz = (b >> 2);
+            if (el_ok) {
+                double *dst = my_stage + ((obz - sz + 1) * 9 + (oby - sy + 1) * 3 + (obx - sx + 1)) * 9;
+#pragma unroll
+                for (int m = 0; m < 9; ++m) dst[m] += G[b][m];
+            }
+            __syncwarp();
+        }
+        // ---- output: lane q < 27 owns neighbour q of each of the warp's 4 nodes -----------------------------
+        if (lane < 27) {
+            const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+            for (int jn = 0; jn < 4; ++jn) {
+                const int n2 = warp * 4 + jn;
+                const int jx = X0 + n2 % TX, jy = Y0 + n2 / TX;
+                if (jx >= L.n1 || jy >= L.n1) continue;
+                const int nx = jx + dx, ny = jy + dy, nz = k + dz;
+                if (nx < 0 || ny < 0 || nz < 0 || nx >= L.n1 || ny >= L.n1 || nz >= L.n1) continue;
+                const int cx = 1 + (jx > 0) + (jx < L.n1 - 1), cy = 1 + (jy > 0) + (jy < L.n1 - 1),
+                          cz = 1 + (k > 0) + (k < L.n1 - 1);
+                const int rank = ((dz + (k > 0)) * cy + (dy + (jy > 0))) * cx + (dx + (jx > 0));
+                const int T = 3 * cx * cy * cz;
+                const int64_t row = (((int64_t)(k - L.k0) * L.n1 + jy) * L.n1 + jx) * 3;
+                const int64_t base = A.rowptr[row] + 3 * rank;
+                const double *g = stage + n2 * STAGE_NODE + lane * 9;
+                const double tr = g[0] + g[4] + g[8];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const double gij = g[c * 3 + j], gji = g[j * 3 + c];
+                        const double v = (c == j) ? A.mat.d11 * gij + A.mat.mu * (tr - gij) : A.mat.lam * gij + A.mat.mu * gji;
+                        A.val[base + (int64_t)c * T + j] = v;
+                        if (lane == 13 && c == j) A.diag[row + c] = v;
+                    }
+            }
+        }
+        __syncthreads();  // staging + ring slot (k-1)&1 are reused by the next plane
+    }
+}
+
+}  // namespace
+
+bool values_tile_enabled() {
+    const char *e = std::getenv("SMFEM_VALUES");
+    return !(e && std::string(e) == "atomic");
+}
+
+void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_values_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        attr_set = true;
+    }
+    if (!K->diag) K->diag = dev_alloc<double>(K->nrows_l);
+    TileArgs A;
+    A.L = mesh->lat;
+    A.coords = mesh->coords;
+    A.rowptr = K->rowptr;
+    A.val = K->val;
+    A.diag = K->diag;
+    A.mat = mat;
+    A.tiles_x = (A.L.n1 + TX - 1) / TX;
+    A.tiles_y = (A.L.n1 + TY - 1) / TY;
+    const int ntiles = A.tiles_x * A.tiles_y, nown = A.L.nown();
+    int nchunks = (ctx->sms * 8 + ntiles - 1) / ntiles;  // aim at >= 8 CTAs per SM over the run
+    if (nchunks > nown / 6) nchunks = nown / 6;           // but keep chunks >= 6 planes (prologue layer amortised)
+    if (nchunks < 1) nchunks = 1;
+    A.chunk = (nown + nchunks - 1) / nchunks;
+    A.nchunks = (nown + A.chunk - 1) / A.chunk;
+    {
+        double xi[2], w[2];
+        smfem_host_gauss(-1, 1, 2, xi, w);
+        const int ix[8] = {0, 1, 1, 0, 0, 1, 1, 0}, iy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, iz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+        for (int g = 0; g < 8; ++g) {
+            double N[8], dN[24];
+            int nn;
+            smfem_host_basis(3, SMFEM_Q1, xi[ix[g]], xi[iy[g]], xi[iz[g]], N, dN, &nn);
+            for (int a = 0; a < 8; ++a)
+                for (int d = 0; d < 3; ++d) A.dN[g][a][d] = dN[d * 8 + a];
+            A.w[g] = w[ix[g]] * w[iy[g]] * w[iz[g]];
+        }
+    }
+    const unsigned grid = (unsigned)(ntiles * A.nchunks);
+    LAUNCH(ctx, k_values_tile, grid, NTH, SMEM_BYTES, A);
 }

@@ -155,7 +155,9 @@ struct smfem_matrix {
     CommView comm;
     void *peer_maps[SMFEM_MAX_RANKS] = {nullptr};
     bool comm_connected = false;
-    int spmv_variant = 0;
+    int spmv_variant = 2;  // 2 = CSR-stream (default), 1 = warp per row, 0 = warp per 3 rows
+    int32_t *blk_row = nullptr;  // CSR-stream row blocks
+    int nblk = 0, max_rowlen = 0, ctas_per_sm = 4;
     // stats
     float last_ms = 0, last_ms_spmv = 0;
     int last_iters = 0;

@@ -253,6 +253,167 @@ __global__ void __launch_bounds__(256) k_spmv(SpmvArgs A) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Variant 2 ("stream", default): CSR-stream.  The nonzeros are cut into blocks of ~SPMV_CH entries
+// aligned to row boundaries (blk_row[], built once per pattern).  A persistent CTA takes blocks
+// cyclically; phase 1 streams val/colind of the whole block with perfectly coalesced L1-bypassing
+// loads (16 independent loads in flight per thread), multiplies by the gathered x and parks the
+// products in shared memory; phase 2 reduces each row from shared memory with one warp per row.
+// Row length never matters for coalescing or lane use, the grid is ~6 CTAs/SM so the fused dot
+// needs < 1k partials, and no atomics are involved.
+// ------------------------------------------------------------------------------------------------
+constexpr int SPMV_CH = 2048;      // target nonzeros per block (8 register-prefetched entries per thread)
+constexpr int SPMV_SLACK = 256;    // max row length supported by the stream kernel
+constexpr int SPMV_NT = 256;
+
+__global__ void k_spmv_blockrows(int64_t nrows, const int64_t *__restrict__ rowptr, int nblk, int32_t *__restrict__ blk_row) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nblk) return;
+    if (b == nblk) {
+        blk_row[b] = (int32_t)nrows;
+        return;
+    }
+    int64_t target = (int64_t)b * SPMV_CH;
+    int64_t lo = 0, hi = nrows;  // first row r with rowptr[r] >= target
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (rowptr[mid] < target) lo = mid + 1;
+        else hi = mid;
+    }
+    blk_row[b] = (int32_t)lo;
+}
+
+__global__ void k_max_rowlen(int64_t nrows, const int64_t *__restrict__ rowptr, int *__restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nrows) atomicMax(out, (int)(rowptr[r + 1] - rowptr[r]));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SPMV_NT) k_spmv_stream(SpmvArgs A, const int32_t *__restrict__ blk_row, int nblk) {
+    constexpr bool MASK = MODE & 1, DOT = MODE & 2, HALO = MODE & 4;
+    constexpr int PER = SPMV_CH / SPMV_NT;                    // streamed entries per thread per block
+    constexpr int EXTRA = (SPMV_SLACK + SPMV_NT - 1) / SPMV_NT;  // tail iterations (row-aligned overshoot)
+    __shared__ double s_prod[SPMV_CH + SPMV_SLACK];
+    __shared__ double s_red[SPMV_NT / 32];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double dot = 0.0;
+    // software pipeline: bounds of block i+1 and the val/colind registers of block i+1 are loaded while
+    // block i is being reduced, so the dependent chain blk_row -> rowptr -> val/col -> x never serialises.
+    auto block_of = [&](int b0) { return HALO ? (int)(((int64_t)b0 + A.rot) % nblk) : b0; };
+    int b0 = blockIdx.x;
+    int R0 = 0, R1 = 0, n = 0;
+    int64_t p0 = 0;
+    double rv[PER + EXTRA];
+    int rc[PER + EXTRA];
+    auto load_bounds = [&](int bb, int &r0, int &r1, int64_t &q0, int &cnt) {
+        if (bb < nblk) {
+            const int b = block_of(bb);
+            r0 = blk_row[b];
+            r1 = blk_row[b + 1];
+            q0 = A.rowptr[r0];
+            cnt = (int)(A.rowptr[r1] - q0);
+        } else {
+            r0 = r1 = 0;
+            q0 = 0;
+            cnt = 0;
+        }
+    };
+    auto issue_loads = [&](int64_t q0, int cnt) {
+#pragma unroll
+        for (int j = 0; j < PER + EXTRA; ++j) {
+            const int t = tid + j * SPMV_NT;
+            if (t < cnt) {
+                rv[j] = ld_stream_f64(A.val + q0 + t);
+                rc[j] = ld_stream_s32(A.colind + q0 + t);
+            }
+        }
+    };
+    load_bounds(b0, R0, R1, p0, n);
+    issue_loads(p0, n);
+    int nR0, nR1, nn;
+    int64_t np0;
+    load_bounds(b0 + gridDim.x, nR0, nR1, np0, nn);
+    for (; b0 < nblk; b0 += gridDim.x) {
+        if (HALO && A.cv.nranks > 1) {
+            const bool lo = (A.cv.rank > 0) && (R0 < A.cv.plane_dofs);
+            const bool hi = (A.cv.rank < A.cv.nranks - 1) && (R1 > A.nrows - A.cv.plane_dofs);
+            if ((lo || hi) && tid == 0) {
+                const unsigned long long need = A.scal->it + 1;
+                if (lo)
+                    while (ld_acquire_sys(&A.cv.self->hflag[0]) < need) {
+                    }
+                if (hi)
+                    while (ld_acquire_sys(&A.cv.self->hflag[1]) < need) {
+                    }
+            }
+            if (lo || hi) __syncthreads();
+        }
+        // products of the current block (registers -> gather x -> shared memory)
+#pragma unroll
+        for (int j = 0; j < PER + EXTRA; ++j) {
+            const int t = tid + j * SPMV_NT;
+            if (t < n) s_prod[t] = rv[j] * A.x[rc[j]];
+        }
+        const int cR0 = R0, cR1 = R1;
+        const int64_t cp0 = p0;
+        __syncthreads();
+        // prefetch the next block into registers, and the bounds of the one after
+        R0 = nR0, R1 = nR1, p0 = np0, n = nn;
+        issue_loads(p0, n);
+        load_bounds(b0 + 2 * gridDim.x, nR0, nR1, np0, nn);
+        // reduce the rows of the current block: one warp per row
+        for (int r = cR0 + warp; r < cR1; r += SPMV_NT / 32) {
+            const int a = (int)(A.rowptr[r] - cp0), e = (int)(A.rowptr[r + 1] - cp0);
+            double s = 0.0;
+            for (int t = a + lane; t < e; t += 32) s += s_prod[t];
+            s = warp_sum(s);
+            if (lane == 0) {
+                if (MASK && A.fixed[r]) s = 0.0;
+                A.y[r] = s;
+                if (DOT) dot += s * A.x[A.ghost_cols + r];
+            }
+        }
+        __syncthreads();
+    }
+    if (DOT) {
+        double s = block_sum<SPMV_NT>(dot, s_red);
+        if (tid == 0) {
+            A.partials[blockIdx.x] = s;
+            __threadfence();
+            unsigned t = atomicAdd(&A.scal->ticketB, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double v = 0.0;
+            for (int i = tid; i < (int)gridDim.x; i += SPMV_NT) v += ld_volatile_f64(A.partials + i);
+            double tot = block_sum<SPMV_NT>(v, s_red);
+            if (tid == 0) {
+                A.scal->ticketB = 0;
+                allreduce_publish(A.cv, 2ull * A.scal->it + 1ull, 1, &tot);
+            }
+        }
+    }
+}
+
+static void spmv_stream_setup(smfem_ctx *ctx, smfem_matrix *K) {
+    if (K->blk_row) return;
+    int *d_max = dev_alloc<int>(1);
+    CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
+    LAUNCH(ctx, k_max_rowlen, (unsigned)((K->nrows_l + 255) / 256), 256, 0, K->nrows_l, (const int64_t *)K->rowptr, d_max);
+    CUDA_CHECK(cudaMemcpyAsync(&K->max_rowlen, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    dev_free(d_max);
+    K->nblk = (int)((K->nnz_l + SPMV_CH - 1) / SPMV_CH);
+    if (K->nblk < 1) K->nblk = 1;
+    K->blk_row = dev_alloc<int32_t>(K->nblk + 1);
+    LAUNCH(ctx, k_spmv_blockrows, (unsigned)((K->nblk + 1 + 255) / 256), 256, 0, K->nrows_l, (const int64_t *)K->rowptr, K->nblk,
+           K->blk_row);
+}
+
 static SpmvArgs make_spmv_args(smfem_matrix *K, const double *x, double *y) {
     SpmvArgs A;
     A.nrows = K->nrows_l;
@@ -272,7 +433,11 @@ static SpmvArgs make_spmv_args(smfem_matrix *K, const double *x, double *y) {
 
 template <int MODE>
 static void launch_spmv(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A, int variant) {
-    if (variant == 1) {
+    if (variant == 2 && K->max_rowlen <= SPMV_SLACK) {
+        int grid = ctx->sms * K->ctas_per_sm;
+        if (grid > K->nblk) grid = K->nblk;
+        LAUNCH(ctx, (k_spmv_stream<MODE>), grid, SPMV_NT, 0, A, (const int32_t *)K->blk_row, K->nblk);
+    } else if (variant == 1 || variant == 2) {
         int64_t nw = A.nrows;
         unsigned grid = (unsigned)((nw * 32 + 255) / 256);
         LAUNCH(ctx, (k_spmv<1, MODE>), grid, 256, 0, A);
@@ -281,6 +446,16 @@ static void launch_spmv(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A, int 
         unsigned grid = (unsigned)((nw * 32 + 255) / 256);
         LAUNCH(ctx, (k_spmv<3, MODE>), grid, 256, 0, A);
     }
+}
+
+// rotation that makes the rows of the boundary planes the LAST work of the grid (halo overlap)
+static int64_t spmv_rotation(smfem_ctx *ctx, smfem_matrix *K, int variant) {
+    if (ctx->nranks == 1 || K->nrows_l == 0) return 0;
+    if (variant == 2 && K->max_rowlen <= SPMV_SLACK)
+        return (int64_t)((double)K->nblk * (double)K->comm.plane_dofs / (double)K->nrows_l) + 1;
+    int64_t nw = (variant == 0) ? (K->nrows_l + 2) / 3 : K->nrows_l;
+    int64_t per_plane = (variant == 0) ? (K->comm.plane_dofs + 2) / 3 : K->comm.plane_dofs;
+    return per_plane % nw;
 }
 
 static int64_t spmv_grid(smfem_matrix *K, int variant) {
@@ -535,6 +710,7 @@ void solver_alloc(smfem_ctx *ctx, smfem_matrix *K) {
     CUDA_CHECK(cudaMemsetAsync(K->qd, 0, sizeof(double) * K->ncols_l, ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(K->fixed, 0, K->nrows_l, ctx->stream));
     CUDA_CHECK(cudaMallocHost(&K->h_pinned, 64));
+    spmv_stream_setup(ctx, K);
     K->comm = CommView();
     K->comm.rank = ctx->rank;
     K->comm.nranks = ctx->nranks;
@@ -564,6 +740,7 @@ void solver_free(smfem_matrix *K) {
     dev_free(K->qd);
     dev_free(K->fixed);
     dev_free(K->partials);
+    dev_free(K->blk_row);
     dev_free(K->scal);
     if (K->h_pinned) cudaFreeHost(K->h_pinned);
     K->h_pinned = nullptr;
@@ -624,9 +801,7 @@ void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *m
     REQUIRE(K->comm_connected, SMFEM_ERR_INVALID, "multi-GPU: call smfem_comm_connect first");
     LAUNCH(ctx, k_fill_pattern, (unsigned)((K->ncols_l + 255) / 256), 256, 0, K->ncols_l, K->p);
     SpmvArgs A = make_spmv_args(K, K->p, K->Ap);
-    int64_t nw = variant == 1 ? K->nrows_l : (K->nrows_l + 2) / 3;
-    int64_t per_plane = variant == 1 ? K->comm.plane_dofs : (K->comm.plane_dofs + 2) / 3;
-    A.rot = (ctx->nranks > 1 && nw > 0) ? per_plane % nw : 0;
+    A.rot = spmv_rotation(ctx, K, variant);
     // sequence numbers for the halo flags continue the solver's counter
     unsigned long long it0 = 0;
     CUDA_CHECK(cudaMemcpyAsync(&it0, &K->scal->it, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -688,11 +863,7 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
     int it = 0;
     double res2 = rr;
     SpmvArgs A = make_spmv_args(K, K->p, K->Ap);
-    {
-        int64_t nw = variant == 1 ? n : (n + 2) / 3;
-        int64_t per_plane = variant == 1 ? K->comm.plane_dofs : (K->comm.plane_dofs + 2) / 3;
-        A.rot = (ctx->nranks > 1 && nw > 0) ? per_plane % nw : 0;
-    }
+    A.rot = spmv_rotation(ctx, K, variant);
     if (bnorm2 > 0.0) {
         const int chunk = 25;
         cudaGraph_t graph = nullptr;

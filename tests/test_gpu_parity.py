@@ -178,6 +178,28 @@ def test_config_c2_ne20_against_golden(golden_dir):
     assert abs(np.abs(q[0::3]).max() - s[7]) <= 1e-9 * s[7]
 
 
+def test_tile_and_atomic_value_kernels_agree(monkeypatch):
+    """The structured path has two value kernels (tiled gather = default, atomic scatter = general);
+    both must meet the parity bar, and the tiled one must be bit-reproducible run to run."""
+    ne = 13  # not a multiple of the 8x4 tile: exercises partial tiles
+    ctx = sf.context()
+    NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.jitter_nodes(NL, ne, seed=99)
+    Ko = o.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4)
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).set_nodelist(NL)
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
+    assert_csc_parity(K, Ko)
+    nz1 = K.to_csc()[2]
+    d1 = K.diag()
+    K.assemble_values(40, 0.4)
+    assert np.array_equal(K.to_csc()[2], nz1), "tiled gather kernel must be deterministic"
+    monkeypatch.setenv("SMFEM_VALUES", "atomic")
+    K.assemble_values(40, 0.4)
+    assert_csc_parity(K, Ko)
+    assert rel(K.diag(), d1) <= 1e-14
+    monkeypatch.delenv("SMFEM_VALUES")
+
+
 def test_spmv_variants_and_host_spmv():
     ne = 9
     NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
@@ -185,7 +207,7 @@ def test_spmv_variants_and_host_spmv():
     K = sf.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4)
     A = o.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4).to_scipy()
     x = np.random.default_rng(3).standard_normal(K.shape[0])
-    for v in (0, 1):
+    for v in (0, 1, 2):
         K.set_spmv_variant(v)
         assert rel(K.spmv(x), A @ x) <= 1e-13
 
