@@ -1,0 +1,214 @@
+# SmearFEMB200.jl -- the reference-side binding: a thin `ccall` shim over libsmearfem_b200.so that keeps
+# smearFEM.jl's call surface (src/smearFEM.jl:3-4 exports + the example-script functions of
+# examples/vector3D.jl).  Julia is not installed in the build image, so this file is NOT exercised by
+# the test-suite; the Python mirror (smearfem.jl_b200/__init__.py) binds the very same symbols with the
+# same argument order and is what the parity tests run.  Keep the two in sync with include/smearfem_b200.h.
+#
+# Usage (drop-in for the hot path):
+#     using SmearFEMB200            # instead of `using smearFEM` for assemble/solve
+#     K  = assemble_system(ne, NodeList, IEN, ndim, "Q1", nDof, ID, Young, ν)      # device-resident
+#     b  = apply_boundary_conditions(ne, NodeList, IEN, IEN_top, IEN_btm, ndim, "Q1", ID)
+#     K̄  = K + β*b                                                                 # in place on the GPU
+#     q_d, C = setboundaryCond(NodeList, ne, ndim, "Q1", d, nDof)
+#     q  = solve(K̄, q_d, C)                 # replaces inv(Matrix(C'K̄C)) * C'(-K̄ q_d); q = q_d + C q_f
+#     SparseMatrixCSC(K)                    # materialise Julia's CSC when really needed
+module SmearFEMB200
+
+using SparseArrays, LinearAlgebra
+
+export assemble_system, gaussian_quadrature, basis_function, greet_fem
+export meshgrid, setboundaryCond, apply_boundary_conditions, inflate_sphere, solve
+export B200SparseMatrix, SurfaceMatrix
+
+const LIB = get(ENV, "SMEARFEM_B200_LIB", joinpath(@__DIR__, "..", "libsmearfem_b200.so"))
+const Q1, Q2 = Cint(1), Cint(2)
+
+struct SmfemError <: Exception
+    code::Cint
+    msg::String
+end
+Base.showerror(io::IO, e::SmfemError) = print(io, "smearfem_b200 [status $(e.code)]: ", e.msg)
+
+last_error() = unsafe_string(ccall((:smfem_last_error, LIB), Cstring, ()))
+check(rc::Cint) = rc == 0 ? nothing : throw(SmfemError(rc, last_error()))
+fclass(s::AbstractString) = s == "Q1" ? Q1 : s == "Q2" ? Q2 : throw(ArgumentError("FunctionClass $s"))
+
+# ---- context: one GPU per process (RANK / WORLD_SIZE / LOCAL_RANK as set by the launcher) -------------------
+mutable struct Context
+    h::Ptr{Cvoid}
+end
+const CTX = Ref{Union{Nothing,Context}}(nothing)
+function context()
+    if CTX[] === nothing
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        dev = parse(Cint, get(ENV, "LOCAL_RANK", "0"))
+        rank = parse(Cint, get(ENV, "RANK", "0"))
+        nr = parse(Cint, get(ENV, "WORLD_SIZE", "1"))
+        check(ccall((:smfem_init, LIB), Cint, (Cint, Cint, Cint, Ptr{Ptr{Cvoid}}), dev, rank, nr, h))
+        c = Context(h[])
+        finalizer(c -> ccall((:smfem_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), c)
+        CTX[] = c
+    end
+    return CTX[]
+end
+
+greet_fem() = println("Hello, I am the FEM module")          # src/fem.jl:4-6
+
+# ---- src/fem.jl:21-31 -------------------------------------------------------------------------------------
+function gaussian_quadrature(a, b, nGaussPoints=2)
+    ξ = zeros(max(nGaussPoints, 1)); w = zeros(max(nGaussPoints, 1))
+    check(ccall((:smfem_gaussian_quadrature, LIB), Cint, (Cdouble, Cdouble, Cint, Ptr{Cdouble}, Ptr{Cdouble}),
+                a, b, nGaussPoints, ξ, w))
+    return ξ, w
+end
+
+# ---- src/fem.jl:48-114 ------------------------------------------------------------------------------------
+function basis_function(ξ, η=nothing, ζ=nothing, FunctionClass="Q1")
+    ndim = isnothing(η) ? 1 : isnothing(ζ) ? 2 : 3
+    N = zeros(9); ΔN = zeros(27); nn = Ref{Cint}(0)
+    check(ccall((:smfem_basis_function, LIB), Cint,
+                (Cint, Cint, Cdouble, Cdouble, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}),
+                ndim, fclass(FunctionClass), ξ, something(η, 0.0), something(ζ, 0.0), N, ΔN, nn))
+    n = Int(nn[])
+    ndim == 1 && return N[1:n], reshape(ΔN[1:2], 1, 2)                 # src/fem.jl:75 (1x2 row)
+    return N[1:n], reshape(ΔN[1:n*ndim], n, ndim)
+end
+
+# ---- mesh handle ------------------------------------------------------------------------------------------
+mutable struct Mesh
+    h::Ptr{Cvoid}
+end
+free!(m::Mesh) = (m.h != C_NULL && ccall((:smfem_mesh_free, LIB), Cint, (Ptr{Cvoid},), m.h); m.h = C_NULL)
+
+function mesh_from_host(NodeList::Matrix{Float64}, IEN::Matrix{Int64}, ID, ndim, nDof, ne)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    idp = ID === nothing ? Ptr{Int64}(C_NULL) : pointer(ID)
+    GC.@preserve NodeList IEN ID begin
+        check(ccall((:smfem_mesh_from_host, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Cint, Cint, Cint, Int64, Ptr{Ptr{Cvoid}}),
+                    context().h, NodeList, IEN, idp, size(NodeList, 2), size(IEN, 1), size(IEN, 2), ndim,
+                    ID === nothing ? nDof : size(ID, 2), ne, h))
+    end
+    m = Mesh(h[]); finalizer(free!, m); return m
+end
+
+# ---- examples/vector3D.jl:10-130 (3-D branch; coordinates generated on the device) -------------------------
+function meshgrid(x0, x1, y0, y1, z0, z1, ne, ndim)
+    ndim == 3 || error("SmearFEMB200.meshgrid: use smearFEM's host meshgrid for ndim = 2")
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:smfem_meshgrid, LIB), Cint,
+                (Ptr{Cvoid}, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Cdouble, Int64, Cint, Ptr{Ptr{Cvoid}}),
+                context().h, x0, x1, y0, y1, z0, z1, ne, ndim, h))
+    m = Mesh(h[])
+    nN, nEl = (ne + 1)^3, ne^3
+    NodeList = zeros(3, nN); IEN = zeros(Int64, nEl, 8); ID = zeros(Int64, nN, 3)
+    IEN_top = zeros(Int64, ne^2, 4); IEN_btm = zeros(Int64, ne^2, 4)
+    check(ccall((:smfem_mesh_export, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+                context().h, m.h, NodeList, IEN, ID, IEN_top, IEN_btm))
+    free!(m)
+    Border = Int[]; Bottom = Int[]; Top = Int[]                        # :76-82 (visualisation lists)
+    mm = 1
+    for k in 1:ne+1, j in 1:ne+1, i in 1:ne+1
+        if i == 1 || i == ne + 1 || j == 1 || j == ne + 1
+            push!(Border, mm)
+        elseif k == 1
+            push!(Bottom, mm)
+        elseif k == ne + 1
+            push!(Top, mm)
+        end
+        mm += 1
+    end
+    return NodeList, IEN, ID, IEN_top, IEN_btm, [Border, Bottom, Top]
+end
+
+# ---- src/PostProcess.jl:30-44 (in place) ----------------------------------------------------------------------
+function inflate_sphere(NodeList::Matrix{Float64}, x0, x1, y0, y1)
+    check(ccall((:smfem_inflate_sphere_host, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Cint, Int64, Cdouble, Cdouble, Cdouble, Cdouble),
+                context().h, NodeList, size(NodeList, 1), size(NodeList, 2), x0, x1, y0, y1))
+    return NodeList
+end
+
+# ---- src/fem.jl:135-256 ------------------------------------------------------------------------------------
+mutable struct B200SparseMatrix            # stands in for SparseMatrixCSC{Float64,Int64}; lives in HBM
+    h::Ptr{Cvoid}
+    mesh::Mesh
+end
+free!(K::B200SparseMatrix) = (K.h != C_NULL && ccall((:smfem_matrix_free, LIB), Cint, (Ptr{Cvoid},), K.h); K.h = C_NULL)
+
+function assemble_system(ne, NodeList, IEN, ndim, FunctionClass="Q1", nDof=1, ID=nothing, Young=1, ν=0.3)
+    mesh = mesh_from_host(Matrix{Float64}(NodeList), Matrix{Int64}(IEN), nDof > 1 ? Matrix{Int64}(ID) : nothing, ndim, nDof, ne)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:smfem_assemble, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Cint, Cint, Cdouble, Cdouble, Ptr{Ptr{Cvoid}}),
+                context().h, mesh.h, ne, ndim, fclass(FunctionClass), nDof, Young, ν, h))
+    K = B200SparseMatrix(h[], mesh); finalizer(free!, K); return K
+end
+
+function info(K::B200SparseMatrix)
+    v = [Ref{Int64}(0) for _ in 1:6]
+    check(ccall((:smfem_matrix_info, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+                K.h, v...))
+    return (m=v[1][], n=v[2][], nnz=v[3][], row0=v[4][], nrows_local=v[5][], nnz_local=v[6][])
+end
+Base.size(K::B200SparseMatrix) = (i = info(K); (Int(i.m), Int(i.n)))
+SparseArrays.nnz(K::B200SparseMatrix) = Int(info(K).nnz)
+
+function SparseArrays.SparseMatrixCSC(K::B200SparseMatrix; which=0)      # what `sparse(E,J,V)` returned (src/fem.jl:253)
+    i = info(K)
+    colptr = zeros(Int64, i.nrows_local + 1); rowval = zeros(Int64, i.nnz_local); nzval = zeros(i.nnz_local)
+    check(ccall((:smfem_matrix_export_csc, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}),
+                context().h, K.h, which, colptr, rowval, nzval))
+    return SparseMatrixCSC(Int(i.m), Int(i.nrows_local), colptr, rowval, nzval)
+end
+
+# ---- examples/vector3D.jl:175-264 and :308 ----------------------------------------------------------------------
+struct SurfaceMatrix                         # b = ∫ NᵀN over top ∪ bottom, kept lazy
+    IEN_top::Matrix{Int64}
+    IEN_btm::Matrix{Int64}
+    β::Float64
+end
+function apply_boundary_conditions(ne, NodeList, IEN, IEN_top, IEN_btm, ndim, FunctionClass, ID, nDof=3)
+    ndim == 3 || error("apply_boundary_conditions: only the 3-D branch of the reference is executable")
+    return SurfaceMatrix(Matrix{Int64}(IEN_top), Matrix{Int64}(IEN_btm), 1.0)
+end
+Base.:*(β::Number, b::SurfaceMatrix) = SurfaceMatrix(b.IEN_top, b.IEN_btm, b.β * β)
+function Base.:+(K::B200SparseMatrix, b::SurfaceMatrix)                    # K̄ = K + β*b, in place on the device
+    check(ccall((:smfem_surface_mass, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Int64, Cdouble, Cint),
+                context().h, K.h, K.mesh.h, b.IEN_top, b.IEN_btm, size(b.IEN_top, 1), b.β, 0))
+    return K
+end
+
+# ---- examples/vector3D.jl:133-173 (host data preparation, verbatim semantics) ------------------------------------
+function setboundaryCond(NodeList, ne, ndim, FunctionClass, d, nDof=1)
+    q_d = zeros(nDof * (ne + 1)^ndim, 1)
+    C = sparse(I, ndim * (ne + 1)^ndim, ndim * (ne + 1)^ndim)
+    rCol = Int[]
+    for nNode in 1:size(NodeList, 2)
+        z = NodeList[3, nNode]
+        if z == 0
+            q_d[3*nNode] = 0; push!(rCol, 3 * nNode)
+        elseif z == 1
+            q_d[3*nNode] = -d; push!(rCol, 3 * nNode)
+        end
+    end
+    return q_d, C[:, setdiff(1:size(C, 2), rCol)]
+end
+
+# ---- examples/vector3D.jl:315-322 ---------------------------------------------------------------------------------
+function solve(K̄::B200SparseMatrix, q_d, C; rtol=1e-12, maxit=20000)
+    ndof = size(C, 1)
+    free = rowvals(C)                                   # C = I[:, free]
+    fixed = Int64.(setdiff(1:ndof, free)); vals = Float64.(q_d[fixed])
+    check(ccall((:smfem_set_dirichlet, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cdouble}, Int64),
+                context().h, K̄.h, fixed, vals, length(fixed)))
+    q = zeros(info(K̄).nrows_local); it = Ref{Cint}(0); rel = Ref{Cdouble}(0)
+    check(ccall((:smfem_pcg_solve, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}, Ptr{Cdouble}),
+                context().h, K̄.h, rtol, maxit, C_NULL, q, it, rel))
+    return q
+end
+
+end # module
