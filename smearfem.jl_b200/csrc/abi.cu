@@ -689,7 +689,7 @@ int smfem_bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, flo
 int smfem_set_spmv_variant(smfem_matrix *K, int variant) {
     return guarded([&] {
         NOTNULL(K);
-        REQUIRE(variant >= 0 && variant <= 2, SMFEM_ERR_INVALID, "unknown SpMV variant");
+        REQUIRE(variant >= 0 && variant <= 4, SMFEM_ERR_INVALID, "unknown SpMV variant");
         K->spmv_variant = variant;
     });
 }

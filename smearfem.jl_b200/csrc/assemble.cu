@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256) k_struct_colind(Lattice L, int64_t nOwned
 }
 
 static void matrix_alloc_pattern(smfem_matrix *K) {
-    K->rowptr = dev_alloc<int64_t>(K->nrows_l + 1);
+    K->rowptr = dev_alloc<int64_t>(K->nrows_l + 1 + 8);  // +8: slack for 16 B-aligned bulk copies (TMA SpMV)
 }
 
 void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
@@ -199,7 +199,8 @@ void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K)
     if (first) {
         CUDA_CHECK(cudaMemcpyAsync(&K->nnz_l, K->rowptr + K->nrows_l, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        K->colind = dev_alloc<int32_t>(K->nnz_l);
+        K->colind = dev_alloc<int32_t>(K->nnz_l + 16);
+        CUDA_CHECK(cudaMemsetAsync(K->colind + K->nnz_l, 0, 16 * sizeof(int32_t), ctx->stream));
     }
     int64_t nOwned = (int64_t)L.nown() * L.plane();
     if (nDof == 3)
@@ -416,7 +417,8 @@ void pattern_build_general(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
         exclusive_scan_impl(ctx, rowlen, K->rowptr, ndof + 1);
         CUDA_CHECK(cudaMemcpy(&K->nnz_l, K->rowptr + ndof, 8, cudaMemcpyDeviceToHost));
         K->nnz_g = K->nnz_l;
-        K->colind = dev_alloc<int32_t>(K->nnz_l);
+        K->colind = dev_alloc<int32_t>(K->nnz_l + 16);
+        CUDA_CHECK(cudaMemsetAsync(K->colind + K->nnz_l, 0, 16 * sizeof(int32_t), ctx->stream));
         LAUNCH(ctx, k_gen_colind, gR, 256, 0, D, adj_ptr, adj, nNodes, K->rowptr, K->colind);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         dev_free(rowlen);
@@ -594,7 +596,10 @@ void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Y
         mat.lam = nu * f;
         mat.mu = (1 - 2 * nu) / 2 * f;
     }
-    if (!K->val) K->val = dev_alloc<double>(K->nnz_l);
+    if (!K->val) {
+        K->val = dev_alloc<double>(K->nnz_l + 16);
+        CUDA_CHECK(cudaMemsetAsync(K->val + K->nnz_l, 0, 16 * sizeof(double), ctx->stream));
+    }
     if (mesh->structured && ndim == 3 && nDof == 3 && values_tile_enabled()) {
         values_assemble_tile(ctx, mesh, K, mat);  // writes every entry and the diagonal: no memset, no extract_diag
         K->values_ready = true;

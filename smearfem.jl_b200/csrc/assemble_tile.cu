@@ -25,12 +25,18 @@ struct Material {
 
 namespace {
 
-constexpr int TX = 8, TY = 4, NTH = 256;
-constexpr int EX = TX + 1, EY = TY + 1, NEL = EX * EY;  // 45 footprint elements per layer
-constexpr int LAYER = 8 * 8 * 3 * NEL + 3;               // doubles per layer in the ring; +3: the two layers a half-warp
-                                                         // reads (sz = 0/1) land in disjoint banks (ncu: 2x excess wavefronts without)
-constexpr int STAGE_NODE = 27 * 9;                       // doubles per node in the staging area
-constexpr size_t SMEM_BYTES = sizeof(double) * (2 * LAYER + TX * TY * STAGE_NODE + 8 * 8 * 3 + 8);
+constexpr int STAGE_NODE = 27 * 9;  // doubles per node in the staging area
+
+template <int TX_, int TY_>
+struct Tile {
+    static constexpr int TX = TX_, TY = TY_, NTH = TX_ * TY_ * 8;
+    static constexpr int EX = TX + 1, EY = TY + 1, NEL = EX * EY;  // footprint elements per layer (45 for 8x4)
+    // doubles per layer in the ring; +3: the two layers a half-warp reads (sz = 0/1) land in disjoint banks
+    // (ncu: 2x excess shared wavefronts without the pad)
+    static constexpr int PAD = (EX == 9) ? 3 : 8;  // 8x4 tile: banks {6,7,8,15,0,1}+3; 4x4 tile: {10,11,12,15,0,1}+8
+    static constexpr int LAYER = 8 * 8 * 3 * NEL + PAD;
+    static constexpr size_t SMEM_BYTES = sizeof(double) * (2 * LAYER + TX * TY * STAGE_NODE + 8 * 8 * 3 + 8);
+};
 
 struct TileArgs {
     Lattice L;
@@ -61,8 +67,10 @@ __device__ __forceinline__ double inv3(const double *J, double *inv) {
 }
 
 // element layer `layer` of the footprint -> ring slot
+template <class T>
 __device__ __forceinline__ void phase1(const TileArgs &A, const double *s_dN, const double *s_w, double *S, int layer, int X0,
                                        int Y0) {
+    constexpr int NEL = T::NEL, EX = T::EX, LAYER = T::LAYER, NTH = T::NTH;
     const Lattice &L = A.L;
     double *dst = S + (layer & 1) * LAYER;
     for (int q = threadIdx.x; q < 8 * NEL; q += NTH) {
@@ -102,7 +110,9 @@ __device__ __forceinline__ void phase1(const TileArgs &A, const double *s_dN, co
     }
 }
 
-__global__ void __launch_bounds__(NTH, 1) k_values_tile(const __grid_constant__ TileArgs A) {
+template <class T, int MINB>
+__global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_constant__ TileArgs A) {
+    constexpr int TX = T::TX, TY = T::TY, NTH = T::NTH, NEL = T::NEL, EX = T::EX, LAYER = T::LAYER;
     extern __shared__ double smem[];
     double *S = smem;                             // [2][gp][b][c][e]
     double *stage = smem + 2 * LAYER;             // [node][27][9]
@@ -137,8 +147,8 @@ __global__ void __launch_bounds__(NTH, 1) k_values_tile(const __grid_constant__ 
     __syncthreads();
 
     for (int k = zs; k < ze; ++k) {
-        if (k == zs && k - 1 >= 0) phase1(A, s_dN, s_w, S, k - 1, X0, Y0);
-        if (k < L.ne) phase1(A, s_dN, s_w, S, k, X0, Y0);
+        if (k == zs && k - 1 >= 0) phase1<T>(A, s_dN, s_w, S, k - 1, X0, Y0);
+        if (k < L.ne) phase1<T>(A, s_dN, s_w, S, k, X0, Y0);
         for (int t = lane; t < 4 * STAGE_NODE; t += 32) warp_stage[t] = 0.0;
         __syncthreads();
 
@@ -222,12 +232,26 @@ bool values_tile_enabled() {
     return !(e && std::string(e) == "atomic");
 }
 
-void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat) {
+template <class T, int MINB>
+static void launch_tile(smfem_ctx *ctx, TileArgs &A, int nown) {
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_values_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(k_values_tile<T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES));
         attr_set = true;
     }
+    A.tiles_x = (A.L.n1 + T::TX - 1) / T::TX;
+    A.tiles_y = (A.L.n1 + T::TY - 1) / T::TY;
+    const int ntiles = A.tiles_x * A.tiles_y;
+    int nchunks = (ctx->sms * 8 * MINB + ntiles - 1) / ntiles;  // aim at >= 8 CTAs per resident slot over the run
+    if (nchunks > nown / 6) nchunks = nown / 6;                  // but keep chunks >= 6 planes (prologue layer amortised)
+    if (nchunks < 1) nchunks = 1;
+    A.chunk = (nown + nchunks - 1) / nchunks;
+    A.nchunks = (nown + A.chunk - 1) / A.chunk;
+    const unsigned grid = (unsigned)(ntiles * A.nchunks);
+    LAUNCH(ctx, (k_values_tile<T, MINB>), grid, T::NTH, T::SMEM_BYTES, A);
+}
+
+void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat) {
     if (!K->diag) K->diag = dev_alloc<double>(K->nrows_l);
     TileArgs A;
     A.L = mesh->lat;
@@ -236,14 +260,6 @@ void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Mat
     A.val = K->val;
     A.diag = K->diag;
     A.mat = mat;
-    A.tiles_x = (A.L.n1 + TX - 1) / TX;
-    A.tiles_y = (A.L.n1 + TY - 1) / TY;
-    const int ntiles = A.tiles_x * A.tiles_y, nown = A.L.nown();
-    int nchunks = (ctx->sms * 8 + ntiles - 1) / ntiles;  // aim at >= 8 CTAs per SM over the run
-    if (nchunks > nown / 6) nchunks = nown / 6;           // but keep chunks >= 6 planes (prologue layer amortised)
-    if (nchunks < 1) nchunks = 1;
-    A.chunk = (nown + nchunks - 1) / nchunks;
-    A.nchunks = (nown + A.chunk - 1) / A.chunk;
     {
         double xi[2], w[2];
         smfem_host_gauss(-1, 1, 2, xi, w);
@@ -257,6 +273,9 @@ void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Mat
             A.w[g] = w[ix[g]] * w[iy[g]] * w[iz[g]];
         }
     }
-    const unsigned grid = (unsigned)(ntiles * A.nchunks);
-    LAUNCH(ctx, k_values_tile, grid, NTH, SMEM_BYTES, A);
+    const char *e = std::getenv("SMFEM_TILE");
+    if (e && std::string(e) == "8x4")
+        launch_tile<Tile<8, 4>, 1>(ctx, A, A.L.nown());   // 256 threads, 200 KB smem, 1 CTA/SM
+    else
+        launch_tile<Tile<4, 4>, 2>(ctx, A, A.L.nown());   // 128 threads, 108 KB smem, 2 CTAs/SM (phases overlap)
 }

@@ -155,9 +155,10 @@ struct smfem_matrix {
     CommView comm;
     void *peer_maps[SMFEM_MAX_RANKS] = {nullptr};
     bool comm_connected = false;
-    int spmv_variant = 2;  // 2 = CSR-stream (default), 1 = warp per row, 0 = warp per 3 rows
+    int spmv_variant = 4;  // 4 = row-triple (default; falls back to 2), 2 = CSR-stream, 3 = CSR-stream via TMA, 1 = warp/row, 0 = warp/3 rows
     int32_t *blk_row = nullptr;  // CSR-stream row blocks
     int nblk = 0, max_rowlen = 0, ctas_per_sm = 4;
+    bool stream_ok = false, group3_ok = false;
     // stats
     float last_ms = 0, last_ms_spmv = 0;
     int last_iters = 0;

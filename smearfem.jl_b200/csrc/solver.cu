@@ -263,9 +263,10 @@ __global__ void __launch_bounds__(256) k_spmv(SpmvArgs A) {
 // Row length never matters for coalescing or lane use, the grid is ~6 CTAs/SM so the fused dot
 // needs < 1k partials, and no atomics are involved.
 // ------------------------------------------------------------------------------------------------
-constexpr int SPMV_CH = 2048;      // target nonzeros per block (8 register-prefetched entries per thread)
+constexpr int SPMV_CH = 1776;      // target nonzeros per block: CH + SLACK + 2*3 alignment strangers <= 2048 = 2 quads/thread
 constexpr int SPMV_SLACK = 256;    // max row length supported by the stream kernel
 constexpr int SPMV_NT = 256;
+constexpr int SPMV_MAXROWS = 512;  // max rows per block handled by the stream kernel (2 per thread)
 
 __global__ void k_spmv_blockrows(int64_t nrows, const int64_t *__restrict__ rowptr, int nblk, int32_t *__restrict__ blk_row) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -289,24 +290,43 @@ __global__ void k_max_rowlen(int64_t nrows, const int64_t *__restrict__ rowptr, 
     if (r < nrows) atomicMax(out, (int)(rowptr[r + 1] - rowptr[r]));
 }
 
+__device__ __forceinline__ double2 ld_stream_v2f64(const double *p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int4 ld_stream_v4s32(const int32_t *p) {
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(SPMV_NT) k_spmv_stream(SpmvArgs A, const int32_t *__restrict__ blk_row, int nblk) {
+__global__ void __launch_bounds__(SPMV_NT, 4) k_spmv_stream(SpmvArgs A, const int32_t *__restrict__ blk_row, int nblk) {
     constexpr bool MASK = MODE & 1, DOT = MODE & 2, HALO = MODE & 4;
-    constexpr int PER = SPMV_CH / SPMV_NT;                    // streamed entries per thread per block
-    constexpr int EXTRA = (SPMV_SLACK + SPMV_NT - 1) / SPMV_NT;  // tail iterations (row-aligned overshoot)
-    __shared__ double s_prod[SPMV_CH + SPMV_SLACK];
+    // 128-bit streaming loads: a plain read stream with 8 B/lane loads tops out at 4.84 TB/s on B200, with
+    // 16 B/lane at 6.86 TB/s (tools/microbench/peaks.cu).  A block [p0, p0+n) is read as aligned quads starting at
+    // pa = p0 & ~3; the <= 3 leading and trailing strangers are multiplied too but never summed.
+    constexpr int QPT = (SPMV_CH + SPMV_SLACK + 8 + 4 * SPMV_NT - 1) / (4 * SPMV_NT);  // quads per thread (2)
+    constexpr int RPT = SPMV_MAXROWS / SPMV_NT;                                         // rows per thread in the epilogue
+    __shared__ __align__(16) double s_prod[QPT * 4 * SPMV_NT];
+    __shared__ double s_y[SPMV_MAXROWS];
+    __shared__ int s_rp[SPMV_MAXROWS + 1];
     __shared__ double s_red[SPMV_NT / 32];
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double dot = 0.0;
-    // software pipeline: bounds of block i+1 and the val/colind registers of block i+1 are loaded while
-    // block i is being reduced, so the dependent chain blk_row -> rowptr -> val/col -> x never serialises.
+    // Software pipeline: while block i is reduced out of shared memory, the registers already hold block
+    // i+1 (val, colind, its row pointers, Dirichlet flags and x_row) and the bounds of block i+2.
     auto block_of = [&](int b0) { return HALO ? (int)(((int64_t)b0 + A.rot) % nblk) : b0; };
     int b0 = blockIdx.x;
     int R0 = 0, R1 = 0, n = 0;
     int64_t p0 = 0;
-    double rv[PER + EXTRA];
-    int rc[PER + EXTRA];
+    double2 rva[QPT], rvb[QPT];
+    int4 rc[QPT];
+    int rrp[RPT + 1];
+    double rxr[RPT];
+    bool rfx[RPT];
     auto load_bounds = [&](int bb, int &r0, int &r1, int64_t &q0, int &cnt) {
         if (bb < nblk) {
             const int b = block_of(bb);
@@ -320,18 +340,31 @@ __global__ void __launch_bounds__(SPMV_NT) k_spmv_stream(SpmvArgs A, const int32
             cnt = 0;
         }
     };
-    auto issue_loads = [&](int64_t q0, int cnt) {
+    auto issue_loads = [&](int r0, int r1, int64_t q0, int cnt) {
+        const int64_t pa = q0 & ~(int64_t)3;
+        const int cnt4 = (int)(q0 - pa) + cnt;  // entries from the aligned start
 #pragma unroll
-        for (int j = 0; j < PER + EXTRA; ++j) {
+        for (int j = 0; j < QPT; ++j) {
+            const int t = 4 * (tid + j * SPMV_NT);
+            if (t < cnt4) {
+                rc[j] = ld_stream_v4s32(A.colind + pa + t);
+                rva[j] = ld_stream_v2f64(A.val + pa + t);
+                rvb[j] = ld_stream_v2f64(A.val + pa + t + 2);
+            }
+        }
+        const int nr = r1 - r0;
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
             const int t = tid + j * SPMV_NT;
-            if (t < cnt) {
-                rv[j] = ld_stream_f64(A.val + q0 + t);
-                rc[j] = ld_stream_s32(A.colind + q0 + t);
+            if (t < nr) {
+                rrp[j] = (int)(A.rowptr[r0 + t] - pa);
+                if (MASK) rfx[j] = A.fixed[r0 + t] != 0;
+                if (DOT) rxr[j] = A.x[A.ghost_cols + r0 + t];
             }
         }
     };
     load_bounds(b0, R0, R1, p0, n);
-    issue_loads(p0, n);
+    issue_loads(R0, R1, p0, n);
     int nR0, nR1, nn;
     int64_t np0;
     load_bounds(b0 + gridDim.x, nR0, nR1, np0, nn);
@@ -350,32 +383,53 @@ __global__ void __launch_bounds__(SPMV_NT) k_spmv_stream(SpmvArgs A, const int32
             }
             if (lo || hi) __syncthreads();
         }
-        // products of the current block (registers -> gather x -> shared memory)
+        // registers -> gather x -> products (and the block's row pointers) into shared memory
+        const int nr = R1 - R0, cR0 = R0;
+        const int cnt4 = (int)(p0 & 3) + n;
 #pragma unroll
-        for (int j = 0; j < PER + EXTRA; ++j) {
-            const int t = tid + j * SPMV_NT;
-            if (t < n) s_prod[t] = rv[j] * A.x[rc[j]];
+        for (int j = 0; j < QPT; ++j) {
+            const int t = 4 * (tid + j * SPMV_NT);
+            if (t < cnt4) {
+                const double x0 = A.x[rc[j].x], x1 = A.x[rc[j].y], x2 = A.x[rc[j].z], x3 = A.x[rc[j].w];
+                *reinterpret_cast<double2 *>(s_prod + t) = make_double2(rva[j].x * x0, rva[j].y * x1);
+                *reinterpret_cast<double2 *>(s_prod + t + 2) = make_double2(rvb[j].x * x2, rvb[j].y * x3);
+            }
         }
-        const int cR0 = R0, cR1 = R1;
-        const int64_t cp0 = p0;
+        bool cfx[RPT];
+        double cxr[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int t = tid + j * SPMV_NT;
+            if (t < nr) s_rp[t] = rrp[j];
+            cfx[j] = MASK ? rfx[j] : false;
+            cxr[j] = DOT ? rxr[j] : 0.0;
+        }
+        if (tid == 0) s_rp[nr] = cnt4;
         __syncthreads();
         // prefetch the next block into registers, and the bounds of the one after
         R0 = nR0, R1 = nR1, p0 = np0, n = nn;
-        issue_loads(p0, n);
+        issue_loads(R0, R1, p0, n);
         load_bounds(b0 + 2 * gridDim.x, nR0, nR1, np0, nn);
-        // reduce the rows of the current block: one warp per row
-        for (int r = cR0 + warp; r < cR1; r += SPMV_NT / 32) {
-            const int a = (int)(A.rowptr[r] - cp0), e = (int)(A.rowptr[r + 1] - cp0);
+        // row sums out of shared memory: one warp per row
+        for (int r = warp; r < nr; r += SPMV_NT / 32) {
+            const int a = s_rp[r], e = s_rp[r + 1];
             double s = 0.0;
             for (int t = a + lane; t < e; t += 32) s += s_prod[t];
             s = warp_sum(s);
-            if (lane == 0) {
-                if (MASK && A.fixed[r]) s = 0.0;
-                A.y[r] = s;
-                if (DOT) dot += s * A.x[A.ghost_cols + r];
-            }
+            if (lane == 0) s_y[r] = s;
         }
         __syncthreads();
+        // epilogue: one thread per row, coalesced store of y, Dirichlet mask, fused p'Ap
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int t = tid + j * SPMV_NT;
+            if (t < nr) {
+                double yv = s_y[t];
+                if (MASK && cfx[j]) yv = 0.0;
+                A.y[cR0 + t] = yv;
+                if (DOT) dot += yv * cxr[j];
+            }
+        }
     }
     if (DOT) {
         double s = block_sum<SPMV_NT>(dot, s_red);
@@ -399,6 +453,439 @@ __global__ void __launch_bounds__(SPMV_NT) k_spmv_stream(SpmvArgs A, const int32
     }
 }
 
+// also records the largest number of rows of any block (the stream kernel handles <= SPMV_MAXROWS)
+__global__ void k_spmv_maxrows(int nblk, const int32_t *__restrict__ blk_row, int *__restrict__ out) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nblk) atomicMax(out, blk_row[b + 1] - blk_row[b]);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Variant 3 ("tma", default): the CSR-stream kernel with the val / colind / rowptr streams moved by
+// the TMA engine (cp.async.bulk global -> shared, completion on an mbarrier) instead of per-thread
+// loads.  ncu on variant 2 showed the L1TEX sector pipeline 68 % busy (201 M sectors for 3 GB of DRAM
+// data: 8 + 4 sectors per 32 nonzeros for val/colind on top of ~13 for the x gather); bulk copies
+// bypass L1TEX, so it only serves the gather.  One producer warp runs STAGES blocks ahead of 8
+// consumer warps; products are formed in place in the val stage, rows reduced by one warp each.
+// ------------------------------------------------------------------------------------------------
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_CAP = SPMV_CH + SPMV_SLACK + 16;  // entries per stage (2320)
+constexpr int TMA_ROWCAP = SPMV_MAXROWS + 4;        // row pointers per stage
+constexpr int TMA_NT = SPMV_NT + 32;                // 8 consumer warps + 1 producer warp
+
+struct TmaStage {
+    alignas(128) double val[TMA_CAP];
+    alignas(128) int col[TMA_CAP];
+    alignas(128) long long rp[TMA_ROWCAP];
+};
+struct TmaSmem {
+    TmaStage st[TMA_STAGES];
+    alignas(16) double y[SPMV_MAXROWS];
+    alignas(16) int bounds[TMA_STAGES][8];  // R0, R1, off, n, rpoff
+    alignas(16) long long p0[TMA_STAGES];
+    alignas(8) unsigned long long full[TMA_STAGES], empty[TMA_STAGES];
+    double red[SPMV_NT / 32];
+    int last;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TMA_NT, 2) k_spmv_tma(SpmvArgs A, const int32_t *__restrict__ blk_row, int nblk) {
+    constexpr bool MASK = MODE & 1, DOT = MODE & 2, HALO = MODE & 4;
+    constexpr int PER = (SPMV_CH + SPMV_SLACK + SPMV_NT - 1) / SPMV_NT;  // 9
+    constexpr int RPT = SPMV_MAXROWS / SPMV_NT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TmaSmem &S = *reinterpret_cast<TmaSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < TMA_STAGES; ++s) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.empty[s], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nmine = (nblk - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // blocks of this CTA
+
+    if (warp == SPMV_NT / 32) {
+        // ------------------------------ producer warp ----------------------------------------------------------
+        // The 32 lanes fetch the bounds of 32 consecutive blocks in parallel (the blk_row -> rowptr chain is two
+        // dependent global loads, ~1.5 us: one lane doing them per block capped the ring at ~3.5 TB/s), then
+        // lane 0 issues the bulk copies from the shuffled values as stages become free.
+        auto fetch = [&](int i, int &R0, int &R1, long long &p0, int &n) {
+            R0 = R1 = n = 0;
+            p0 = 0;
+            if (i < nmine) {
+                const int b0 = blockIdx.x + i * gridDim.x;
+                const int b = HALO ? (int)(((int64_t)b0 + A.rot) % nblk) : b0;
+                R0 = blk_row[b];
+                R1 = blk_row[b + 1];
+                p0 = A.rowptr[R0];
+                n = (int)(A.rowptr[R1] - p0);
+            }
+        };
+        int nR0, nR1, nn;
+        long long np0;
+        fetch(lane, nR0, nR1, np0, nn);
+        for (int base = 0; base < nmine; base += 32) {
+            const int cR0 = nR0, cR1 = nR1, cn = nn;
+            const long long cp0 = np0;
+            fetch(base + 32 + lane, nR0, nR1, np0, nn);  // next batch in flight while this one is issued
+            const int lim = min(32, nmine - base);
+            for (int j = 0; j < lim; ++j) {
+                const int R0 = __shfl_sync(0xffffffffu, cR0, j), R1 = __shfl_sync(0xffffffffu, cR1, j);
+                const int n = __shfl_sync(0xffffffffu, cn, j);
+                const long long p0 = __shfl_sync(0xffffffffu, cp0, j);
+                if (lane == 0) {
+                    const int i = base + j;
+                    const int st = i % TMA_STAGES;
+                    if (i >= TMA_STAGES) mbar_wait(&S.empty[st], ((i / TMA_STAGES) - 1) & 1);
+                    const long long pa = p0 & ~3ll;  // 32 B / 16 B aligned sources
+                    const int off = (int)(p0 - pa);
+                    const unsigned cnt4 = (unsigned)((off + n + 3) & ~3);
+                    const int ra = R0 & ~1;
+                    const int rpoff = R0 - ra;
+                    const unsigned nrp = (unsigned)((rpoff + (R1 - R0) + 1 + 1) & ~1);
+                    S.bounds[st][0] = R0;
+                    S.bounds[st][1] = R1;
+                    S.bounds[st][2] = off;
+                    S.bounds[st][3] = n;
+                    S.bounds[st][4] = rpoff;
+                    S.p0[st] = p0;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(&S.full[st], cnt4 * 12u + nrp * 8u);
+                    bulk_g2s(S.st[st].val, A.val + pa, cnt4 * 8u, &S.full[st]);
+                    bulk_g2s(S.st[st].col, A.colind + pa, cnt4 * 4u, &S.full[st]);
+                    bulk_g2s(S.st[st].rp, A.rowptr + ra, nrp * 8u, &S.full[st]);
+                }
+                __syncwarp();
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------- consumers: 8 warps ---------------------------------------------------
+    double dot = 0.0;
+    for (int i = 0; i < nmine; ++i) {
+        const int st = i % TMA_STAGES;
+        mbar_wait(&S.full[st], (i / TMA_STAGES) & 1);
+        const int R0 = S.bounds[st][0], R1 = S.bounds[st][1], off = S.bounds[st][2], n = S.bounds[st][3],
+                  rpoff = S.bounds[st][4];
+        const long long p0 = S.p0[st];
+        const int nr = R1 - R0;
+        if (HALO && A.cv.nranks > 1) {
+            const bool lo = (A.cv.rank > 0) && (R0 < A.cv.plane_dofs);
+            const bool hi = (A.cv.rank < A.cv.nranks - 1) && (R1 > A.nrows - A.cv.plane_dofs);
+            if ((lo || hi) && tid == 0) {
+                const unsigned long long need = A.scal->it + 1;
+                if (lo)
+                    while (ld_acquire_sys(&A.cv.self->hflag[0]) < need) {
+                    }
+                if (hi)
+                    while (ld_acquire_sys(&A.cv.self->hflag[1]) < need) {
+                    }
+            }
+            if (lo || hi) asm volatile("bar.sync 1, %0;" ::"n"(SPMV_NT) : "memory");
+        }
+        // row metadata for the epilogue (latency hidden behind the products + row sums)
+        bool cfx[RPT];
+        double cxr[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int t = tid + j * SPMV_NT;
+            cfx[j] = false;
+            cxr[j] = 0.0;
+            if (t < nr) {
+                if (MASK) cfx[j] = A.fixed[R0 + t] != 0;
+                if (DOT) cxr[j] = A.x[A.ghost_cols + R0 + t];
+            }
+        }
+        // products in place: val[t] *= x[col[t]]
+        double *v = S.st[st].val + off;
+        const int *c = S.st[st].col + off;
+        double xv[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int t = tid + j * SPMV_NT;
+            if (t < n) xv[j] = A.x[c[t]];
+        }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int t = tid + j * SPMV_NT;
+            if (t < n) v[t] *= xv[j];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(SPMV_NT) : "memory");
+        const long long *rp = S.st[st].rp + rpoff;
+        for (int r = warp; r < nr; r += SPMV_NT / 32) {
+            const int a = (int)(rp[r] - p0), e = (int)(rp[r + 1] - p0);
+            double s = 0.0;
+            for (int t = a + lane; t < e; t += 32) s += v[t];
+            s = warp_sum(s);
+            if (lane == 0) S.y[r] = s;
+        }
+        // generic-proxy writes (in-place products) must be ordered before the TMA refills this stage
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(SPMV_NT) : "memory");
+        if (tid == 0) mbar_arrive(&S.empty[st]);  // the stage may be refilled
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int t = tid + j * SPMV_NT;
+            if (t < nr) {
+                double yv = S.y[t];
+                if (MASK && cfx[j]) yv = 0.0;
+                A.y[R0 + t] = yv;
+                if (DOT) dot += yv * cxr[j];
+            }
+        }
+        // S.y is rewritten only after the next block's first consumer barrier: no extra sync needed
+    }
+    if (DOT) {
+        double s = warp_sum(dot);
+        if (lane == 0) S.red[warp] = s;
+        asm volatile("bar.sync 1, %0;" ::"n"(SPMV_NT) : "memory");
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < SPMV_NT / 32; ++w) tot += S.red[w];
+            A.partials[blockIdx.x] = tot;
+            __threadfence();
+            unsigned t = atomicAdd(&A.scal->ticketB, 1u);
+            S.last = (t == gridDim.x - 1) ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(SPMV_NT) : "memory");
+        if (S.last) {
+            __threadfence();
+            double vv = 0.0;
+            for (int k = tid; k < (int)gridDim.x; k += SPMV_NT) vv += ld_volatile_f64(A.partials + k);
+            vv = warp_sum(vv);
+            asm volatile("bar.sync 1, %0;" ::"n"(SPMV_NT) : "memory");
+            if (lane == 0) S.red[warp] = vv;
+            asm volatile("bar.sync 1, %0;" ::"n"(SPMV_NT) : "memory");
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < SPMV_NT / 32; ++w) tot += S.red[w];
+                A.scal->ticketB = 0;
+                allreduce_publish(A.cv, 2ull * A.scal->it + 1ull, 1, &tot);
+            }
+        }
+    }
+}
+
+template <int MODE>
+static void launch_spmv_tma(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_spmv_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem)));
+        attr_set = true;
+    }
+    int grid = ctx->sms * 2;
+    if (grid > K->nblk) grid = K->nblk;
+    LAUNCH(ctx, (k_spmv_tma<MODE>), grid, TMA_NT, sizeof(TmaSmem), A, (const int32_t *)K->blk_row, K->nblk);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Variant 4 ("group3", default when applicable): rows come in triples with identical column patterns (the
+// three dofs of a node; checked once per pattern by k_check_group3).  One warp takes a triple: colind
+// is read and x gathered ONCE per column slot and used for the three rows.  ncu on the other variants
+// showed the L1TEX pipeline, not DRAM, as the limiter: per 32 nonzeros ~13 gather sectors + 12
+// val/colind sectors; sharing the gather and colind halves the L1 wavefronts and cuts DRAM traffic from
+// 12 to 9.33 B per nonzero (the matrix stays plain CSR; rows whose patterns differ use variant 2).
+// Persistent grid: each warp walks triples with stride #warps, next triple's row pointer prefetched.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_check_group3(int64_t ngroups, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                               int *__restrict__ bad) {
+    int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (g >= ngroups) return;
+    int64_t b0 = rowptr[3 * g], b1 = rowptr[3 * g + 1], b2 = rowptr[3 * g + 2], b3 = rowptr[3 * g + 3];
+    int64_t L = b1 - b0;
+    if (b2 - b1 != L || b3 - b2 != L) {
+        if (lane == 0) *bad = 1;
+        return;
+    }
+    for (int64_t s = lane; s < L; s += 32) {
+        int c = colind[b0 + s];
+        if (colind[b1 + s] != c || colind[b2 + s] != c) *bad = 1;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 3) k_spmv_group3(SpmvArgs A) {
+    constexpr bool MASK = MODE & 1, DOT = MODE & 2, HALO = MODE & 4;
+    __shared__ double s_red[8];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31;
+    const int64_t ngroups = A.nrows / 3;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    double dot = 0.0;
+    auto group_of = [&](int64_t gi) { return HALO ? (gi + A.rot) % ngroups : gi; };
+    // register sets: [cur] is being reduced while [nxt] is in flight (warp-level software pipeline)
+    int cc[3], nc[3];
+    double cw[3][3], nw[3][3];
+    int64_t cb0 = 0, nb0 = 0, fb0 = 0, fb1 = 0;  // cur / next / future row pointers
+    int cL = 0, nL = 0;
+    int64_t cg = 0, ng_ = 0, fg = 0;
+    auto issue = [&](int64_t b0, int L, int (&c)[3], double (&w)[3][3]) {
+        const double *__restrict__ v0 = A.val + b0;
+        const int32_t *__restrict__ c0 = A.colind + b0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int s = lane + 32 * j;
+            if (s < L) {
+                c[j] = ld_stream_s32(c0 + s);
+                w[j][0] = ld_stream_f64(v0 + s);
+                w[j][1] = ld_stream_f64(v0 + L + s);
+                w[j][2] = ld_stream_f64(v0 + 2 * L + s);
+            }
+        }
+    };
+    // prologue: bounds of the first two triples, loads of the first
+    if (g < ngroups) {
+        cg = group_of(g);
+        cb0 = A.rowptr[3 * cg];
+        cL = (int)(A.rowptr[3 * cg + 1] - cb0);
+        issue(cb0, cL, cc, cw);
+    }
+    if (g + nwarps < ngroups) {
+        fg = group_of(g + nwarps);
+        fb0 = A.rowptr[3 * fg];
+        fb1 = A.rowptr[3 * fg + 1];
+    }
+    for (; g < ngroups; g += nwarps) {
+        const int64_t r0 = 3 * cg;
+        if (HALO && A.cv.nranks > 1) {
+            const bool lo = (A.cv.rank > 0) && (r0 < A.cv.plane_dofs);
+            const bool hi = (A.cv.rank < A.cv.nranks - 1) && (r0 + 3 > A.nrows - A.cv.plane_dofs);
+            if (lo || hi) {
+                if (lane == 0) {
+                    const unsigned long long need = A.scal->it + 1;
+                    if (lo)
+                        while (ld_acquire_sys(&A.cv.self->hflag[0]) < need) {
+                        }
+                    if (hi)
+                        while (ld_acquire_sys(&A.cv.self->hflag[1]) < need) {
+                        }
+                }
+                __syncwarp();
+            }
+        }
+        // gathers for the current triple (its colind registers have landed or are about to)
+        double xv[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) xv[j] = (lane + 32 * j < cL) ? A.x[cc[j]] : 0.0;
+        // next triple: its bounds were loaded one iteration ago -> issue its streams now; fetch future bounds
+        const bool have_next = g + nwarps < ngroups;
+        if (have_next) {
+            ng_ = fg;
+            nb0 = fb0;
+            nL = (int)(fb1 - fb0);
+            issue(nb0, nL, nc, nw);
+        }
+        if (g + 2 * nwarps < ngroups) {
+            fg = group_of(g + 2 * nwarps);
+            fb0 = A.rowptr[3 * fg];
+            fb1 = A.rowptr[3 * fg + 1];
+        }
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (lane + 32 * j < cL) {
+                a0 += cw[j][0] * xv[j];
+                a1 += cw[j][1] * xv[j];
+                a2 += cw[j][2] * xv[j];
+            }
+        if (cL > 96) {  // long rows (unstructured meshes with > 32 neighbour nodes): plain tail loop
+            const double *__restrict__ v0 = A.val + cb0;
+            const int32_t *__restrict__ c0 = A.colind + cb0;
+            for (int s = lane + 96; s < cL; s += 32) {
+                const double x1 = A.x[c0[s]];
+                a0 += v0[s] * x1;
+                a1 += v0[cL + s] * x1;
+                a2 += v0[2 * cL + s] * x1;
+            }
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        if (lane < 3) {
+            double yv = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+            if (MASK && A.fixed[r0 + lane]) yv = 0.0;
+            A.y[r0 + lane] = yv;
+            if (DOT) dot += yv * A.x[A.ghost_cols + r0 + lane];
+        }
+        // rotate the pipeline
+        cg = ng_;
+        cb0 = nb0;
+        cL = nL;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            cc[j] = nc[j];
+            cw[j][0] = nw[j][0];
+            cw[j][1] = nw[j][1];
+            cw[j][2] = nw[j][2];
+        }
+    }
+    if (DOT) {
+        double s = block_sum<256>(dot, s_red);
+        if (threadIdx.x == 0) {
+            A.partials[blockIdx.x] = s;
+            __threadfence();
+            unsigned t = atomicAdd(&A.scal->ticketB, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double v = 0.0;
+            for (int64_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += ld_volatile_f64(A.partials + i);
+            double tot = block_sum<256>(v, s_red);
+            if (threadIdx.x == 0) {
+                A.scal->ticketB = 0;
+                allreduce_publish(A.cv, 2ull * A.scal->it + 1ull, 1, &tot);
+            }
+        }
+    }
+}
+
+template <int MODE>
+static void launch_spmv_group3(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_group3<MODE>, 256, 0));
+        if (per_sm < 1) per_sm = 1;
+    }
+    LAUNCH(ctx, (k_spmv_group3<MODE>), ctx->sms * per_sm, 256, 0, A);  // exactly the resident grid: no second wave
+}
+
 static void spmv_stream_setup(smfem_ctx *ctx, smfem_matrix *K) {
     if (K->blk_row) return;
     int *d_max = dev_alloc<int>(1);
@@ -412,6 +899,27 @@ static void spmv_stream_setup(smfem_ctx *ctx, smfem_matrix *K) {
     K->blk_row = dev_alloc<int32_t>(K->nblk + 1);
     LAUNCH(ctx, k_spmv_blockrows, (unsigned)((K->nblk + 1 + 255) / 256), 256, 0, K->nrows_l, (const int64_t *)K->rowptr, K->nblk,
            K->blk_row);
+    int *d_mr = dev_alloc<int>(1);
+    int mr = 0;
+    CUDA_CHECK(cudaMemsetAsync(d_mr, 0, sizeof(int), ctx->stream));
+    LAUNCH(ctx, k_spmv_maxrows, (unsigned)((K->nblk + 255) / 256), 256, 0, K->nblk, (const int32_t *)K->blk_row, d_mr);
+    CUDA_CHECK(cudaMemcpyAsync(&mr, d_mr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    dev_free(d_mr);
+    K->stream_ok = (K->max_rowlen <= SPMV_SLACK && mr <= SPMV_MAXROWS);
+    K->group3_ok = false;
+    if (K->nDof == 3 && K->nrows_l % 3 == 0 && K->nrows_l > 0) {
+        int *d_bad = dev_alloc<int>(1);
+        int bad = 1;
+        CUDA_CHECK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+        int64_t ng = K->nrows_l / 3;
+        LAUNCH(ctx, k_check_group3, (unsigned)((ng * 32 + 255) / 256), 256, 0, ng, (const int64_t *)K->rowptr,
+               (const int32_t *)K->colind, d_bad);
+        CUDA_CHECK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        dev_free(d_bad);
+        K->group3_ok = (bad == 0);
+    }
 }
 
 static SpmvArgs make_spmv_args(smfem_matrix *K, const double *x, double *y) {
@@ -433,11 +941,15 @@ static SpmvArgs make_spmv_args(smfem_matrix *K, const double *x, double *y) {
 
 template <int MODE>
 static void launch_spmv(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A, int variant) {
-    if (variant == 2 && K->max_rowlen <= SPMV_SLACK) {
+    if (variant == 4 && K->group3_ok) {
+        launch_spmv_group3<MODE>(ctx, K, A);
+    } else if (variant == 3 && K->stream_ok) {
+        launch_spmv_tma<MODE>(ctx, K, A);
+    } else if ((variant == 2 || variant == 3 || variant == 4) && K->stream_ok) {
         int grid = ctx->sms * K->ctas_per_sm;
         if (grid > K->nblk) grid = K->nblk;
         LAUNCH(ctx, (k_spmv_stream<MODE>), grid, SPMV_NT, 0, A, (const int32_t *)K->blk_row, K->nblk);
-    } else if (variant == 1 || variant == 2) {
+    } else if (variant >= 1) {
         int64_t nw = A.nrows;
         unsigned grid = (unsigned)((nw * 32 + 255) / 256);
         LAUNCH(ctx, (k_spmv<1, MODE>), grid, 256, 0, A);
@@ -451,7 +963,8 @@ static void launch_spmv(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A, int 
 // rotation that makes the rows of the boundary planes the LAST work of the grid (halo overlap)
 static int64_t spmv_rotation(smfem_ctx *ctx, smfem_matrix *K, int variant) {
     if (ctx->nranks == 1 || K->nrows_l == 0) return 0;
-    if (variant == 2 && K->max_rowlen <= SPMV_SLACK)
+    if (variant == 4 && K->group3_ok) return (K->comm.plane_dofs / 3) % (K->nrows_l / 3);
+    if ((variant == 2 || variant == 3 || variant == 4) && K->stream_ok)
         return (int64_t)((double)K->nblk * (double)K->comm.plane_dofs / (double)K->nrows_l) + 1;
     int64_t nw = (variant == 0) ? (K->nrows_l + 2) / 3 : K->nrows_l;
     int64_t per_plane = (variant == 0) ? (K->comm.plane_dofs + 2) / 3 : K->comm.plane_dofs;

@@ -14,6 +14,6 @@ for _ in range(2):
 K.add_surface_mass(100.0)
 i = K.info()
 b = 12 * i["nnz_local"] + 24 * i["nrows_local"]
-for v in (2, 1, 0):
+for v in (4, 3, 2, 1, 0):
     ms = K.bench_spmv(reps=reps, variant=v)
     print(f"spmv variant {v}: {ms:.4f} ms  {b / ms / 1e6:.1f} GB/s")
