@@ -130,6 +130,10 @@ int smfem_assemble_values(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, dou
 /* Re-run the pattern kernels into K's existing buffers (no allocation, asynchronous): lets the
  * bench time pattern build + values back to back with CUDA events.  Structured meshes only. */
 int smfem_pattern_rebuild(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
+/* Full assembly (pattern AND values) into K's existing buffers, asynchronous, no allocation: rowptr in
+ * closed form + the tiled value kernel, whose output phase also writes colind (fused; one pass over K).
+ * This is what smfem_assemble runs after allocating, and what bench.py times as a step. */
+int smfem_reassemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu);
 
 /* m, n: global dims; nnz: global stored entries; row0/nrows_local/nnz_local: this rank's slab */
 int smfem_matrix_info(smfem_matrix *K, int64_t *m, int64_t *n, int64_t *nnz, int64_t *row0, int64_t *nrows_local,

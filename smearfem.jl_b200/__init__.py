@@ -207,6 +207,11 @@ class SparseMatrixB200:
         call("smfem_assemble_values", self.ctx.handle, self.mesh.handle, self.handle, float(Young), float(nu))
         return self
 
+    def reassemble(self, Young, nu):
+        """pattern + values into the existing buffers (fused colind/value kernel); asynchronous."""
+        call("smfem_reassemble", self.ctx.handle, self.mesh.handle, self.handle, float(Young), float(nu))
+        return self
+
     def pattern_rebuild(self):
         call("smfem_pattern_rebuild", self.ctx.handle, self.mesh.handle, self.handle)
         return self

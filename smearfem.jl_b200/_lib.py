@@ -54,6 +54,7 @@ SIGNATURES = {
     "smfem_pattern_build": [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)],
     "smfem_assemble_values": [_vp, _vp, _vp, C.c_double, C.c_double],
     "smfem_pattern_rebuild": [_vp, _vp, _vp],
+    "smfem_reassemble": [_vp, _vp, _vp, C.c_double, C.c_double],
     "smfem_matrix_info": [_vp, _i64p, _i64p, _i64p, _i64p, _i64p, _i64p],
     "smfem_matrix_export_csc": [_vp, _vp, C.c_int, _i64p, _i64p, _f64p],
     "smfem_matrix_diag": [_vp, _vp, _f64p],

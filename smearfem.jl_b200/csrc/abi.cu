@@ -1,5 +1,6 @@
 // extern "C" boundary of libsmearfem_b200.so (see include/smearfem_b200.h).  Every entry point
 // catches C++ exceptions and converts them into status codes + a thread-local message.
+#include <cstdlib>
 #include <cstring>
 
 #include "smfem_internal.cuh"
@@ -505,6 +506,21 @@ int smfem_pattern_rebuild(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
         NOTNULL(K);
         REQUIRE(mesh->structured && K->structured, SMFEM_ERR_UNSUPPORTED, "pattern_rebuild: structured meshes only");
         pattern_build_structured(ctx, mesh, K);  // buffers exist: kernels only, no allocation, no host sync
+    });
+}
+
+int smfem_reassemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(mesh);
+        NOTNULL(K);
+        REQUIRE(mesh->structured && K->structured, SMFEM_ERR_UNSUPPORTED, "reassemble: structured meshes only");
+        if (const char *dbg = std::getenv("SMFEM_DEBUG_CLEAR"); dbg && dbg[0] == '1') {  // tests: prove every entry is rewritten
+            CUDA_CHECK(cudaMemsetAsync(K->colind, 0xFF, sizeof(int32_t) * K->nnz_l, ctx->stream));
+            CUDA_CHECK(cudaMemsetAsync(K->rowptr, 0xFF, sizeof(int64_t) * (K->nrows_l + 1), ctx->stream));
+            if (K->val) CUDA_CHECK(cudaMemsetAsync(K->val, 0xFF, sizeof(double) * K->nnz_l, ctx->stream));
+        }
+        values_assemble(ctx, mesh, K, Young, nu, /*fuse_pattern=*/true);
     });
 }
 

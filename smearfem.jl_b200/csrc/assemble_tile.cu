@@ -35,7 +35,8 @@ struct Tile {
     // (ncu: 2x excess shared wavefronts without the pad)
     static constexpr int PAD = (EX == 9) ? 3 : 8;  // 8x4 tile: banks {6,7,8,15,0,1}+3; 4x4 tile: {10,11,12,15,0,1}+8
     static constexpr int LAYER = 8 * 8 * 3 * NEL + PAD;
-    static constexpr size_t SMEM_BYTES = sizeof(double) * (2 * LAYER + TX * TY * STAGE_NODE + 8 * 8 * 3 + 8);
+    static constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY * 3;  // node-plane coordinate buffer (with halo)
+    static constexpr size_t SMEM_BYTES = sizeof(double) * (2 * LAYER + TX * TY * STAGE_NODE + 8 * 8 * 3 + 8 + 4 * PLANE);
 };
 
 struct TileArgs {
@@ -43,6 +44,7 @@ struct TileArgs {
     const double *coords;
     const int64_t *rowptr;
     double *val;
+    int32_t *colind;  // non-null: the output phase also writes the pattern's column indices (fused assembly)
     double *diag;
     Material mat;
     int tiles_x, tiles_y, nchunks, chunk;
@@ -50,31 +52,34 @@ struct TileArgs {
     double w[8];
 };
 
-__device__ __forceinline__ double inv3(const double *J, double *inv) {
-    double c00 = J[4] * J[8] - J[5] * J[7], c01 = J[5] * J[6] - J[3] * J[8], c02 = J[3] * J[7] - J[4] * J[6];
-    double d = J[0] * c00 + J[1] * c01 + J[2] * c02;
-    double id = 1.0 / d;
-    inv[0] = c00 * id;
-    inv[1] = (J[2] * J[7] - J[1] * J[8]) * id;
-    inv[2] = (J[1] * J[5] - J[2] * J[4]) * id;
-    inv[3] = c01 * id;
-    inv[4] = (J[0] * J[8] - J[2] * J[6]) * id;
-    inv[5] = (J[2] * J[3] - J[0] * J[5]) * id;
-    inv[6] = c02 * id;
-    inv[7] = (J[1] * J[6] - J[0] * J[7]) * id;
-    inv[8] = (J[0] * J[4] - J[1] * J[3]) * id;
-    return d;
+// asynchronous copy of node plane k (tile + 1-node halo, clipped to the lattice) into the coordinate ring
+template <class T>
+__device__ __forceinline__ void stage_plane(const TileArgs &A, double *s_xyz, int k, int X0, int Y0) {
+    const Lattice &L = A.L;
+    if (k < 0 || k >= L.n1) return;
+    double *dst = s_xyz + (k & 3) * T::PLANE;
+    for (int t = threadIdx.x; t < T::PLANE; t += T::NTH) {
+        const int c = t % 3, n = t / 3;
+        const int px = n % T::PX, py = n / T::PX;
+        const int gx = X0 - 1 + px, gy = Y0 - 1 + py;
+        if (gx < 0 || gy < 0 || gx >= L.n1 || gy >= L.n1) continue;
+        const double *src = A.coords + 3 * L.lnode(gx, gy, k) + c;
+        unsigned d = (unsigned)__cvta_generic_to_shared(dst + t);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+    }
 }
 
-// element layer `layer` of the footprint -> ring slot
+// element layer `layer` of the footprint -> ring slot.  g_b = dN_b adj(J) * sign(det) * sqrt(wp / |det|)
+// ( = sqrt(wp |det|) * dN_b J^-1, src/fem.jl:192-196, with one rsqrt instead of a division and a sqrt )
 template <class T>
-__device__ __forceinline__ void phase1(const TileArgs &A, const double *s_dN, const double *s_w, double *S, int layer, int X0,
-                                       int Y0) {
+__device__ __forceinline__ void phase1(const TileArgs &A, const double *s_dN, const double *s_sw, const double *s_xyz, double *S,
+                                       int layer, int X0, int Y0) {
     constexpr int NEL = T::NEL, EX = T::EX, LAYER = T::LAYER, NTH = T::NTH;
     const Lattice &L = A.L;
     double *dst = S + (layer & 1) * LAYER;
-    for (int q = threadIdx.x; q < 8 * NEL; q += NTH) {
-        const int gp = q / NEL, e = q - gp * NEL;
+    const double *P0 = s_xyz + (layer & 3) * T::PLANE, *P1 = s_xyz + ((layer + 1) & 3) * T::PLANE;
+    for (int q = threadIdx.x; q < 4 * NEL; q += NTH) {  // task = (element, pair of Gauss points): coordinates loaded once
+        const int gpp = q / NEL, e = q - gpp * NEL;
         const int fy = e / EX, fx = e - fy * EX;
         const int ex = X0 - 1 + fx, ey = Y0 - 1 + fy;
         if (ex < 0 || ey < 0 || ex >= L.ne || ey >= L.ne) continue;
@@ -82,31 +87,46 @@ __device__ __forceinline__ void phase1(const TileArgs &A, const double *s_dN, co
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const int ox = ((b & 3) == 1 || (b & 3) == 2), oy = ((b & 3) >= 2), oz = (b >> 2);
-            const double *p = A.coords + 3 * L.lnode(ex + ox, ey + oy, layer + oz);
+            const double *p = (oz ? P1 : P0) + 3 * ((fy + oy) * T::PX + fx + ox);
             X[b][0] = p[0];
             X[b][1] = p[1];
             X[b][2] = p[2];
         }
-        const double *dN = s_dN + gp * 24;
-        double J[9], inv[9];
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+        for (int h = 0; h < 2; ++h) {
+            const int gp = 2 * gpp + h;
+            const double *dN = s_dN + gp * 24;
+            double J[9];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                double s = 0.0;
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) s += X[b][r] * dN[b * 3 + c];  // Jac = coords*dN, src/fem.jl:192
-                J[r * 3 + c] = s;
-            }
-        const double det = inv3(J, inv);
-        const double sw = sqrt(s_w[gp] * fabs(det));  // w = wp*|det J|, src/fem.jl:194
+                for (int c = 0; c < 3; ++c) {
+                    double s = 0.0;
 #pragma unroll
-        for (int b = 0; b < 8; ++b)
+                    for (int b = 0; b < 8; ++b) s += X[b][r] * dN[b * 3 + c];  // Jac = coords*dN, src/fem.jl:192
+                    J[r * 3 + c] = s;
+                }
+            double adj[9];
+            adj[0] = J[4] * J[8] - J[5] * J[7];
+            adj[1] = J[2] * J[7] - J[1] * J[8];
+            adj[2] = J[1] * J[5] - J[2] * J[4];
+            adj[3] = J[5] * J[6] - J[3] * J[8];
+            adj[4] = J[0] * J[8] - J[2] * J[6];
+            adj[5] = J[2] * J[3] - J[0] * J[5];
+            adj[6] = J[3] * J[7] - J[4] * J[6];
+            adj[7] = J[1] * J[6] - J[0] * J[7];
+            adj[8] = J[0] * J[4] - J[1] * J[3];
+            const double det = J[0] * adj[0] + J[1] * adj[3] + J[2] * adj[6];
+            const double sc = copysign(rsqrt(fabs(det)), det) * s_sw[gp];  // sign(det) sqrt(wp/|det|)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                double s = dN[b * 3] * inv[c] + dN[b * 3 + 1] * inv[3 + c] + dN[b * 3 + 2] * inv[6 + c];  // dNdX, :196
-                dst[((gp * 8 + b) * 3 + c) * NEL + e] = s * sw;
-            }
+            for (int i = 0; i < 9; ++i) adj[i] *= sc;
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    dst[((gp * 8 + b) * 3 + c) * NEL + e] =
+                        dN[b * 3] * adj[c] + dN[b * 3 + 1] * adj[3 + c] + dN[b * 3 + 2] * adj[6 + c];
+        }
     }
 }
 
@@ -117,11 +137,12 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
     double *S = smem;                             // [2][gp][b][c][e]
     double *stage = smem + 2 * LAYER;             // [node][27][9]
     double *s_dN = stage + TX * TY * STAGE_NODE;  // [gp][b][c]
-    double *s_w = s_dN + 8 * 8 * 3;
+    double *s_w = s_dN + 8 * 8 * 3;   // sqrt of the Gauss weights
+    double *s_xyz = s_w + 8;          // [4][PLANE] node-plane coordinate ring
     const Lattice &L = A.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int t = tid; t < 8 * 8 * 3; t += NTH) s_dN[t] = (&A.dN[0][0][0])[t];
-    if (tid < 8) s_w[tid] = A.w[tid];
+    if (tid < 8) s_w[tid] = sqrt(A.w[tid]);
 
     int bid = blockIdx.x;
     const int tix = bid % A.tiles_x;
@@ -144,11 +165,21 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
     const int a = sz * 4 + ((sy << 1) | (sx ^ sy));  // local node number of this node inside element -s
     double *my_stage = stage + nt * STAGE_NODE;
     double *warp_stage = stage + warp * 4 * STAGE_NODE;
+    // closed-form CSR row starts (no dependent global load in the output phase): see k_struct_rowptr
+    const int64_t S1 = 3 * (int64_t)L.n1 - 2;
+    auto pre1 = [](int i) -> int64_t { return i == 0 ? 0 : 3 * (int64_t)i - 1; };
+    auto cnt1 = [&](int i) -> int { return 1 + (i > 0) + (i < L.n1 - 1); };
+    const int64_t pairs_base = pre1(L.k0) * S1 * S1;
+    stage_plane<T>(A, s_xyz, zs - 1, X0, Y0);
+    stage_plane<T>(A, s_xyz, zs, X0, Y0);
+    stage_plane<T>(A, s_xyz, zs + 1, X0, Y0);
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
     for (int k = zs; k < ze; ++k) {
-        if (k == zs && k - 1 >= 0) phase1<T>(A, s_dN, s_w, S, k - 1, X0, Y0);
-        if (k < L.ne) phase1<T>(A, s_dN, s_w, S, k, X0, Y0);
+        stage_plane<T>(A, s_xyz, k + 2, X0, Y0);  // lands during this plane's phase 2; ring slot (k+2)&3 is free
+        if (k == zs && k - 1 >= 0) phase1<T>(A, s_dN, s_w, s_xyz, S, k - 1, X0, Y0);
+        if (k < L.ne) phase1<T>(A, s_dN, s_w, s_xyz, S, k, X0, Y0);
         for (int t = lane; t < 4 * STAGE_NODE; t += 32) warp_stage[t] = 0.0;
         __syncthreads();
 
@@ -207,7 +238,8 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
                 const int rank = ((dz + (k > 0)) * cy + (dy + (jy > 0))) * cx + (dx + (jx > 0));
                 const int T = 3 * cx * cy * cz;
                 const int64_t row = (((int64_t)(k - L.k0) * L.n1 + jy) * L.n1 + jx) * 3;
-                const int64_t base = A.rowptr[row] + 3 * rank;
+                const int64_t pairs = pre1(k) * S1 * S1 + (int64_t)cz * (pre1(jy) * S1 + (int64_t)cy * pre1(jx)) - pairs_base;
+                const int64_t base = 9 * pairs + 3 * rank;
                 const double *g = stage + n2 * STAGE_NODE + lane * 9;
                 const double tr = g[0] + g[4] + g[8];
 #pragma unroll
@@ -218,10 +250,12 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
                         const double v = (c == j) ? A.mat.d11 * gij + A.mat.mu * (tr - gij) : A.mat.lam * gij + A.mat.mu * gji;
                         A.val[base + (int64_t)c * T + j] = v;
                         if (lane == 13 && c == j) A.diag[row + c] = v;
+                        if (A.colind) A.colind[base + (int64_t)c * T + j] = (int32_t)(L.lnode(nx, ny, nz) * 3 + j);
                     }
             }
         }
-        __syncthreads();  // staging + ring slot (k-1)&1 are reused by the next plane
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();  // staging + ring slot (k-1)&1 are reused by the next plane; coordinate plane k+2 has landed
     }
 }
 
@@ -251,13 +285,14 @@ static void launch_tile(smfem_ctx *ctx, TileArgs &A, int nown) {
     LAUNCH(ctx, (k_values_tile<T, MINB>), grid, T::NTH, T::SMEM_BYTES, A);
 }
 
-void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat) {
+void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind) {
     if (!K->diag) K->diag = dev_alloc<double>(K->nrows_l);
     TileArgs A;
     A.L = mesh->lat;
     A.coords = mesh->coords;
     A.rowptr = K->rowptr;
     A.val = K->val;
+    A.colind = write_colind ? K->colind : nullptr;
     A.diag = K->diag;
     A.mat = mat;
     {

@@ -175,7 +175,7 @@ void mesh_inflate(smfem_ctx *ctx, smfem_mesh *m, double x0, double x1, double y0
 
 void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
 void pattern_build_general(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
-void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu);
+void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu, bool fuse_pattern = false);
 void surface_mass(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, const int32_t *faces_dev, int64_t nFaces,
                   double beta, bool keep_b);
 void extract_diag(smfem_ctx *ctx, smfem_matrix *K);

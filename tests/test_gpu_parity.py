@@ -193,6 +193,17 @@ def test_tile_and_atomic_value_kernels_agree(monkeypatch):
     d1 = K.diag()
     K.assemble_values(40, 0.4)
     assert np.array_equal(K.to_csc()[2], nz1), "tiled gather kernel must be deterministic"
+    # fused reassembly (rowptr closed form + colind written by the value kernel) rewrites EVERY entry of the pattern
+    monkeypatch.setenv("SMFEM_DEBUG_CLEAR", "1")
+    K.reassemble(40, 0.4)
+    monkeypatch.delenv("SMFEM_DEBUG_CLEAR")
+    assert_csc_parity(K, Ko)
+    assert np.array_equal(K.to_csc()[2], nz1)
+    for tile in ("8x4", "4x4"):
+        monkeypatch.setenv("SMFEM_TILE", tile)
+        K.reassemble(40, 0.4)
+        assert_csc_parity(K, Ko)
+    monkeypatch.delenv("SMFEM_TILE")
     monkeypatch.setenv("SMFEM_VALUES", "atomic")
     K.assemble_values(40, 0.4)
     assert_csc_parity(K, Ko)

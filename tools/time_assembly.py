@@ -19,3 +19,12 @@ ctx.timer_start()
 for _ in range(10):
     K.pattern_rebuild()
 print(f"pattern {ctx.timer_stop()/10:.3f} ms")
+for tile in ("4x4", "8x4"):
+    os.environ["SMFEM_TILE"] = tile
+    for _ in range(3):
+        K.reassemble(40.0, 0.4)
+    ctx.timer_start()
+    for _ in range(10):
+        K.reassemble(40.0, 0.4)
+    ms = ctx.timer_stop() / 10
+    print(f"tile {tile}: fused pattern+values {ms:.3f} ms  -> {ne**3/ms/1e3:.1f} M el/s")
