@@ -165,6 +165,8 @@ int smfem_destroy(smfem_ctx *ctx) {
     return guarded([&] {
         if (!ctx) return;
         cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        dev_cache_release();
         if (ctx->flush_buf) cudaFree(ctx->flush_buf);
         cudaEventDestroy(ctx->ev0);
         cudaEventDestroy(ctx->ev1);

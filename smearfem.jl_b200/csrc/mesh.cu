@@ -4,7 +4,79 @@
 #include <cmath>
 #include <cstring>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "smfem_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// caching device allocator (see smfem_internal.cuh)
+// ------------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_cache_mu;
+std::unordered_map<void *, size_t> g_live;                    // ptr -> bytes (all blocks we handed out)
+std::unordered_multimap<size_t, void *> g_free;               // bytes -> cached free blocks
+size_t g_cached_bytes = 0;
+constexpr size_t CACHE_MIN = (size_t)1 << 20;                 // only blocks >= 1 MiB are worth caching
+constexpr size_t CACHE_MAX = (size_t)96 << 30;                // keep at most 96 GiB parked
+}  // namespace
+
+static size_t cache_key(size_t bytes) {  // blocks are only reused on the device they were allocated on
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return bytes ^ ((size_t)(dev + 1) << 56);
+}
+
+void *dev_cache_alloc(size_t bytes) {
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_free.find(cache_key(bytes));
+        if (it != g_free.end()) {
+            void *p = it->second;
+            g_free.erase(it);
+            g_cached_bytes -= bytes;
+            g_live[p] = bytes;
+            return p;
+        }
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {  // out of memory: drop the cache and retry once
+        cudaGetLastError();
+        dev_cache_release();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess)
+        throw SmfemError(SMFEM_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(bytes) + " bytes) -> " + cudaGetErrorString(e));
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_live[p] = bytes;
+    return p;
+}
+
+void dev_cache_free(void *p) {
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto it = g_live.find(p);
+        if (it != g_live.end()) {
+            bytes = it->second;
+            g_live.erase(it);
+            if (bytes >= CACHE_MIN && g_cached_bytes + bytes <= CACHE_MAX) {
+                g_free.emplace(cache_key(bytes), p);  // stream-ordered reuse is safe: the library uses ONE stream per context
+                g_cached_bytes += bytes;
+                return;
+            }
+        }
+    }
+    cudaFree(p);
+}
+
+void dev_cache_release() {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (auto &kv : g_free) cudaFree(kv.second);
+    g_free.clear();
+    g_cached_bytes = 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // src/fem.jl:21-31 -- same expression order as the reference so its `==` tests hold bit-for-bit

@@ -49,16 +49,21 @@ struct smfem_ctx {
         CUDA_CHECK(cudaGetLastError());                                    \
     } while (0)
 
+// Device allocations go through a small per-process cache (exact-size free lists): the reference-facing
+// calls (mesh_from_host -> assemble -> free) would otherwise spend more time in cudaMalloc/cudaFree of
+// multi-GB buffers than in the kernels.  Cached blocks are returned to the driver by dev_cache_release().
+void *dev_cache_alloc(size_t bytes);
+void dev_cache_free(void *p);
+void dev_cache_release();
+
 template <class T>
 inline T *dev_alloc(size_t n) {
-    T *p = nullptr;
     if (n == 0) n = 1;
-    CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
-    return p;
+    return static_cast<T *>(dev_cache_alloc(n * sizeof(T)));
 }
 template <class T>
 inline void dev_free(T *&p) {
-    if (p) cudaFree(p);
+    if (p) dev_cache_free((void *)p);
     p = nullptr;
 }
 

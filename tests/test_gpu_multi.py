@@ -62,7 +62,7 @@ def _worker(rank, ws, port, ne, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ws,ne", [(2, 8), (2, 13)])
+@pytest.mark.parametrize("ws,ne", [(2, 8), (2, 13), (4, 12), (8, 16)])
 def test_slab_partition_matches_oracle(ws, ne):
     import torch
 
