@@ -48,6 +48,7 @@ struct TileArgs {
     double *diag;
     Material mat;
     int tiles_x, tiles_y, nchunks, chunk;
+    int skip;  // ablation bitmask (env SMFEM_TILE_SKIP; profiling only): 1 phase 1, 2 main loop, 4 combine, 8 output
     double dN[8][8][3];  // reference gradients at the 8 Gauss points (src/fem.jl:63, :174-176)
     double w[8];
 };
@@ -178,8 +179,10 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
 
     for (int k = zs; k < ze; ++k) {
         stage_plane<T>(A, s_xyz, k + 2, X0, Y0);  // lands during this plane's phase 2; ring slot (k+2)&3 is free
-        if (k == zs && k - 1 >= 0) phase1<T>(A, s_dN, s_w, s_xyz, S, k - 1, X0, Y0);
-        if (k < L.ne) phase1<T>(A, s_dN, s_w, s_xyz, S, k, X0, Y0);
+        if (!(A.skip & 1)) {
+            if (k == zs && k - 1 >= 0) phase1<T>(A, s_dN, s_w, s_xyz, S, k - 1, X0, Y0);
+            if (k < L.ne) phase1<T>(A, s_dN, s_w, s_xyz, S, k, X0, Y0);
+        }
         for (int t = lane; t < 4 * STAGE_NODE; t += 32) warp_stage[t] = 0.0;
         __syncthreads();
 
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
         for (int b = 0; b < 8; ++b)
 #pragma unroll
             for (int m = 0; m < 9; ++m) G[b][m] = 0.0;
-        if (el_ok) {
+        if (el_ok && !(A.skip & 2)) {
             const double *Sb = S + (layer & 1) * LAYER + e;
 #pragma unroll 2
             for (int gp = 0; gp < 8; ++gp) {
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const int obx = ((b & 3) == 1 || (b & 3) == 2), oby = ((b & 3) >= 2), obz = (b >> 2);
-            if (el_ok) {
+            if (el_ok && !(A.skip & 4)) {
                 double *dst = my_stage + ((obz - sz + 1) * 9 + (oby - sy + 1) * 3 + (obx - sx + 1)) * 9;
 #pragma unroll
                 for (int m = 0; m < 9; ++m) dst[m] += G[b][m];
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
             __syncwarp();
         }
         // ---- output: lane q < 27 owns neighbour q of each of the warp's 4 nodes -----------------------------
-        if (lane < 27) {
+        if (lane < 27 && !(A.skip & 8)) {
             const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
             for (int jn = 0; jn < 4; ++jn) {
                 const int n2 = warp * 4 + jn;
@@ -307,6 +310,10 @@ void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Mat
                 for (int d = 0; d < 3; ++d) A.dN[g][a][d] = dN[d * 8 + a];
             A.w[g] = w[ix[g]] * w[iy[g]] * w[iz[g]];
         }
+    }
+    {
+        const char *sk = std::getenv("SMFEM_TILE_SKIP");
+        A.skip = sk ? std::atoi(sk) : 0;
     }
     const char *e = std::getenv("SMFEM_TILE");
     if (e && std::string(e) == "8x4")
