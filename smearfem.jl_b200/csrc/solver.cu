@@ -737,24 +737,29 @@ __global__ void k_check_group3(int64_t ngroups, const int64_t *__restrict__ rowp
     }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256, 3) k_spmv_group3(SpmvArgs A) {
+template <int MODE, int G>
+__global__ void __launch_bounds__(256, 3) k_spmv_group(SpmvArgs A) {
+    // G = 3: row triples sharing one column pattern (k_check_group3);  G = 1: any CSR matrix, one row per warp step.
     constexpr bool MASK = MODE & 1, DOT = MODE & 2, HALO = MODE & 4;
     __shared__ double s_red[8];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31;
-    const int64_t ngroups = A.nrows / 3;
+    const int64_t ngroups = A.nrows / G;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     double dot = 0.0;
-    auto group_of = [&](int64_t gi) { return HALO ? (gi + A.rot) % ngroups : gi; };
+    auto group_of = [&](int64_t gi) {  // rotation (boundary planes last) without a 64-bit modulo: rot < ngroups
+        if (!HALO) return gi;
+        const int64_t t = gi + A.rot;
+        return t >= ngroups ? t - ngroups : t;
+    };
     // register sets: [cur] is being reduced while [nxt] is in flight (warp-level software pipeline)
     int cc[3], nc[3];
-    double cw[3][3], nw[3][3];
+    double cw[3][G], nw[3][G];
     int64_t cb0 = 0, nb0 = 0, fb0 = 0, fb1 = 0;  // cur / next / future row pointers
     int cL = 0, nL = 0;
     int64_t cg = 0, ng_ = 0, fg = 0;
-    auto issue = [&](int64_t b0, int L, int (&c)[3], double (&w)[3][3]) {
+    auto issue = [&](int64_t b0, int L, int (&c)[3], double (&w)[3][G]) {
         const double *__restrict__ v0 = A.val + b0;
         const int32_t *__restrict__ c0 = A.colind + b0;
 #pragma unroll
@@ -762,29 +767,28 @@ __global__ void __launch_bounds__(256, 3) k_spmv_group3(SpmvArgs A) {
             const int s = lane + 32 * j;
             if (s < L) {
                 c[j] = ld_stream_s32(c0 + s);
-                w[j][0] = ld_stream_f64(v0 + s);
-                w[j][1] = ld_stream_f64(v0 + L + s);
-                w[j][2] = ld_stream_f64(v0 + 2 * L + s);
+#pragma unroll
+                for (int q = 0; q < G; ++q) w[j][q] = ld_stream_f64(v0 + (int64_t)q * L + s);
             }
         }
     };
-    // prologue: bounds of the first two triples, loads of the first
+    // prologue: bounds of the first two groups, loads of the first
     if (g < ngroups) {
         cg = group_of(g);
-        cb0 = A.rowptr[3 * cg];
-        cL = (int)(A.rowptr[3 * cg + 1] - cb0);
+        cb0 = A.rowptr[G * cg];
+        cL = (int)(A.rowptr[G * cg + 1] - cb0);
         issue(cb0, cL, cc, cw);
     }
     if (g + nwarps < ngroups) {
         fg = group_of(g + nwarps);
-        fb0 = A.rowptr[3 * fg];
-        fb1 = A.rowptr[3 * fg + 1];
+        fb0 = A.rowptr[G * fg];
+        fb1 = A.rowptr[G * fg + 1];
     }
     for (; g < ngroups; g += nwarps) {
-        const int64_t r0 = 3 * cg;
+        const int64_t r0 = G * cg;
         if (HALO && A.cv.nranks > 1) {
             const bool lo = (A.cv.rank > 0) && (r0 < A.cv.plane_dofs);
-            const bool hi = (A.cv.rank < A.cv.nranks - 1) && (r0 + 3 > A.nrows - A.cv.plane_dofs);
+            const bool hi = (A.cv.rank < A.cv.nranks - 1) && (r0 + G > A.nrows - A.cv.plane_dofs);
             if (lo || hi) {
                 if (lane == 0) {
                     const unsigned long long need = A.scal->it + 1;
@@ -798,11 +802,11 @@ __global__ void __launch_bounds__(256, 3) k_spmv_group3(SpmvArgs A) {
                 __syncwarp();
             }
         }
-        // gathers for the current triple (its colind registers have landed or are about to)
+        // gathers for the current group (its colind registers have landed or are about to)
         double xv[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) xv[j] = (lane + 32 * j < cL) ? A.x[cc[j]] : 0.0;
-        // next triple: its bounds were loaded one iteration ago -> issue its streams now; fetch future bounds
+        // next group: its bounds were loaded one iteration ago -> issue its streams now; fetch future bounds
         const bool have_next = g + nwarps < ngroups;
         if (have_next) {
             ng_ = fg;
@@ -812,35 +816,57 @@ __global__ void __launch_bounds__(256, 3) k_spmv_group3(SpmvArgs A) {
         }
         if (g + 2 * nwarps < ngroups) {
             fg = group_of(g + 2 * nwarps);
-            fb0 = A.rowptr[3 * fg];
-            fb1 = A.rowptr[3 * fg + 1];
+            fb0 = A.rowptr[G * fg];
+            fb1 = A.rowptr[G * fg + 1];
         }
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        double acc[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q) acc[q] = 0.0;
 #pragma unroll
         for (int j = 0; j < 3; ++j)
             if (lane + 32 * j < cL) {
-                a0 += cw[j][0] * xv[j];
-                a1 += cw[j][1] * xv[j];
-                a2 += cw[j][2] * xv[j];
+#pragma unroll
+                for (int q = 0; q < G; ++q) acc[q] += cw[j][q] * xv[j];
             }
-        if (cL > 96) {  // long rows (unstructured meshes with > 32 neighbour nodes): plain tail loop
+        if (cL > 96) {  // long rows (> 32 neighbour nodes): plain tail loop
             const double *__restrict__ v0 = A.val + cb0;
             const int32_t *__restrict__ c0 = A.colind + cb0;
             for (int s = lane + 96; s < cL; s += 32) {
                 const double x1 = A.x[c0[s]];
-                a0 += v0[s] * x1;
-                a1 += v0[cL + s] * x1;
-                a2 += v0[2 * cL + s] * x1;
+#pragma unroll
+                for (int q = 0; q < G; ++q) acc[q] += v0[(int64_t)q * cL + s] * x1;
             }
         }
-        a0 = warp_sum(a0);
-        a1 = warp_sum(a1);
-        a2 = warp_sum(a2);
-        if (lane < 3) {
-            double yv = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
-            if (MASK && A.fixed[r0 + lane]) yv = 0.0;
+#pragma unroll
+        for (int q = 0; q < G; ++q) acc[q] = warp_sum(acc[q]);  // xor-shuffles: every lane holds the row sums
+        if (lane < G) {
+            double yv = acc[0];
+#pragma unroll
+            for (int q = 1; q < G; ++q)
+                if (lane == q) yv = acc[q];
+            // MASK: Dirichlet rows are NOT masked here any more: p = 0 on them, so p'Ap is unaffected, and
+            // k_pcg_update_xr pins r = 0 where dinv == 0 (no per-group load of the flag in the hot loop).
             A.y[r0 + lane] = yv;
-            if (DOT) dot += yv * A.x[A.ghost_cols + r0 + lane];
+        }
+        if (DOT) {
+            // x_row (= p on the group's own rows) is among the gathered values: the diagonal columns
+            const int dcol = (int)(A.ghost_cols + r0);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (lane + 32 * j < cL) {
+#pragma unroll
+                    for (int q = 0; q < G; ++q)
+                        if (cc[j] == dcol + q) dot += acc[q] * xv[j];
+                }
+            if (cL > 96) {
+                const int32_t *__restrict__ c0 = A.colind + cb0;
+                for (int s2 = lane + 96; s2 < cL; s2 += 32) {
+                    const int c = c0[s2];
+#pragma unroll
+                    for (int q = 0; q < G; ++q)
+                        if (c == dcol + q) dot += acc[q] * A.x[c];
+                }
+            }
         }
         // rotate the pipeline
         cg = ng_;
@@ -849,10 +875,17 @@ __global__ void __launch_bounds__(256, 3) k_spmv_group3(SpmvArgs A) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             cc[j] = nc[j];
-            cw[j][0] = nw[j][0];
-            cw[j][1] = nw[j][1];
-            cw[j][2] = nw[j][2];
+#pragma unroll
+            for (int q = 0; q < G; ++q) cw[j][q] = nw[j][q];
         }
+    }
+    if (G > 1 && blockIdx.x == 0 && threadIdx.x < (unsigned)(A.nrows % G)) {  // nrows % G leftover rows (never for G = 3 here)
+        const int64_t r = (A.nrows / G) * G + threadIdx.x;
+        double sacc = 0.0;
+        for (int64_t p = A.rowptr[r]; p < A.rowptr[r + 1]; ++p) sacc += A.val[p] * A.x[A.colind[p]];
+        if (MASK && A.fixed[r]) sacc = 0.0;
+        A.y[r] = sacc;
+        if (DOT) dot += sacc * A.x[A.ghost_cols + r];
     }
     if (DOT) {
         double s = block_sum<256>(dot, s_red);
@@ -876,14 +909,14 @@ __global__ void __launch_bounds__(256, 3) k_spmv_group3(SpmvArgs A) {
     }
 }
 
-template <int MODE>
-static void launch_spmv_group3(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A) {
+template <int MODE, int G>
+static void launch_spmv_group(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A) {
     static int per_sm = 0;
     if (per_sm == 0) {
-        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_group3<MODE>, 256, 0));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spmv_group<MODE, G>, 256, 0));
         if (per_sm < 1) per_sm = 1;
     }
-    LAUNCH(ctx, (k_spmv_group3<MODE>), ctx->sms * per_sm, 256, 0, A);  // exactly the resident grid: no second wave
+    LAUNCH(ctx, (k_spmv_group<MODE, G>), ctx->sms * per_sm, 256, 0, A);  // exactly the resident grid: no second wave
 }
 
 static void spmv_stream_setup(smfem_ctx *ctx, smfem_matrix *K) {
@@ -942,7 +975,9 @@ static SpmvArgs make_spmv_args(smfem_matrix *K, const double *x, double *y) {
 template <int MODE>
 static void launch_spmv(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A, int variant) {
     if (variant == 4 && K->group3_ok) {
-        launch_spmv_group3<MODE>(ctx, K, A);
+        launch_spmv_group<MODE, 3>(ctx, K, A);
+    } else if (variant == 4) {
+        launch_spmv_group<MODE, 1>(ctx, K, A);  // same pipeline, one row per warp step
     } else if (variant == 3 && K->stream_ok) {
         launch_spmv_tma<MODE>(ctx, K, A);
     } else if ((variant == 2 || variant == 3 || variant == 4) && K->stream_ok) {
@@ -964,6 +999,7 @@ static void launch_spmv(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A, int 
 static int64_t spmv_rotation(smfem_ctx *ctx, smfem_matrix *K, int variant) {
     if (ctx->nranks == 1 || K->nrows_l == 0) return 0;
     if (variant == 4 && K->group3_ok) return (K->comm.plane_dofs / 3) % (K->nrows_l / 3);
+    if (variant == 4) return K->comm.plane_dofs % K->nrows_l;
     if ((variant == 2 || variant == 3 || variant == 4) && K->stream_ok)
         return (int64_t)((double)K->nblk * (double)K->comm.plane_dofs / (double)K->nrows_l) + 1;
     int64_t nw = (variant == 0) ? (K->nrows_l + 2) / 3 : K->nrows_l;
@@ -1061,11 +1097,12 @@ k_pcg_update_xr(int64_t n, int64_t ghost_cols, const double *__restrict__ p, con
     const double *po = p + ghost_cols;
     double rz = 0.0, rr = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double di = dinv[i];
         double xv = x[i] + alpha * po[i];
-        double rv = r[i] - alpha * Ap[i];
+        double rv = (di == 0.0) ? 0.0 : r[i] - alpha * Ap[i];  // Dirichlet rows (dinv == 0): residual pinned to 0
         x[i] = xv;
         r[i] = rv;
-        rz += rv * rv * dinv[i];
+        rz += rv * rv * di;
         rr += rv * rv;
     }
     double s1 = block_sum<VEC_NT>(rz, s_red);
