@@ -49,7 +49,7 @@ struct TileArgs {
     Material mat;
     int tiles_x, tiles_y, nchunks, chunk;
     int skip;  // ablation bitmask (env SMFEM_TILE_SKIP; profiling only): 1 phase 1, 2 main loop, 4 combine, 8 output
-    double dN[8][8][3];  // reference gradients at the 8 Gauss points (src/fem.jl:63, :174-176)
+    double gp[8][3];     // the 8 Gauss points in the reference's order (src/fem.jl:174-176)
     double w[8];
 };
 
@@ -71,42 +71,62 @@ __device__ __forceinline__ void stage_plane(const TileArgs &A, double *s_xyz, in
 }
 
 // element layer `layer` of the footprint -> ring slot.  g_b = dN_b adj(J) * sign(det) * sqrt(wp / |det|)
-// ( = sqrt(wp |det|) * dN_b J^-1, src/fem.jl:192-196, with one rsqrt instead of a division and a sqrt )
+// ( = sqrt(wp |det|) * dN_b J^-1, src/fem.jl:192-196 ).  Register-only formulation of the Q1 gradients:
+//   dN_b/dxi = sx_b (1 + sy_b eta)(1 + sz_b zeta)/8  (src/fem.jl:63)  ->  12 products per Gauss point, no table loads;
+//   J(:,xi)  = sum over the 4 xi-edges of  YZ[oy][oz] * (x_{b+} - x_{b-})   (edge differences shared by the Gauss points);
+//   the unscaled gradients dN adj(J) are formed while the rsqrt of |det| is in flight, then scaled.
 template <class T>
-__device__ __forceinline__ void phase1(const TileArgs &A, const double *s_dN, const double *s_sw, const double *s_xyz, double *S,
+__device__ __forceinline__ void phase1(const TileArgs &A, const double *s_gp, const double *s_sw, const double *s_xyz, double *S,
                                        int layer, int X0, int Y0) {
     constexpr int NEL = T::NEL, EX = T::EX, LAYER = T::LAYER, NTH = T::NTH;
     const Lattice &L = A.L;
     double *dst = S + (layer & 1) * LAYER;
     const double *P0 = s_xyz + (layer & 3) * T::PLANE, *P1 = s_xyz + ((layer + 1) & 3) * T::PLANE;
-    for (int q = threadIdx.x; q < 4 * NEL; q += NTH) {  // task = (element, pair of Gauss points): coordinates loaded once
+    for (int q = threadIdx.x; q < 4 * NEL; q += NTH) {  // task = (element, pair of Gauss points)
         const int gpp = q / NEL, e = q - gpp * NEL;
         const int fy = e / EX, fx = e - fy * EX;
         const int ex = X0 - 1 + fx, ey = Y0 - 1 + fy;
         if (ex < 0 || ey < 0 || ex >= L.ne || ey >= L.ne) continue;
-        double X[8][3];
+        // nodes in natural order u = ox + 2 oy + 4 oz
+        double Xn[8][3];
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int ox = ((b & 3) == 1 || (b & 3) == 2), oy = ((b & 3) >= 2), oz = (b >> 2);
+        for (int u = 0; u < 8; ++u) {
+            const int ox = u & 1, oy = (u >> 1) & 1, oz = u >> 2;
             const double *p = (oz ? P1 : P0) + 3 * ((fy + oy) * T::PX + fx + ox);
-            X[b][0] = p[0];
-            X[b][1] = p[1];
-            X[b][2] = p[2];
+            Xn[u][0] = p[0];
+            Xn[u][1] = p[1];
+            Xn[u][2] = p[2];
+        }
+        double Ex[4][3], Ey[4][3], Ez[4][3];  // edge differences along xi / eta / zeta
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int o1 = t & 1, o2 = t >> 1;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                Ex[t][r] = Xn[1 + 2 * o1 + 4 * o2][r] - Xn[2 * o1 + 4 * o2][r];  // t = (oy, oz)
+                Ey[t][r] = Xn[o1 + 2 + 4 * o2][r] - Xn[o1 + 4 * o2][r];          // t = (ox, oz)
+                Ez[t][r] = Xn[o1 + 2 * o2 + 4][r] - Xn[o1 + 2 * o2][r];          // t = (ox, oy)
+            }
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int gp = 2 * gpp + h;
-            const double *dN = s_dN + gp * 24;
-            double J[9];
+            const double xi = s_gp[3 * gp], eta = s_gp[3 * gp + 1], zeta = s_gp[3 * gp + 2];
+            const double Xf[2] = {1.0 - xi, 1.0 + xi}, Yf[2] = {1.0 - eta, 1.0 + eta}, Zf[2] = {0.125 * (1.0 - zeta), 0.125 * (1.0 + zeta)};
+            double YZ[4], XZ[4], XY[4];  // index t = o1 + 2 o2
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+            for (int t = 0; t < 4; ++t) {
+                YZ[t] = Yf[t & 1] * Zf[t >> 1];
+                XZ[t] = Xf[t & 1] * Zf[t >> 1];
+                XY[t] = 0.125 * Xf[t & 1] * Yf[t >> 1];
+            }
+            double J[9];  // J[r*3+k] = d x_r / d xi_k   (Jac = coords*dN, src/fem.jl:192)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) s += X[b][r] * dN[b * 3 + c];  // Jac = coords*dN, src/fem.jl:192
-                    J[r * 3 + c] = s;
-                }
+            for (int r = 0; r < 3; ++r) {
+                J[r * 3 + 0] = YZ[0] * Ex[0][r] + YZ[1] * Ex[1][r] + YZ[2] * Ex[2][r] + YZ[3] * Ex[3][r];
+                J[r * 3 + 1] = XZ[0] * Ey[0][r] + XZ[1] * Ey[1][r] + XZ[2] * Ey[2][r] + XZ[3] * Ey[3][r];
+                J[r * 3 + 2] = XY[0] * Ez[0][r] + XY[1] * Ez[1][r] + XY[2] * Ez[2][r] + XY[3] * Ez[3][r];
+            }
             double adj[9];
             adj[0] = J[4] * J[8] - J[5] * J[7];
             adj[1] = J[2] * J[7] - J[1] * J[8];
@@ -118,15 +138,19 @@ __device__ __forceinline__ void phase1(const TileArgs &A, const double *s_dN, co
             adj[7] = J[1] * J[6] - J[0] * J[7];
             adj[8] = J[0] * J[4] - J[1] * J[3];
             const double det = J[0] * adj[0] + J[1] * adj[3] + J[2] * adj[6];
-            const double sc = copysign(rsqrt(fabs(det)), det) * s_sw[gp];  // sign(det) sqrt(wp/|det|)
+            const double sc = copysign(rsqrt(fabs(det)), det) * s_sw[gp];  // sign(det) sqrt(wp/|det|): long latency ...
+            // ... overlapped with the unscaled gradients  t_u[c] = sum_k dN_u[k] adj[k][c]
 #pragma unroll
-            for (int i = 0; i < 9; ++i) adj[i] *= sc;
-#pragma unroll
-            for (int b = 0; b < 8; ++b)
+            for (int u = 0; u < 8; ++u) {
+                const int ox = u & 1, oy = (u >> 1) & 1, oz = u >> 2;
+                const double d0 = ox ? YZ[oy + 2 * oz] : -YZ[oy + 2 * oz];
+                const double d1 = oy ? XZ[ox + 2 * oz] : -XZ[ox + 2 * oz];
+                const double d2 = oz ? XY[ox + 2 * oy] : -XY[ox + 2 * oy];
+                const int b = oz * 4 + (oy ? (ox ? 2 : 3) : (ox ? 1 : 0));  // reference local numbering (vector3D.jl:94-101)
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    dst[((gp * 8 + b) * 3 + c) * NEL + e] =
-                        dN[b * 3] * adj[c] + dN[b * 3 + 1] * adj[3 + c] + dN[b * 3 + 2] * adj[6 + c];
+                    dst[((gp * 8 + b) * 3 + c) * NEL + e] = (d0 * adj[c] + d1 * adj[3 + c] + d2 * adj[6 + c]) * sc;
+            }
         }
     }
 }
@@ -137,12 +161,12 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
     extern __shared__ double smem[];
     double *S = smem;                             // [2][gp][b][c][e]
     double *stage = smem + 2 * LAYER;             // [node][27][9]
-    double *s_dN = stage + TX * TY * STAGE_NODE;  // [gp][b][c]
+    double *s_dN = stage + TX * TY * STAGE_NODE;  // [gp][3]: Gauss-point coordinates (xi, eta, zeta)
     double *s_w = s_dN + 8 * 8 * 3;   // sqrt of the Gauss weights
     double *s_xyz = s_w + 8;          // [4][PLANE] node-plane coordinate ring
     const Lattice &L = A.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int t = tid; t < 8 * 8 * 3; t += NTH) s_dN[t] = (&A.dN[0][0][0])[t];
+    for (int t = tid; t < 8 * 3; t += NTH) s_dN[t] = (&A.gp[0][0])[t];
     if (tid < 8) s_w[tid] = sqrt(A.w[tid]);
 
     int bid = blockIdx.x;
@@ -165,7 +189,6 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
     const int e = (ty - sy + 1) * EX + (tx - sx + 1);
     const int a = sz * 4 + ((sy << 1) | (sx ^ sy));  // local node number of this node inside element -s
     double *my_stage = stage + nt * STAGE_NODE;
-    double *warp_stage = stage + warp * 4 * STAGE_NODE;
     // closed-form CSR row starts (no dependent global load in the output phase): see k_struct_rowptr
     const int64_t S1 = 3 * (int64_t)L.n1 - 2;
     auto pre1 = [](int i) -> int64_t { return i == 0 ? 0 : 3 * (int64_t)i - 1; };
@@ -183,7 +206,6 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
             if (k == zs && k - 1 >= 0) phase1<T>(A, s_dN, s_w, s_xyz, S, k - 1, X0, Y0);
             if (k < L.ne) phase1<T>(A, s_dN, s_w, s_xyz, S, k, X0, Y0);
         }
-        for (int t = lane; t < 4 * STAGE_NODE; t += 32) warp_stage[t] = 0.0;
         __syncthreads();
 
         // ---- phase 2: G_ab for b = 0..7 -------------------------------------------------------
@@ -215,15 +237,24 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
                 }
             }
         }
-        // ---- combine: round b -> neighbour offset d = o(b) - s, distinct for the 8 slot threads -------
+        // ---- combine: round beta (natural order) -> neighbour offset d = beta - s, distinct for the 8 slot threads.
+        // Block d is touched for the FIRST time in round beta_min(d) = max(d,0) per axis, i.e. by the lanes with
+        // (s & beta) == 0: those plain-store (no zeroing pass, no load), everybody else read-modify-writes.
+        // Threads whose element does not exist still take part with G = 0 so that every block gets initialised.
         __syncwarp();
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const int obx = ((b & 3) == 1 || (b & 3) == 2), oby = ((b & 3) >= 2), obz = (b >> 2);
-            if (el_ok && !(A.skip & 4)) {
+        for (int beta = 0; beta < 8; ++beta) {
+            const int obx = beta & 1, oby = (beta >> 1) & 1, obz = beta >> 2;
+            const int b = obz * 4 + (oby ? (obx ? 2 : 3) : (obx ? 1 : 0));  // reference local numbering
+            if (!(A.skip & 4)) {
                 double *dst = my_stage + ((obz - sz + 1) * 9 + (oby - sy + 1) * 3 + (obx - sx + 1)) * 9;
+                if ((s & beta) == 0) {
 #pragma unroll
-                for (int m = 0; m < 9; ++m) dst[m] += G[b][m];
+                    for (int m = 0; m < 9; ++m) dst[m] = G[b][m];
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 9; ++m) dst[m] += G[b][m];
+                }
             }
             __syncwarp();
         }
@@ -303,11 +334,9 @@ void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Mat
         smfem_host_gauss(-1, 1, 2, xi, w);
         const int ix[8] = {0, 1, 1, 0, 0, 1, 1, 0}, iy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, iz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
         for (int g = 0; g < 8; ++g) {
-            double N[8], dN[24];
-            int nn;
-            smfem_host_basis(3, SMFEM_Q1, xi[ix[g]], xi[iy[g]], xi[iz[g]], N, dN, &nn);
-            for (int a = 0; a < 8; ++a)
-                for (int d = 0; d < 3; ++d) A.dN[g][a][d] = dN[d * 8 + a];
+            A.gp[g][0] = xi[ix[g]];
+            A.gp[g][1] = xi[iy[g]];
+            A.gp[g][2] = xi[iz[g]];
             A.w[g] = w[ix[g]] * w[iy[g]] * w[iz[g]];
         }
     }
