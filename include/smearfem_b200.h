@@ -174,6 +174,11 @@ int smfem_set_dirichlet(smfem_ctx *ctx, smfem_matrix *K, const int64_t *dofs, co
 int smfem_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const double *rhs_extra,
                     double *q_out, int *iters_out, double *relres_out);
 
+/* Load stepping (examples/vector3D.jl:310-338: the same K̄ solved for 50 prescribed displacements d; q is exactly
+ * linear in d): the NEXT smfem_pcg_solve on K starts from scale * (previous solution on the free dofs) instead of 0.
+ * Typical use: set_dirichlet_zplanes(d_new); set_warm_start(d_new / d_old); pcg_solve(...) -> 0-2 iterations. */
+int smfem_pcg_set_warm_start(smfem_matrix *K, double scale);
+
 /* y = K x with host vectors of this rank's slab (nranks == 1 only; for tests) */
 int smfem_spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y);
 /* Time `reps` back-to-back device-resident SpMVs (x = deterministic pattern, halo exchange

@@ -28,7 +28,7 @@ from ._lib import SmearFEMError, call
 
 __all__ = [
     "gaussian_quadrature", "basis_function", "assemble_system", "inflate_sphere", "meshgrid", "setboundaryCond",
-    "apply_boundary_conditions", "solve", "greet_fem", "Context", "Mesh", "SparseMatrixB200", "SmearFEMError", "context",
+    "apply_boundary_conditions", "solve", "load_steps", "greet_fem", "Context", "Mesh", "SparseMatrixB200", "SmearFEMError", "context",
 ]
 
 _i64p = C.POINTER(C.c_int64)
@@ -279,7 +279,10 @@ class SparseMatrixB200:
         call("smfem_set_dirichlet", self.ctx.handle, self.handle, _pi(dofs), _pf(values), dofs.shape[0])
         return self
 
-    def pcg_solve(self, rtol=1e-12, maxit=20000, rhs_extra=None, want_q=True):
+    def pcg_solve(self, rtol=1e-12, maxit=20000, rhs_extra=None, want_q=True, warm_scale=0.0):
+        """Jacobi-PCG on the Dirichlet-masked operator.  warm_scale != 0: start from warm_scale * previous solution."""
+        if warm_scale:
+            call("smfem_pcg_set_warm_start", self.handle, float(warm_scale))
         n = self.info()["nrows_local"]
         q = np.zeros(n) if want_q else None
         ex = None if rhs_extra is None else np.ascontiguousarray(rhs_extra, dtype=np.float64)
@@ -311,6 +314,19 @@ class SparseMatrixB200:
         if self.handle:
             _lib.lib().smfem_matrix_free(self.handle)
             self.handle = None
+
+
+def load_steps(K_bar, deltas, rtol=1e-12, maxit=20000):
+    """The load-stepping loop of examples/vector3D.jl:310-338 on a device-resident K̄ (structured mesh):
+    for every prescribed top displacement d, set the Dirichlet data, solve, and yield (d, q, iterations).
+    K̄ is assembled once; since q is linear in d every solve after the first is warm-started with q*d/d_prev."""
+    prev = None
+    for d in deltas:
+        K_bar.set_dirichlet_zplanes(float(d))
+        warm = (float(d) / prev) if prev else 0.0
+        q, it, rel = K_bar.pcg_solve(rtol=rtol, maxit=maxit, warm_scale=warm)
+        prev = float(d)
+        yield float(d), q, it
 
 
 class SurfaceMatrix:

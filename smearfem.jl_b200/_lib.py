@@ -63,6 +63,7 @@ SIGNATURES = {
     "smfem_set_dirichlet_zplanes": [_vp, _vp, _vp, C.c_double],
     "smfem_set_dirichlet": [_vp, _vp, _i64p, _f64p, C.c_int64],
     "smfem_pcg_solve": [_vp, _vp, C.c_double, C.c_int, _f64p, _f64p, C.POINTER(C.c_int), _f64p],
+    "smfem_pcg_set_warm_start": [_vp, C.c_double],
     "smfem_spmv_host": [_vp, _vp, _f64p, _f64p],
     "smfem_bench_spmv": [_vp, _vp, C.c_int, C.c_int, C.POINTER(C.c_float)],
     "smfem_set_spmv_variant": [_vp, C.c_int],

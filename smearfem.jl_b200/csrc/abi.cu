@@ -685,6 +685,14 @@ int smfem_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, con
     });
 }
 
+int smfem_pcg_set_warm_start(smfem_matrix *K, double scale) {
+    return guarded([&] {
+        NOTNULL(K);
+        REQUIRE(K->x != nullptr || scale == 0.0, SMFEM_ERR_INVALID, "warm start needs a previous solve on this matrix");
+        K->warm_scale = scale;
+    });
+}
+
 int smfem_spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y) {
     return guarded([&] {
         NOTNULL(ctx);

@@ -160,6 +160,7 @@ struct smfem_matrix {
     CommView comm;
     void *peer_maps[SMFEM_MAX_RANKS] = {nullptr};
     bool comm_connected = false;
+    double warm_scale = 0.0;  // next solve starts from warm_scale * (previous solution); reset after use
     int spmv_variant = 4;  // 4 = row-triple (default; falls back to 2), 2 = CSR-stream, 3 = CSR-stream via TMA, 1 = warp/row, 0 = warp/3 rows
     int32_t *blk_row = nullptr;  // CSR-stream row blocks
     int nblk = 0, max_rowlen = 0, ctas_per_sm = 4;

@@ -1137,18 +1137,24 @@ k_pcg_update_xr(int64_t n, int64_t ghost_cols, const double *__restrict__ p, con
 
 // r0 = free ? (extra - K q_d) : 0 ; x0 = 0 ; D^-1 ; publishes (r'D^-1 r, r'r) and opens a new solve
 __global__ void __launch_bounds__(VEC_NT)
-k_pcg_init(int64_t n, const double *__restrict__ Kqd, const double *__restrict__ extra, const double *__restrict__ diag,
+k_pcg_init(int64_t n, const double *__restrict__ Kqd, const double *__restrict__ Kq0, const double *__restrict__ extra,
+           const double *__restrict__ diag,
            const uint8_t *__restrict__ fixed, double *__restrict__ x, double *__restrict__ r, double *__restrict__ dinv,
-           double *__restrict__ partials, PcgScalars *scal, CommView cv) {
+           double *__restrict__ partials, PcgScalars *scal, CommView cv, double warm) {
     __shared__ double s_red[VEC_NT / 32];
     __shared__ bool s_last;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    double rz = 0.0, rr = 0.0;
+    // Kqd = K (q_d + x0) gives the residual; Kq0 (warm start only) = K q_d gives the right-hand side b, whose norm
+    // is the reference of the stopping test (with a good warm start ||r0|| is already at rounding level).
+    double rz = 0.0, rr = 0.0, bb = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         bool fx = fixed[i] != 0;
-        double rv = fx ? 0.0 : ((extra ? extra[i] : 0.0) - Kqd[i]);
+        const double ex = extra ? extra[i] : 0.0;
+        double rv = fx ? 0.0 : (ex - Kqd[i]);
+        const double bv = fx ? 0.0 : (Kq0 ? ex - Kq0[i] : rv);
+        bb += bv * bv;
         double di = (fx || diag[i] == 0.0) ? 0.0 : 1.0 / diag[i];
-        x[i] = 0.0;
+        x[i] = (warm != 0.0 && !fx) ? warm * x[i] : 0.0;  // warm start: x0 = warm * (previous solution on the free dofs)
         r[i] = rv;
         dinv[i] = di;
         rz += rv * rv * di;
@@ -1156,9 +1162,11 @@ k_pcg_init(int64_t n, const double *__restrict__ Kqd, const double *__restrict__
     }
     double s1 = block_sum<VEC_NT>(rz, s_red);
     double s2 = block_sum<VEC_NT>(rr, s_red);
+    double s3 = block_sum<VEC_NT>(bb, s_red);
     if (threadIdx.x == 0) {
-        partials[2 * blockIdx.x] = s1;
-        partials[2 * blockIdx.x + 1] = s2;
+        partials[3 * blockIdx.x] = s1;
+        partials[3 * blockIdx.x + 1] = s2;
+        partials[3 * blockIdx.x + 2] = s3;
         __threadfence();
         unsigned t = atomicAdd(&scal->ticketC, 1u);
         s_last = (t == gridDim.x - 1);
@@ -1166,32 +1174,46 @@ k_pcg_init(int64_t n, const double *__restrict__ Kqd, const double *__restrict__
     __syncthreads();
     if (s_last) {
         __threadfence();
-        double a = 0.0, b = 0.0;
+        double a = 0.0, b = 0.0, c = 0.0;
         for (int64_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-            a += ld_volatile_f64(partials + 2 * i);
-            b += ld_volatile_f64(partials + 2 * i + 1);
+            a += ld_volatile_f64(partials + 3 * i);
+            b += ld_volatile_f64(partials + 3 * i + 1);
+            c += ld_volatile_f64(partials + 3 * i + 2);
         }
         double t1 = block_sum<VEC_NT>(a, s_red);
         double t2 = block_sum<VEC_NT>(b, s_red);
+        double t3 = block_sum<VEC_NT>(c, s_red);
         if (threadIdx.x == 0) {
             const unsigned long long it = scal->it;
             scal->ticketC = 0;
             scal->spare = 1.0;  // marks "first iteration": beta = 0
             scal->breakdown = 0;
-            double v[2] = {t1, t2};
-            allreduce_publish(cv, 2ull * it + 2ull, 2, v);
+            double v[3] = {t1, t2, t3};
+            allreduce_publish(cv, 2ull * it + 2ull, 3, v);
             __threadfence();
             scal->it = it + 1;
         }
     }
 }
 
+// w = q_d + warm * x_prev on the owned entries (ghost entries: q_d only; neighbours' planes arrive by halo push)
+__global__ void k_warm_vector(int64_t n, int64_t ghost_cols, int64_t ncols, const double *__restrict__ qd,
+                              const double *__restrict__ x, double warm, double *__restrict__ w) {
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncols) return;
+    double v = qd[c];
+    int64_t r = c - ghost_cols;
+    if (r >= 0 && r < n) v += warm * x[r];
+    w[c] = v;
+}
+
 // fetch the current global (rz, rr) into scal (so the host can read the residual)
-__global__ void k_pcg_fetch(PcgScalars *scal, CommView cv, double *out2) {
-    double v[2];
-    allreduce_fetch(cv, 2ull * scal->it, 2, v);
-    out2[0] = v[0];
-    out2[1] = v[1];
+__global__ void k_pcg_fetch(PcgScalars *scal, CommView cv, double *out3) {
+    double v[3];
+    allreduce_fetch(cv, 2ull * scal->it, 3, v);  // the third value is only meaningful right after k_pcg_init (||b||^2)
+    out3[0] = v[0];
+    out3[1] = v[1];
+    out3[2] = v[2];
 }
 
 __global__ void k_final_q(int64_t n, int64_t ghost_cols, const double *__restrict__ qd, const double *__restrict__ x,
@@ -1252,7 +1274,7 @@ void solver_alloc(smfem_ctx *ctx, smfem_matrix *K) {
     int64_t np = spmv_grid(K, 0);
     int64_t np1 = spmv_grid(K, 1);
     if (np1 > np) np = np1;
-    if (np < 2 * (int64_t)ctx->sms * 8) np = 2 * (int64_t)ctx->sms * 8;
+    if (np < 4 * (int64_t)ctx->sms * 8) np = 4 * (int64_t)ctx->sms * 8;  // k_pcg_init writes 3 partials per CTA
     K->partials = dev_alloc<double>(np + 16);
     K->partials_n = np;
     K->scal = dev_alloc<PcgScalars>(1);
@@ -1392,24 +1414,48 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
     }
     const int vg = vec_grid(ctx, n);
     CUDA_CHECK(cudaEventRecord(ctx->ev2, ctx->stream));
-    // K q_d (unmasked rows; q_d's ghost entries are filled locally, no exchange needed)
-    {
+    const double warm = K->warm_scale;
+    K->warm_scale = 0.0;  // applies to one solve
+    if (warm == 0.0) {
+        // K q_d (unmasked rows; q_d's ghost entries are filled locally, no exchange needed)
         SpmvArgs A = make_spmv_args(K, K->qd, K->Ap);
         launch_spmv<0>(ctx, K, A, variant);
+    } else {
+        // warm start (load stepping, examples/vector3D.jl:310-338: q is linear in d):  r0 = extra - K (q_d + warm x_prev)
+        {  // b = extra - K q_d is still needed for the stopping test: K q_d -> r (r is rewritten by k_pcg_init)
+            SpmvArgs A0 = make_spmv_args(K, K->qd, K->r);
+            launch_spmv<0>(ctx, K, A0, variant);
+        }
+        LAUNCH(ctx, k_warm_vector, (unsigned)((K->ncols_l + 255) / 256), 256, 0, n, K->ghost_cols, K->ncols_l, (const double *)K->qd,
+               (const double *)K->x, warm, K->p);
+        SpmvArgs A = make_spmv_args(K, K->p, K->Ap);
+        if (ctx->nranks > 1) {
+            unsigned long long it0 = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&it0, &K->scal->it, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            int g = (int)((K->comm.plane_dofs + 255) / 256);
+            if (g > ctx->sms * 4) g = ctx->sms * 4;
+            LAUNCH(ctx, k_halo_push, g, 256, 0, n, K->ghost_cols, (const double *)K->p, K->scal, K->comm, it0 + 1);
+            A.rot = spmv_rotation(ctx, K, variant);
+            launch_spmv<4>(ctx, K, A, variant);
+        } else {
+            launch_spmv<0>(ctx, K, A, variant);
+        }
     }
-    LAUNCH(ctx, k_pcg_init, vg, VEC_NT, 0, n, (const double *)K->Ap, (const double *)extra, (const double *)K->diag,
-           (const uint8_t *)K->fixed, K->x, K->r, K->dinv, K->partials, K->scal, K->comm);
+    LAUNCH(ctx, k_pcg_init, vg, VEC_NT, 0, n, (const double *)K->Ap, (const double *)(warm != 0.0 ? K->r : nullptr),
+           (const double *)extra, (const double *)K->diag, (const uint8_t *)K->fixed, K->x, K->r, K->dinv, K->partials, K->scal,
+           K->comm, warm);
     double *d_out2 = K->partials + K->partials_n;  // tail slots (see solver_alloc)
     auto fetch = [&](double &rz, double &rr) {
         LAUNCH(ctx, k_pcg_fetch, 1, 1, 0, K->scal, K->comm, d_out2);
-        CUDA_CHECK(cudaMemcpyAsync(K->h_pinned, d_out2, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(K->h_pinned, d_out2, 24, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         rz = K->h_pinned[0];
         rr = K->h_pinned[1];
     };
     double rz, rr;
     fetch(rz, rr);
-    const double bnorm2 = rr;
+    const double bnorm2 = K->h_pinned[2];  // ||b||^2 (== ||r0||^2 for a cold start)
     int it = 0;
     double res2 = rr;
     SpmvArgs A = make_spmv_args(K, K->p, K->Ap);

@@ -198,7 +198,9 @@ function setboundaryCond(NodeList, ne, ndim, FunctionClass, d, nDof=1)
 end
 
 # ---- examples/vector3D.jl:315-322 ---------------------------------------------------------------------------------
-function solve(K̄::B200SparseMatrix, q_d, C; rtol=1e-12, maxit=20000)
+function solve(K̄::B200SparseMatrix, q_d, C; rtol=1e-12, maxit=20000, warm_scale=0.0)
+    # warm_scale != 0: start from warm_scale * previous solution (load stepping, examples/vector3D.jl:310-338: q ∝ d)
+    warm_scale != 0 && check(ccall((:smfem_pcg_set_warm_start, LIB), Cint, (Ptr{Cvoid}, Cdouble), K̄.h, warm_scale))
     ndof = size(C, 1)
     free = rowvals(C)                                   # C = I[:, free]
     fixed = Int64.(setdiff(1:ndof, free)); vals = Float64.(q_d[fixed])

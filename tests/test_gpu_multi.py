@@ -50,6 +50,15 @@ def _worker(rank, ws, port, ne, q):
             rels.append(float(np.linalg.norm(qg - r["q"]) / np.linalg.norm(r["q"])))
             out["iters"] = it
         out["relq"] = rels
+        # warm-started second load step (examples/vector3D.jl:310): halo push of q_d + 11*x before the residual SpMV
+        K.set_spmv_variant(4)
+        K.set_dirichlet_zplanes(0.011)
+        sd.barrier(ctx)
+        ql, it2, _ = K.pcg_solve(rtol=1e-13, maxit=20000, warm_scale=11.0)
+        sd.barrier(ctx)
+        qg = sd.gather_vector(ql)
+        out["relq_warm"] = float(np.linalg.norm(qg - 11 * r["q"]) / np.linalg.norm(11 * r["q"]))
+        out["iters_warm"] = it2
         # halo path of the SpMV benchmark must run and agree across variants
         out["spmv_ms"] = [K.bench_spmv(reps=3, variant=v) for v in (4, 3, 2, 1, 0)]
         sd.barrier(ctx)
@@ -87,3 +96,4 @@ def test_slab_partition_matches_oracle(ws, ne):
         assert r["pattern"], r
         assert r["relK"] <= 1e-10, r
         assert max(r["relq"]) <= 1e-10, r
+        assert r["relq_warm"] <= 1e-10 and r["iters_warm"] <= 25, r

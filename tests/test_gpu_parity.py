@@ -308,3 +308,20 @@ def test_full_size_100_properties():
     u[2::3][top] = -0.001
     q, it, relres = K.pcg_solve(rtol=1e-12, maxit=8000, rhs_extra=K.spmv(u))
     assert relres <= 1e-12 and rel(q, u) <= 1e-8
+
+
+def test_load_stepping_warm_start():
+    """examples/vector3D.jl:310-338: 50 load steps d = 0.001:0.01:0.5 on one assembled K̄; q is linear in d, so the
+    warm-started solves must converge in (almost) no iterations and still match the oracle scaled by d."""
+    ne = 8
+    ctx = sf.context()
+    r = o.example_problem(ne, d=0.001)
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4).add_surface_mass(100.0)
+    deltas = np.arange(0.001, 0.5, 0.01)  # Julia's 0.001:0.01:0.5
+    assert len(deltas) == 50
+    iters = []
+    for d, q, it in sf.load_steps(K, deltas, rtol=1e-13):
+        assert rel(q, r["q"] * (d / 0.001)) <= TOL
+        iters.append(it)
+    assert iters[0] > 50 and max(iters[1:]) <= 25  # first solve cold, the rest start converged (<= one graph chunk)
