@@ -10,7 +10,8 @@ mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
 K = sf.SparseMatrixB200.pattern(ctx, mesh, 3, 3)
 for _ in range(2):
     K.pattern_rebuild()
-    K.assemble_values(40.0, 0.4)
+    K.assemble_values(40.0, 0.4)   # k_values_tile, values only
+    K.reassemble(40.0, 0.4)        # k_struct_rowptr + k_values_tile writing colind too (fused assembly step)
 K.add_surface_mass(100.0)
 i = K.info()
 b = 12 * i["nnz_local"] + 24 * i["nrows_local"]
