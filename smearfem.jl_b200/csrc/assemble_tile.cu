@@ -25,7 +25,14 @@ struct Material {
 
 namespace {
 
-constexpr int STAGE_NODE = 27 * 9;  // doubles per node in the staging area
+// Staging area of a node: 27 neighbour blocks of 3x3.  Block d = (dx,dy,dz) lives in slot c_slot[q] (q = (dz+1)*9 +
+// (dy+1)*3 + (dx+1)), slot = r + 8k where the residue r in 0..7 is DISTINCT inside every 2x2x2 sub-cube of the 3x3x3
+// neighbourhood (found by backtracking; at most 4 blocks share a residue -> 32 slots).  In a combine round the 8 slot
+// threads of a node hit such a sub-cube, so their 8-byte banks 9*slot + m (mod 16) are pairwise distinct and, with the
+// node stride == 8 (mod 16), disjoint from those of the second node of the half-warp: the read-modify-write rounds are
+// bank-conflict free (they were exactly 2-way conflicted with the plain [27][9] layout: 148 vs 74 wavefronts per node).
+__constant__ unsigned char c_slot[27] = {5, 7, 20, 6, 3, 22, 2, 23, 17, 4, 18, 9, 1, 0, 29, 21, 12, 26, 13, 15, 28, 14, 11, 30, 10, 31, 25};
+constexpr int STAGE_NODE = 32 * 9 + 8;  // 296 doubles per node (== 8 mod 16)
 
 template <int TX_, int TY_>
 struct Tile {
@@ -36,7 +43,10 @@ struct Tile {
     static constexpr int PAD = (EX == 9) ? 3 : 8;  // 8x4 tile: banks {6,7,8,15,0,1}+3; 4x4 tile: {10,11,12,15,0,1}+8
     static constexpr int LAYER = 8 * 8 * 3 * NEL + PAD;
     static constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY * 3;  // node-plane coordinate buffer (with halo)
-    static constexpr size_t SMEM_BYTES = sizeof(double) * (2 * LAYER + TX * TY * STAGE_NODE + 8 * 8 * 3 + 8 + 4 * PLANE);
+    // the staging area aliases the ring slot of the element layer that is dead after the main loop when it fits (4x4)
+    static constexpr bool ALIAS = TX * TY * STAGE_NODE <= LAYER;
+    static constexpr size_t SMEM_BYTES =
+        sizeof(double) * (2 * LAYER + (ALIAS ? 0 : TX * TY * STAGE_NODE) + 8 * 8 * 3 + 8 + 4 * PLANE);
 };
 
 struct TileArgs {
@@ -160,8 +170,8 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
     constexpr int TX = T::TX, TY = T::TY, NTH = T::NTH, NEL = T::NEL, EX = T::EX, LAYER = T::LAYER;
     extern __shared__ double smem[];
     double *S = smem;                             // [2][gp][b][c][e]
-    double *stage = smem + 2 * LAYER;             // [node][27][9]
-    double *s_dN = stage + TX * TY * STAGE_NODE;  // [gp][3]: Gauss-point coordinates (xi, eta, zeta)
+    double *stage_own = smem + 2 * LAYER;         // [node][32 slots][9] when not aliased
+    double *s_dN = stage_own + (T::ALIAS ? 0 : TX * TY * STAGE_NODE);  // [gp][3]: Gauss-point coordinates (xi, eta, zeta)
     double *s_w = s_dN + 8 * 8 * 3;   // sqrt of the Gauss weights
     double *s_xyz = s_w + 8;          // [4][PLANE] node-plane coordinate ring
     const Lattice &L = A.L;
@@ -188,7 +198,11 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
     const bool el_xy_ok = node_ok && ex >= 0 && ey >= 0 && ex < L.ne && ey < L.ne;
     const int e = (ty - sy + 1) * EX + (tx - sx + 1);
     const int a = sz * 4 + ((sy << 1) | (sx ^ sy));  // local node number of this node inside element -s
-    double *my_stage = stage + nt * STAGE_NODE;
+    int soff[8];  // staging offset of this thread's target block in combine round beta
+#pragma unroll
+    for (int beta = 0; beta < 8; ++beta)
+        soff[beta] = 9 * c_slot[((beta >> 2) - sz + 1) * 9 + (((beta >> 1) & 1) - sy + 1) * 3 + ((beta & 1) - sx + 1)];
+    const int out_off = lane < 27 ? 9 * c_slot[lane] : 0;
     // closed-form CSR row starts (no dependent global load in the output phase): see k_struct_rowptr
     const int64_t S1 = 3 * (int64_t)L.n1 - 2;
     auto pre1 = [](int i) -> int64_t { return i == 0 ? 0 : 3 * (int64_t)i - 1; };
@@ -241,13 +255,17 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
         // Block d is touched for the FIRST time in round beta_min(d) = max(d,0) per axis, i.e. by the lanes with
         // (s & beta) == 0: those plain-store (no zeroing pass, no load), everybody else read-modify-writes.
         // Threads whose element does not exist still take part with G = 0 so that every block gets initialised.
-        __syncwarp();
+        // the staging area lives in the ring slot of layer k-1, which every thread has finished reading now
+        double *stage = T::ALIAS ? S + ((k - 1) & 1) * LAYER : stage_own;
+        double *my_stage = stage + nt * STAGE_NODE;
+        if (T::ALIAS) __syncthreads();
+        else __syncwarp();
 #pragma unroll
         for (int beta = 0; beta < 8; ++beta) {
             const int obx = beta & 1, oby = (beta >> 1) & 1, obz = beta >> 2;
             const int b = obz * 4 + (oby ? (obx ? 2 : 3) : (obx ? 1 : 0));  // reference local numbering
             if (!(A.skip & 4)) {
-                double *dst = my_stage + ((obz - sz + 1) * 9 + (oby - sy + 1) * 3 + (obx - sx + 1)) * 9;
+                double *dst = my_stage + soff[beta];
                 if ((s & beta) == 0) {
 #pragma unroll
                     for (int m = 0; m < 9; ++m) dst[m] = G[b][m];
@@ -274,7 +292,7 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
                 const int64_t row = (((int64_t)(k - L.k0) * L.n1 + jy) * L.n1 + jx) * 3;
                 const int64_t pairs = pre1(k) * S1 * S1 + (int64_t)cz * (pre1(jy) * S1 + (int64_t)cy * pre1(jx)) - pairs_base;
                 const int64_t base = 9 * pairs + 3 * rank;
-                const double *g = stage + n2 * STAGE_NODE + lane * 9;
+                const double *g = stage + n2 * STAGE_NODE + out_off;
                 const double tr = g[0] + g[4] + g[8];
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
