@@ -53,13 +53,22 @@ __global__ void k_check_lattice(int64_t nEl, int ne, const int64_t *__restrict__
         int ei = (int)(e % ne), ej = (int)((e / ne) % ne), ek = (int)(e / ((int64_t)ne * ne));
         int ox = ((a & 3) == 1 || (a & 3) == 2), oy = ((a & 3) >= 2), oz = (a >> 2);
         int64_t want = ((int64_t)(ek + oz) * n1 + (ej + oy)) * n1 + (ei + ox) + 1;
-        if (IEN[t] != want) *mismatch = 1;
+        if (IEN[t] != want) mismatch[0] = 1;
     }
     if (ID && t < nNodes * nDof) {
         int64_t m = t % nNodes;
         int l = (int)(t / nNodes);
-        if (ID[t] != nDof * m + l + 1) *mismatch = 1;
+        if (ID[t] != nDof * m + l + 1) mismatch[1] = 1;
     }
+}
+
+// is ID the standard node-major map ID[m,l] = nDof*(m-1)+l (examples/vector3D.jl:74)?
+__global__ void k_check_std_id(int64_t nNodes, int nDof, const int64_t *__restrict__ ID, int *__restrict__ mismatch) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nNodes * nDof) return;
+    int64_t m = t % nNodes;
+    int l = (int)(t / nNodes);
+    if (ID[t] != nDof * m + l + 1) *mismatch = 1;
 }
 
 __global__ void k_max_i64(int64_t n, const int64_t *__restrict__ in, unsigned long long *__restrict__ out) {
@@ -275,18 +284,18 @@ int smfem_mesh_from_host(smfem_ctx *ctx, const double *NodeList, const int64_t *
             d_id = dev_alloc<int64_t>(nNodes * nDof);
             CUDA_CHECK(cudaMemcpyAsync(d_id, ID, 8 * nNodes * nDof, cudaMemcpyHostToDevice, ctx->stream));
         }
-        int *d_flag = dev_alloc<int>(2);
-        CUDA_CHECK(cudaMemsetAsync(d_flag, 0, 8, ctx->stream));
+        int *d_flag = dev_alloc<int>(4);  // [0] IEN != lattice, [1] ID != standard (lattice check), [2] range error, [3] ID != standard
+        CUDA_CHECK(cudaMemsetAsync(d_flag, 0, 16, ctx->stream));
         bool lattice = false;
         if (ndim == 3 && ctx->nranks >= 1 && ne >= 1 && nEl == ne * ne * ne && nNodes == (ne + 1) * (ne + 1) * (ne + 1) &&
             (nDof == 3 || nDof == 1)) {
             int64_t nt = nEl * 8 > nNodes * nDof ? nEl * 8 : nNodes * nDof;
             LAUNCH(ctx, k_check_lattice, (unsigned)((nt + 255) / 256), 256, 0, nEl, (int)ne, (const int64_t *)d_ien, nNodes,
                    nDof, (const int64_t *)d_id, d_flag);
-            int h = 1;
-            CUDA_CHECK(cudaMemcpyAsync(&h, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            int h[2] = {1, 1};
+            CUDA_CHECK(cudaMemcpyAsync(h, d_flag, 8, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-            lattice = (h == 0);
+            lattice = (h[0] == 0 && h[1] == 0);
         }
         if (lattice) {
             set_lattice(ctx, m, ne);
@@ -306,12 +315,21 @@ int smfem_mesh_from_host(smfem_ctx *ctx, const double *NodeList, const int64_t *
             CUDA_CHECK(cudaMemcpyAsync(m->coords, NodeList, 8 * (int64_t)ndim * nNodes, cudaMemcpyHostToDevice, ctx->stream));
             m->ien = dev_alloc<int32_t>(nEl * nLocal);
             LAUNCH(ctx, k_convert_index, (unsigned)((nEl * nLocal + 255) / 256), 256, 0, nEl * nLocal, (const int64_t *)d_ien,
-                   (int64_t)1, nNodes, m->ien, d_flag + 1);
+                   (int64_t)1, nNodes, m->ien, d_flag + 2);
+            bool std_id = false;
             if (ID) {
+                LAUNCH(ctx, k_check_std_id, (unsigned)((nNodes * nDof + 255) / 256), 256, 0, nNodes, nDof, (const int64_t *)d_id,
+                       d_flag + 3);
+                int h3 = 1;
+                CUDA_CHECK(cudaMemcpyAsync(&h3, d_flag + 3, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+                std_id = (h3 == 0);  // standard node-major numbering: no ID table needed on the device (dof = nDof*node + comp)
+            }
+            if (ID && !std_id) {
                 m->id = dev_alloc<int32_t>(nNodes * nDof);
                 m->nDof_id = nDof;
                 LAUNCH(ctx, k_convert_index, (unsigned)((nNodes * nDof + 255) / 256), 256, 0, nNodes * nDof,
-                       (const int64_t *)d_id, (int64_t)1, (int64_t)INT32_MAX - 1, m->id, d_flag + 1);
+                       (const int64_t *)d_id, (int64_t)1, (int64_t)INT32_MAX - 1, m->id, d_flag + 2);
                 unsigned long long *d_max = (unsigned long long *)dev_alloc<int64_t>(1);
                 CUDA_CHECK(cudaMemsetAsync(d_max, 0, 8, ctx->stream));
                 LAUNCH(ctx, k_max_i64, (unsigned)((nNodes * nDof + 255) / 256), 256, 0, nNodes * nDof, (const int64_t *)d_id, d_max);
@@ -319,10 +337,12 @@ int smfem_mesh_from_host(smfem_ctx *ctx, const double *NodeList, const int64_t *
                 CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
                 cudaFree(d_max);
             }
-            int h[2] = {0, 0};
-            CUDA_CHECK(cudaMemcpyAsync(h, d_flag, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            if (ID && std_id) m->nDof_id = nDof;
+            m->std_id = (ID == nullptr) || std_id;
+            int h[4] = {0, 0, 0, 0};
+            CUDA_CHECK(cudaMemcpyAsync(h, d_flag, 16, cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-            if (h[1]) {
+            if (h[2]) {
                 dev_free(d_ien);
                 dev_free(d_id);
                 dev_free(d_flag);
@@ -461,8 +481,9 @@ static smfem_matrix *new_matrix(smfem_ctx *ctx, smfem_mesh *mesh, int ndim, int 
     REQUIRE(ndim == mesh->ndim, SMFEM_ERR_INVALID, "ndim does not match the mesh (reference: DimensionMismatch)");
     REQUIRE((ndim == 3 && (nDof == 3 || nDof == 1)) || (ndim == 2 && (nDof == 2 || nDof == 1)), SMFEM_ERR_UNSUPPORTED,
             "supported (ndim,nDof): (3,3) (3,1) (2,2) (2,1)");
-    REQUIRE(mesh->structured || mesh->id != nullptr || nDof == 1, SMFEM_ERR_INVALID, "ID is required when nDof > 1");
-    REQUIRE(mesh->structured || mesh->id == nullptr || mesh->nDof_id == nDof || nDof == 1, SMFEM_ERR_INVALID,
+    REQUIRE(mesh->structured || mesh->id != nullptr || mesh->nDof_id == nDof || nDof == 1, SMFEM_ERR_INVALID,
+            "ID is required when nDof > 1");
+    REQUIRE(mesh->structured || mesh->nDof_id == 0 || mesh->nDof_id == nDof || nDof == 1, SMFEM_ERR_INVALID,
             "size(ID,2) must equal nDof (src/fem.jl:238-242 is only consistent then)");
     smfem_matrix *K = new smfem_matrix();
     K->ctx = ctx;

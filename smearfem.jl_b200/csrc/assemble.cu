@@ -2,6 +2,7 @@
 // diagonal extraction, CSC export.
 //   reference: src/fem.jl:135-256 (assemble_system), examples/vector3D.jl:175-264 (surface matrix)
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include "smfem_internal.cuh"
 
@@ -315,26 +316,29 @@ __global__ void k_gen_colind(DofMap D, const int64_t *__restrict__ adj_ptr, cons
     }
 }
 
-template <class T>
-static void exclusive_scan(smfem_ctx *ctx, const T *in, int64_t *out, int64_t n);
+struct IntTo64 {
+    __host__ __device__ int64_t operator()(int v) const { return (int64_t)v; }
+};
 
+// device exclusive prefix sum (CUB) of `n` values; `in` may be a transform iterator
 template <class In>
-static void exclusive_scan_impl(smfem_ctx *ctx, In in, int64_t *out, int64_t n) {
+static void exclusive_scan_dev(smfem_ctx *ctx, In in, int64_t *out, int64_t n) {
     void *tmp = nullptr;
     size_t bytes = 0;
     REQUIRE(n < (int64_t)INT32_MAX, SMFEM_ERR_UNSUPPORTED, "scan length exceeds int32");
     CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, (int)n, ctx->stream));
-    CUDA_CHECK(cudaMalloc(&tmp, bytes ? bytes : 1));
+    tmp = dev_alloc<unsigned char>(bytes ? bytes : 1);
     CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, (int)n, ctx->stream));
     ctx->launches += 2;
+    unsigned char *t8 = static_cast<unsigned char *>(tmp);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(tmp);
+    dev_free(t8);
 }
 
-struct IntTo64 {
-    const int *p;
-    __host__ __device__ int64_t operator()(int64_t i) const { return (int64_t)p[i]; }
-};
+__global__ void k_max_int(int64_t n, const int *__restrict__ v, int *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) atomicMax(out, v[t]);
+}
 
 void pattern_build_general(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
     REQUIRE(ctx->nranks == 1, SMFEM_ERR_UNSUPPORTED, "general (unstructured) meshes are single-GPU only");
@@ -342,7 +346,7 @@ void pattern_build_general(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
     const int nn = mesh->nn, nDof = K->nDof;
     K->structured = false;
     K->ghost_cols = 0;
-    int64_t ndof = mesh->id ? mesh->ndof_id : nNodes * nDof;
+    int64_t ndof = mesh->id ? mesh->ndof_id : nNodes * nDof;  // id == nullptr: standard map (or nDof == 1 raw node ids)
     REQUIRE(ndof == nNodes * nDof, SMFEM_ERR_UNSUPPORTED,
             "ID must be a bijection onto 1..nDof*nNodes (max(ID) != nDof*nNodes)");
     K->m_g = ndof;
@@ -351,85 +355,73 @@ void pattern_build_general(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
     K->row0 = 0;
     REQUIRE(ndof < (int64_t)INT32_MAX, SMFEM_ERR_UNSUPPORTED, "dof count exceeds int32 column indices");
 
-    int *cnt = dev_alloc<int>(nNodes + 1), *cursor = dev_alloc<int>(nNodes + 1), *err = dev_alloc<int>(1);
+    // everything below runs on the device; the host only reads back three scalars (max valence, totals) and flags
+    int *cnt = dev_alloc<int>(nNodes + 1), *cursor = dev_alloc<int>(nNodes + 1), *flags = dev_alloc<int>(4);
     int64_t *n2e_ptr = dev_alloc<int64_t>(nNodes + 1), *adj_ptr = dev_alloc<int64_t>(nNodes + 1);
-    CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int) * (nNodes + 1), ctx->stream));
-    CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(int) * (nNodes + 1), ctx->stream));
-    CUDA_CHECK(cudaMemsetAsync(err, 0, sizeof(int), ctx->stream));
-    unsigned gE = (unsigned)((nEl * nn + 255) / 256), gN = (unsigned)((nNodes + 127) / 128);
-    LAUNCH(ctx, k_n2e_count, gE, 256, 0, mesh->ien, nEl, nn, cnt);
-    {
-        // scan of int counts into int64 offsets (nNodes+1 entries: last one = total)
-        int64_t *tmp64 = dev_alloc<int64_t>(nNodes + 1);
-        CUDA_CHECK(cudaMemsetAsync(tmp64, 0, 8 * (nNodes + 1), ctx->stream));
-        // widen
-        std::vector<int> h(nNodes + 1);
-        CUDA_CHECK(cudaMemcpyAsync(h.data(), cnt, sizeof(int) * (nNodes + 1), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        int mx = 0;
-        for (int64_t i = 0; i < nNodes; ++i) mx = h[i] > mx ? h[i] : mx;
-        REQUIRE(mx <= MAX_VAL, SMFEM_ERR_UNSUPPORTED, "a node is shared by more than 16 elements");
-        std::vector<int64_t> p(nNodes + 1);
-        int64_t s = 0;
-        for (int64_t i = 0; i <= nNodes; ++i) {
-            p[i] = s;
-            if (i < nNodes) s += h[i];
-        }
-        CUDA_CHECK(cudaMemcpyAsync(n2e_ptr, p.data(), 8 * (nNodes + 1), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        dev_free(tmp64);
-    }
-    int32_t *n2e = dev_alloc<int32_t>(nEl * nn);
-    LAUNCH(ctx, k_n2e_fill, gE, 256, 0, mesh->ien, nEl, nn, n2e_ptr, cursor, n2e);
-    // (element order inside a node's list is irrelevant: the adjacency below is sorted + unique)
-    int *adj_cnt = cnt;  // reuse
-    LAUNCH(ctx, k_node_adj, gN, 128, 0, mesh->ien, nEl, nn, nNodes, n2e_ptr, n2e, (const int64_t *)nullptr,
-           (int32_t *)nullptr, adj_cnt, err);
-    CUDA_CHECK(cudaMemsetAsync(adj_cnt + nNodes, 0, sizeof(int), ctx->stream));
-    {
-        std::vector<int> h(nNodes + 1);
-        CUDA_CHECK(cudaMemcpyAsync(h.data(), adj_cnt, sizeof(int) * (nNodes + 1), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        std::vector<int64_t> p(nNodes + 1);
-        int64_t s = 0;
-        for (int64_t i = 0; i <= nNodes; ++i) {
-            p[i] = s;
-            if (i < nNodes) s += h[i];
-        }
-        CUDA_CHECK(cudaMemcpyAsync(adj_ptr, p.data(), 8 * (nNodes + 1), cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        int herr = 0;
-        CUDA_CHECK(cudaMemcpy(&herr, err, sizeof(int), cudaMemcpyDeviceToHost));
-        REQUIRE(herr == 0, SMFEM_ERR_UNSUPPORTED, "a node has more than 64 neighbour nodes");
-        int32_t *adj = dev_alloc<int32_t>(s);
-        LAUNCH(ctx, k_node_adj, gN, 128, 0, mesh->ien, nEl, nn, nNodes, n2e_ptr, n2e, adj_ptr, adj, adj_cnt, err);
-
+    int32_t *n2e = nullptr, *adj = nullptr;
+    int64_t *rowlen = nullptr;
+    auto cleanup = [&] {
+        dev_free(cnt);
+        dev_free(cursor);
+        dev_free(flags);
+        dev_free(n2e_ptr);
+        dev_free(adj_ptr);
+        dev_free(n2e);
+        dev_free(adj);
+        dev_free(rowlen);
+    };
+    try {
+        CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int) * (nNodes + 1), ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(int) * (nNodes + 1), ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * 4, ctx->stream));
+        int *err = flags, *d_maxval = flags + 1;
+        const unsigned gE = (unsigned)((nEl * nn + 255) / 256), gN = (unsigned)((nNodes + 127) / 128);
+        // node -> element lists
+        LAUNCH(ctx, k_n2e_count, gE, 256, 0, (const int32_t *)mesh->ien, nEl, nn, cnt);
+        LAUNCH(ctx, k_max_int, (unsigned)((nNodes + 255) / 256), 256, 0, nNodes, (const int *)cnt, d_maxval);
+        exclusive_scan_dev(ctx, cub::TransformInputIterator<int64_t, IntTo64, const int *>(cnt, IntTo64()), n2e_ptr, nNodes + 1);
+        int h[2] = {0, 0};
+        CUDA_CHECK(cudaMemcpy(h, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost));
+        REQUIRE(h[1] <= MAX_VAL, SMFEM_ERR_UNSUPPORTED, "a node is shared by more than 16 elements");
+        n2e = dev_alloc<int32_t>(nEl * nn);
+        LAUNCH(ctx, k_n2e_fill, gE, 256, 0, (const int32_t *)mesh->ien, nEl, nn, (const int64_t *)n2e_ptr, cursor, n2e);
+        // (element order inside a node's list is irrelevant: the adjacency below is sorted + unique)
+        // node -> node adjacency: count pass, scan, fill pass
+        int *adj_cnt = cnt;
+        LAUNCH(ctx, k_node_adj, gN, 128, 0, (const int32_t *)mesh->ien, nEl, nn, nNodes, (const int64_t *)n2e_ptr,
+               (const int32_t *)n2e, (const int64_t *)nullptr, (int32_t *)nullptr, adj_cnt, err);
+        CUDA_CHECK(cudaMemsetAsync(adj_cnt + nNodes, 0, sizeof(int), ctx->stream));
+        exclusive_scan_dev(ctx, cub::TransformInputIterator<int64_t, IntTo64, const int *>(adj_cnt, IntTo64()), adj_ptr, nNodes + 1);
+        int64_t nadj = 0;
+        CUDA_CHECK(cudaMemcpy(&nadj, adj_ptr + nNodes, 8, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(h, flags, sizeof(int), cudaMemcpyDeviceToHost));
+        REQUIRE(h[0] == 0, SMFEM_ERR_UNSUPPORTED, "a node has more than 64 neighbour nodes");
+        adj = dev_alloc<int32_t>(nadj);
+        LAUNCH(ctx, k_node_adj, gN, 128, 0, (const int32_t *)mesh->ien, nEl, nn, nNodes, (const int64_t *)n2e_ptr,
+               (const int32_t *)n2e, (const int64_t *)adj_ptr, adj, adj_cnt, err);
+        // rows through the dof map
         DofMap D = make_dofmap(mesh, K);
         D.nrows_l = ndof;
-        int64_t *rowlen = dev_alloc<int64_t>(ndof + 1);
+        rowlen = dev_alloc<int64_t>(ndof + 1);
         CUDA_CHECK(cudaMemsetAsync(rowlen, 0, 8 * (ndof + 1), ctx->stream));
-        unsigned gR = (unsigned)((nNodes * nDof + 255) / 256);
-        LAUNCH(ctx, k_gen_rowlen, gR, 256, 0, D, adj_ptr, nNodes, ndof, rowlen, err);
-        CUDA_CHECK(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        REQUIRE(herr == 0, SMFEM_ERR_INVALID, "ID is not a bijection onto 1..nDof*nNodes");
+        const unsigned gR = (unsigned)((nNodes * nDof + 255) / 256);
+        LAUNCH(ctx, k_gen_rowlen, gR, 256, 0, D, (const int64_t *)adj_ptr, nNodes, ndof, rowlen, err);
         matrix_alloc_pattern(K);
-        exclusive_scan_impl(ctx, rowlen, K->rowptr, ndof + 1);
+        exclusive_scan_dev(ctx, (const int64_t *)rowlen, K->rowptr, ndof + 1);
+        CUDA_CHECK(cudaMemcpy(h, flags, sizeof(int), cudaMemcpyDeviceToHost));
+        REQUIRE(h[0] == 0, SMFEM_ERR_INVALID, "ID is not a bijection onto 1..nDof*nNodes");
         CUDA_CHECK(cudaMemcpy(&K->nnz_l, K->rowptr + ndof, 8, cudaMemcpyDeviceToHost));
         K->nnz_g = K->nnz_l;
         K->colind = dev_alloc<int32_t>(K->nnz_l + 16);
         CUDA_CHECK(cudaMemsetAsync(K->colind + K->nnz_l, 0, 16 * sizeof(int32_t), ctx->stream));
-        LAUNCH(ctx, k_gen_colind, gR, 256, 0, D, adj_ptr, adj, nNodes, K->rowptr, K->colind);
+        LAUNCH(ctx, k_gen_colind, gR, 256, 0, D, (const int64_t *)adj_ptr, (const int32_t *)adj, nNodes, (const int64_t *)K->rowptr,
+               K->colind);
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        dev_free(rowlen);
-        dev_free(adj);
+    } catch (...) {
+        cleanup();
+        throw;
     }
-    dev_free(n2e);
-    dev_free(cnt);
-    dev_free(cursor);
-    dev_free(err);
-    dev_free(n2e_ptr);
-    dev_free(adj_ptr);
+    cleanup();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -565,6 +557,10 @@ k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64
             double tr = 0;
 #pragma unroll
             for (int i = 0; i < NDIM; ++i) tr += G[b][(i * NDIM + i) % GS];
+            // standard dof map: the NDOF columns of node b are consecutive and the NDOF rows of node a share one
+            // pattern -> ONE search per node pair instead of NDOF^2
+            int64_t rel0 = -1;
+            if (D.id == nullptr && rows[0] >= 0) rel0 = csr_find(rowptr, colind, rows[0], D.col(nodes[b], 0)) - rowptr[rows[0]];
 #pragma unroll
             for (int i = 0; i < NDIM; ++i) {
                 if (rows[i % NDOF] < 0) continue;
@@ -572,7 +568,8 @@ k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64
                 for (int j = 0; j < NDIM; ++j) {
                     double gij = G[b][(i * NDIM + j) % GS], gji = G[b][(j * NDIM + i) % GS];
                     double v = (i == j) ? mat.d11 * gij + mat.mu * (tr - gij) : mat.lam * gij + mat.mu * gji;
-                    int64_t pos = csr_find(rowptr, colind, rows[i % NDOF], D.col(nodes[b], j % NDOF));
+                    int64_t pos = (rel0 >= 0) ? rowptr[rows[i % NDOF]] + rel0 + j
+                                              : csr_find(rowptr, colind, rows[i % NDOF], D.col(nodes[b], j % NDOF));
                     atomicAdd(&val[pos], v);
                 }
             }

@@ -104,6 +104,7 @@ struct smfem_mesh {
     int32_t *ien = nullptr;  // [a][e], 0-based node ids (SoA like Julia's column-major IEN)
     int32_t *id = nullptr;   // [comp][node], 0-based dof ids; nullptr -> dof = nDof*node+comp
     int nDof_id = 0;
+    bool std_id = false;     // ID is the standard node-major map (or absent): dof = nDof*node + comp
     int64_t ndof_id = 0;  // max(ID)
     // surface faces for general meshes are passed to smfem_surface_mass directly
 };

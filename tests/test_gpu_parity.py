@@ -103,6 +103,26 @@ def test_general_path_permuted_ids_and_elements():
     assert_csc_parity(K, Ko)
 
 
+def test_general_path_shuffled_elements_standard_ids():
+    """Shuffled element order with the standard dof map: general (unstructured) path, but the device recognises the
+    node-major ID (one CSR search per node pair, row-triple SpMV); the fold order over elements differs from the
+    reference's ascending order only in rounding."""
+    ne = 6
+    NL, IEN, ID, top, btm, _ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.inflate_sphere(NL, 0, 1, 0, 1)
+    perm = np.random.default_rng(11).permutation(IEN.shape[0])
+    K = sf.assemble_system(ne, NL, IEN[perm], 3, "Q1", 3, ID, 40, 0.4)
+    assert not K.mesh.info()["structured"]
+    Ko = o.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4)  # same matrix: element order does not change K
+    assert_csc_parity(K, Ko, tol=1e-13)
+    # the whole example pipeline on the general path (explicit face lists, general Dirichlet list)
+    b = sf.apply_boundary_conditions(ne, NL, IEN[perm], top, btm, 3, "Q1", ID)
+    K_bar = K + 100 * b
+    q_d, C = sf.setboundaryCond(NL, ne, 3, "Q1", 0.001, 3)
+    q = sf.solve(K_bar, q_d, C, rtol=1e-13)
+    assert rel(q, o.example_problem(ne)["q"]) <= TOL
+
+
 @pytest.mark.parametrize("ne", [2, 4, 9])
 def test_plane_stress_quad4(ne, golden_dir):  # config C1 geometry, src/fem.jl:210-217
     NL, IEN, ID, *_ = sf.meshgrid(0, 1, 0, 1, 0, 1, ne, 2)
