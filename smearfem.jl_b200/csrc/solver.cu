@@ -3,6 +3,7 @@
 //   reference: examples/vector3D.jl:133-173 (setboundaryCond), :308-322 (solve; the dense inverse
 //   of :318 is replaced by PCG on the same system K̄[free,free] q_f = -(K̄ q_d)[free]).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "smfem_internal.cuh"
@@ -169,6 +170,7 @@ struct SpmvArgs {
     PcgScalars *scal;
     CommView cv;
     int64_t rot;  // warp rotation so that boundary-plane rows run last
+    int64_t row_begin, row_end;  // k_spmv_group: rows [row_begin, row_end) (multiples of the group size)
 };
 
 template <int RPW, int MODE>
@@ -744,15 +746,11 @@ __global__ void __launch_bounds__(256, 3) k_spmv_group(SpmvArgs A) {
     __shared__ double s_red[8];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31;
-    const int64_t ngroups = A.nrows / G;
+    const int64_t ngroups = A.row_end / G;  // groups [row_begin/G, row_end/G)
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t g = A.row_begin / G + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     double dot = 0.0;
-    auto group_of = [&](int64_t gi) {  // rotation (boundary planes last) without a 64-bit modulo: rot < ngroups
-        if (!HALO) return gi;
-        const int64_t t = gi + A.rot;
-        return t >= ngroups ? t - ngroups : t;
-    };
+    auto group_of = [&](int64_t gi) { return gi; };
     // register sets: [cur] is being reduced while [nxt] is in flight (warp-level software pipeline)
     int cc[3], nc[3];
     double cw[3][G], nw[3][G];
@@ -879,7 +877,7 @@ __global__ void __launch_bounds__(256, 3) k_spmv_group(SpmvArgs A) {
             for (int q = 0; q < G; ++q) cw[j][q] = nw[j][q];
         }
     }
-    if (G > 1 && blockIdx.x == 0 && threadIdx.x < (unsigned)(A.nrows % G)) {  // nrows % G leftover rows (never for G = 3 here)
+    if (G > 1 && A.row_end == A.nrows && blockIdx.x == 0 && threadIdx.x < (unsigned)(A.nrows % G)) {  // leftover rows (never for G = 3 here)
         const int64_t r = (A.nrows / G) * G + threadIdx.x;
         double sacc = 0.0;
         for (int64_t p = A.rowptr[r]; p < A.rowptr[r + 1]; ++p) sacc += A.val[p] * A.x[A.colind[p]];
@@ -969,6 +967,8 @@ static SpmvArgs make_spmv_args(smfem_matrix *K, const double *x, double *y) {
     A.scal = K->scal;
     A.cv = K->comm;
     A.rot = 0;
+    A.row_begin = 0;
+    A.row_end = K->nrows_l;
     return A;
 }
 
@@ -1207,6 +1207,36 @@ __global__ void k_warm_vector(int64_t n, int64_t ghost_cols, int64_t ncols, cons
     w[c] = v;
 }
 
+// p'Ap as its own pass (50 MB of traffic, ~11 us at 100^3): fusing it into the SpMV cost 60 us there
+__global__ void __launch_bounds__(VEC_NT)
+k_pcg_dot(int64_t n, int64_t ghost_cols, const double *__restrict__ p, const double *__restrict__ Ap, double *__restrict__ partials,
+          PcgScalars *scal, CommView cv) {
+    __shared__ double s_red[VEC_NT / 32];
+    __shared__ bool s_last;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const double *po = p + ghost_cols;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += po[i] * Ap[i];
+    double s1 = block_sum<VEC_NT>(acc, s_red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = s1;
+        __threadfence();
+        unsigned t = atomicAdd(&scal->ticketB, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double v = 0.0;
+        for (int64_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += ld_volatile_f64(partials + i);
+        double tot = block_sum<VEC_NT>(v, s_red);
+        if (threadIdx.x == 0) {
+            scal->ticketB = 0;
+            allreduce_publish(cv, 2ull * scal->it + 1ull, 1, &tot);
+        }
+    }
+}
+
 // fetch the current global (rz, rr) into scal (so the host can read the residual)
 __global__ void k_pcg_fetch(PcgScalars *scal, CommView cv, double *out3) {
     double v[3];
@@ -1349,6 +1379,43 @@ void comm_connect(smfem_ctx *ctx, smfem_matrix *K, const void *handles) {
     K->comm_connected = true;
 }
 
+
+// y = K x without mask / fused dot.  halo: the rows of the first / last owned plane wait for the ghost planes pushed by the
+// neighbours.  For the row-group kernel the SpMV is split into an interior launch (no flag code at all: the halo variant
+// costs 46 us even on one GPU) followed by a boundary-plane launch that waits -- stream order gives the overlap of the
+// NVLink transfer with the interior rows for free.  Other variants keep the single rotated launch.
+static void spmv_apply(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y, bool halo) {
+    SpmvArgs A = make_spmv_args(K, x, y);
+    const int variant = K->spmv_variant;
+    if (!halo || ctx->nranks == 1) {
+        launch_spmv<0>(ctx, K, A, variant);
+        return;
+    }
+    if (variant != 4) {
+        A.rot = spmv_rotation(ctx, K, variant);
+        launch_spmv<4>(ctx, K, A, variant);
+        return;
+    }
+    const int64_t pd = K->comm.plane_dofs, n = K->nrows_l;
+    const int64_t lo = (ctx->rank > 0) ? pd : 0;                     // first owned plane needs ghost_lo
+    const int64_t hi = (ctx->rank < ctx->nranks - 1) ? n - pd : n;   // last owned plane needs ghost_hi
+    if (hi > lo) {
+        A.row_begin = lo;
+        A.row_end = hi;
+        launch_spmv<0>(ctx, K, A, variant);
+    }
+    if (lo > 0) {
+        A.row_begin = 0;
+        A.row_end = lo < hi ? lo : (lo < n ? lo : n);
+        launch_spmv<4>(ctx, K, A, variant);
+    }
+    if (hi < n) {
+        A.row_begin = hi > lo ? hi : lo;  // a single owned plane is both first and last
+        A.row_end = n;
+        if (A.row_end > A.row_begin) launch_spmv<4>(ctx, K, A, variant);
+    }
+}
+
 void spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y) {
     REQUIRE(ctx->nranks == 1, SMFEM_ERR_UNSUPPORTED, "spmv_host is single-GPU");
     REQUIRE(K->values_ready, SMFEM_ERR_INVALID, "matrix has no values yet");
@@ -1378,15 +1445,22 @@ void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *m
     unsigned long long it0 = 0;
     CUDA_CHECK(cudaMemcpyAsync(&it0, &K->scal->it, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    int dbg_mode = 0;  // experiments: SMFEM_BENCH_MODE = 1 mask, 2 dot, 3 mask|dot, 7 solve mode (single GPU only)
+    if (const char *e = std::getenv("SMFEM_BENCH_MODE")) dbg_mode = std::atoi(e);
+    const int saved_variant = K->spmv_variant;
+    K->spmv_variant = variant;
     auto one = [&](int j) {
-        if (ctx->nranks > 1) {
+        if (ctx->nranks == 1 && dbg_mode == 2) launch_spmv<2>(ctx, K, A, variant);
+        else if (ctx->nranks == 1 && dbg_mode == 3) launch_spmv<3>(ctx, K, A, variant);
+        else if (ctx->nranks == 1 && dbg_mode == 7) launch_spmv<7>(ctx, K, A, variant);
+        else if (ctx->nranks > 1) {
             unsigned long long seq = it0 + 1;  // SpMV waits for hflag >= scal->it + 1 (it is not advanced here)
             int g = (int)((K->comm.plane_dofs + 255) / 256);
             if (g > ctx->sms * 4) g = ctx->sms * 4;
             LAUNCH(ctx, k_halo_push, g, 256, 0, K->nrows_l, K->ghost_cols, (const double *)K->p, K->scal, K->comm, seq);
-            launch_spmv<4>(ctx, K, A, variant);
+            spmv_apply(ctx, K, K->p, K->Ap, true);
         } else {
-            launch_spmv<0>(ctx, K, A, variant);
+            spmv_apply(ctx, K, K->p, K->Ap, false);
         }
         (void)j;
     };
@@ -1398,6 +1472,7 @@ void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *m
     float t = 0;
     CUDA_CHECK(cudaEventElapsedTime(&t, ctx->ev2, ctx->ev3));
     *ms = t / reps;
+    K->spmv_variant = saved_variant;
 }
 
 void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const double *rhs_extra, double *q_out,
@@ -1428,7 +1503,6 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
         }
         LAUNCH(ctx, k_warm_vector, (unsigned)((K->ncols_l + 255) / 256), 256, 0, n, K->ghost_cols, K->ncols_l, (const double *)K->qd,
                (const double *)K->x, warm, K->p);
-        SpmvArgs A = make_spmv_args(K, K->p, K->Ap);
         if (ctx->nranks > 1) {
             unsigned long long it0 = 0;
             CUDA_CHECK(cudaMemcpyAsync(&it0, &K->scal->it, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1436,11 +1510,8 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
             int g = (int)((K->comm.plane_dofs + 255) / 256);
             if (g > ctx->sms * 4) g = ctx->sms * 4;
             LAUNCH(ctx, k_halo_push, g, 256, 0, n, K->ghost_cols, (const double *)K->p, K->scal, K->comm, it0 + 1);
-            A.rot = spmv_rotation(ctx, K, variant);
-            launch_spmv<4>(ctx, K, A, variant);
-        } else {
-            launch_spmv<0>(ctx, K, A, variant);
         }
+        spmv_apply(ctx, K, K->p, K->Ap, ctx->nranks > 1);
     }
     LAUNCH(ctx, k_pcg_init, vg, VEC_NT, 0, n, (const double *)K->Ap, (const double *)(warm != 0.0 ? K->r : nullptr),
            (const double *)extra, (const double *)K->diag, (const uint8_t *)K->fixed, K->x, K->r, K->dinv, K->partials, K->scal,
@@ -1458,28 +1529,31 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
     const double bnorm2 = K->h_pinned[2];  // ||b||^2 (== ||r0||^2 for a cold start)
     int it = 0;
     double res2 = rr;
-    SpmvArgs A = make_spmv_args(K, K->p, K->Ap);
-    A.rot = spmv_rotation(ctx, K, variant);
     if (bnorm2 > 0.0) {
         const int chunk = 25;
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t gexec = nullptr;
-        // capture `chunk` iterations once; replay until converged
+        // capture `chunk` iterations once; replay until converged.  One iteration:
+        //   update_p (+ halo push) | SpMV (interior, then boundary planes after the halo flags) | p'Ap | update x, r
+        const int64_t l0 = ctx->launches;
         CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         for (int j = 0; j < chunk; ++j) {
             LAUNCH(ctx, k_pcg_update_p, vg, VEC_NT, 0, n, K->ghost_cols, (const double *)K->r, (const double *)K->dinv, K->p,
                    K->scal, K->comm, 0ull);
-            launch_spmv<7>(ctx, K, A, variant);
+            spmv_apply(ctx, K, K->p, K->Ap, true);
+            LAUNCH(ctx, k_pcg_dot, vg, VEC_NT, 0, n, K->ghost_cols, (const double *)K->p, (const double *)K->Ap, K->partials,
+                   K->scal, K->comm);
             LAUNCH(ctx, k_pcg_update_xr, vg, VEC_NT, 0, n, K->ghost_cols, (const double *)K->p, (const double *)K->Ap,
                    (const double *)K->dinv, K->x, K->r, K->partials, K->scal, K->comm);
         }
+        const int64_t per_replay = ctx->launches - l0;
         CUDA_CHECK(cudaStreamEndCapture(ctx->stream, &graph));
-        ctx->launches -= 3 * chunk;  // captured, not launched; counted per replay below
+        ctx->launches = l0;  // captured, not launched; counted per replay below
         CUDA_CHECK(cudaGraphInstantiate(&gexec, graph, 0));
         const double tol2 = rtol * rtol * bnorm2;
         while (it < maxit && res2 > tol2) {
             CUDA_CHECK(cudaGraphLaunch(gexec, ctx->stream));
-            ctx->launches += 3 * chunk;
+            ctx->launches += per_replay;
             it += chunk;
             fetch(rz, res2);
             if (!(res2 == res2)) break;  // NaN guard
