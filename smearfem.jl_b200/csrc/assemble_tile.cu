@@ -31,7 +31,8 @@ namespace {
 // threads of a node hit such a sub-cube, so their 8-byte banks 9*slot + m (mod 16) are pairwise distinct and, with the
 // node stride == 8 (mod 16), disjoint from those of the second node of the half-warp: the read-modify-write rounds are
 // bank-conflict free (they were exactly 2-way conflicted with the plain [27][9] layout: 148 vs 74 wavefronts per node).
-__constant__ unsigned char c_slot[27] = {5, 7, 20, 6, 3, 22, 2, 23, 17, 4, 18, 9, 1, 0, 29, 21, 12, 26, 13, 15, 28, 14, 11, 30, 10, 31, 25};
+// (the k of same-residue blocks is chosen so that the 27 output lanes also read with few conflicts: 27 vs ideal 18 wavefronts)
+__constant__ unsigned char c_slot[27] = {5, 7, 4, 6, 3, 14, 2, 15, 1, 12, 10, 9, 17, 0, 13, 21, 20, 18, 29, 23, 28, 22, 11, 30, 26, 31, 25};
 constexpr int STAGE_NODE = 32 * 9 + 8;  // 296 doubles per node (== 8 mod 16)
 
 template <int TX_, int TY_>
@@ -41,7 +42,10 @@ struct Tile {
     // doubles per layer in the ring; +3: the two layers a half-warp reads (sz = 0/1) land in disjoint banks
     // (ncu: 2x excess shared wavefronts without the pad)
     static constexpr int PAD = (EX == 9) ? 3 : 8;  // 8x4 tile: banks {6,7,8,15,0,1}+3; 4x4 tile: {10,11,12,15,0,1}+8
-    static constexpr int LAYER = 8 * 8 * 3 * NEL + PAD;
+    // element stride of the ring: 28 instead of 25 for the 4x4 tile makes the slot-dependent g_a loads 2-way instead of
+    // 3-way conflicted (brute-force search over stride / pad; the g_b loads are conflict-free either way)
+    static constexpr int NELP = (EX == 5) ? 28 : NEL;
+    static constexpr int LAYER = 8 * 8 * 3 * NELP + PAD;
     static constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY * 3;  // node-plane coordinate buffer (with halo)
     // the staging area aliases the ring slot of the element layer that is dead after the main loop when it fits (4x4)
     static constexpr bool ALIAS = TX * TY * STAGE_NODE <= LAYER;
@@ -88,12 +92,17 @@ __device__ __forceinline__ void stage_plane(const TileArgs &A, double *s_xyz, in
 template <class T>
 __device__ __forceinline__ void phase1(const TileArgs &A, const double *s_gp, const double *s_sw, const double *s_xyz, double *S,
                                        int layer, int X0, int Y0) {
-    constexpr int NEL = T::NEL, EX = T::EX, LAYER = T::LAYER, NTH = T::NTH;
+    constexpr int NEL = T::NEL, NELP = T::NELP, EX = T::EX, LAYER = T::LAYER, NTH = T::NTH;
     const Lattice &L = A.L;
     double *dst = S + (layer & 1) * LAYER;
     const double *P0 = s_xyz + (layer & 3) * T::PLANE, *P1 = s_xyz + ((layer + 1) & 3) * T::PLANE;
-    for (int q = threadIdx.x; q < 4 * NEL; q += NTH) {  // task = (element, pair of Gauss points)
-        const int gpp = q / NEL, e = q - gpp * NEL;
+    // task = (element, pair of Gauss points).  Tasks are laid out in groups of RND lanes per Gauss-point pair (RND = NEL
+    // rounded up to a warp multiple) so that the lanes of a warp store to consecutive e of ONE (gp, b, c) row of the
+    // ring: no wrap-around bank conflicts (8x4 tile: 45 elements -> 64 lanes per pair, one pass of 256 threads).
+    constexpr int RND = (NEL <= 25) ? NEL : (NEL + 31) / 32 * 32;  // 4x4 tile: dense mapping measured faster (3.1 vs 4 busy warps)
+    for (int q = threadIdx.x; q < 4 * RND; q += NTH) {
+        const int gpp = q / RND, e = q - gpp * RND;
+        if (e >= NEL) continue;
         const int fy = e / EX, fx = e - fy * EX;
         const int ex = X0 - 1 + fx, ey = Y0 - 1 + fy;
         if (ex < 0 || ey < 0 || ex >= L.ne || ey >= L.ne) continue;
@@ -159,7 +168,7 @@ __device__ __forceinline__ void phase1(const TileArgs &A, const double *s_gp, co
                 const int b = oz * 4 + (oy ? (ox ? 2 : 3) : (ox ? 1 : 0));  // reference local numbering (vector3D.jl:94-101)
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    dst[((gp * 8 + b) * 3 + c) * NEL + e] = (d0 * adj[c] + d1 * adj[3 + c] + d2 * adj[6 + c]) * sc;
+                    dst[((gp * 8 + b) * 3 + c) * NELP + e] = (d0 * adj[c] + d1 * adj[3 + c] + d2 * adj[6 + c]) * sc;
             }
         }
     }
@@ -167,7 +176,7 @@ __device__ __forceinline__ void phase1(const TileArgs &A, const double *s_gp, co
 
 template <class T, int MINB>
 __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_constant__ TileArgs A) {
-    constexpr int TX = T::TX, TY = T::TY, NTH = T::NTH, NEL = T::NEL, EX = T::EX, LAYER = T::LAYER;
+    constexpr int TX = T::TX, TY = T::TY, NTH = T::NTH, NEL = T::NELP /* ring stride */, EX = T::EX, LAYER = T::LAYER;
     extern __shared__ double smem[];
     double *S = smem;                             // [2][gp][b][c][e]
     double *stage_own = smem + 2 * LAYER;         // [node][32 slots][9] when not aliased
