@@ -120,7 +120,8 @@ int smfem_mesh_free(smfem_mesh *mesh);
 /* assemble_system(ne,NodeList,IEN,ndim,FunctionClass,nDof,ID,Young,nu)   src/fem.jl:135-256.
  * Builds the sparsity pattern on device (bit-exact with Julia's sparse(E,J,V), src/fem.jl:253:
  * explicit zeros kept, rows ascending per column) and the values (fp64).  nDof==1: scalar Laplace
- * (:199-208); nDof==2: plane stress (:210-217); nDof==3: 3-D isotropic (:218-230).
+ * (:199-208); nDof==2: plane stress (:210-217); nDof==3: 3-D isotropic (:218-230).  func_class SMFEM_Q2 is accepted
+ * where upstream's Q2 is executable: ndim == 2, nDof == 1, 9-node elements, 2x2 Gauss rule (:77-111, :183).
  * The result stays on the device; this rank holds the rows of its owned nodes. */
 int smfem_assemble(smfem_ctx *ctx, smfem_mesh *mesh, int64_t ne, int ndim, int func_class, int nDof, double Young,
                    double nu, smfem_matrix **K_out);

@@ -265,7 +265,8 @@ int smfem_mesh_from_host(smfem_ctx *ctx, const double *NodeList, const int64_t *
         NOTNULL(IEN);
         REQUIRE(ndim == 2 || ndim == 3, SMFEM_ERR_UNSUPPORTED,
                 "assemble_system: the reference's 1-D branch is not executable (src/fem.jl:75 vs :192)");
-        REQUIRE(nLocal == (1 << ndim), SMFEM_ERR_UNSUPPORTED, "only Q1 elements (2^ndim nodes) are built; Q2 is out of scope");
+        REQUIRE(nLocal == (1 << ndim) || (ndim == 2 && nLocal == 9), SMFEM_ERR_UNSUPPORTED,
+                "elements must be Q1 (2^ndim nodes) or the reference's 2-D Q2 quad (9 nodes)");
         REQUIRE(nNodes >= 1 && nEl >= 1 && nNodes < (int64_t)INT32_MAX / 4, SMFEM_ERR_INVALID, "bad mesh sizes");
         REQUIRE(nDof >= 1 && nDof <= 3, SMFEM_ERR_INVALID, "nDof must be 1, 2 or 3");
         REQUIRE(ID != nullptr || nDof == 1, SMFEM_ERR_INVALID, "ID is required when nDof > 1 (reference: MethodError on size(nothing,2))");
@@ -481,6 +482,7 @@ static smfem_matrix *new_matrix(smfem_ctx *ctx, smfem_mesh *mesh, int ndim, int 
     REQUIRE(ndim == mesh->ndim, SMFEM_ERR_INVALID, "ndim does not match the mesh (reference: DimensionMismatch)");
     REQUIRE((ndim == 3 && (nDof == 3 || nDof == 1)) || (ndim == 2 && (nDof == 2 || nDof == 1)), SMFEM_ERR_UNSUPPORTED,
             "supported (ndim,nDof): (3,3) (3,1) (2,2) (2,1)");
+    REQUIRE(mesh->nn != 9 || nDof == 1, SMFEM_ERR_UNSUPPORTED, "9-node (Q2) elements: scalar problems only, as upstream");
     REQUIRE(mesh->structured || mesh->id != nullptr || mesh->nDof_id == nDof || nDof == 1, SMFEM_ERR_INVALID,
             "ID is required when nDof > 1");
     REQUIRE(mesh->structured || mesh->nDof_id == 0 || mesh->nDof_id == nDof || nDof == 1, SMFEM_ERR_INVALID,
@@ -568,7 +570,12 @@ int smfem_assemble(smfem_ctx *ctx, smfem_mesh *mesh, int64_t ne, int ndim, int f
                    smfem_matrix **K_out) {
     int rc = guarded([&] {
         NOTNULL(mesh);
-        REQUIRE(func_class == SMFEM_Q1, SMFEM_ERR_UNSUPPORTED, "only FunctionClass \"Q1\" is built (Q2 is 2-D scalar only upstream)");
+        REQUIRE(func_class == SMFEM_Q1 || func_class == SMFEM_Q2, SMFEM_ERR_INVALID, "unknown FunctionClass");
+        if (func_class == SMFEM_Q2)  // upstream Q2 exists in 2-D only and its nDof > 1 sizing assumes 2^ndim nodes (src/fem.jl:77-111, :143-145)
+            REQUIRE(ndim == 2 && nDof == 1 && mesh->nn == 9, SMFEM_ERR_UNSUPPORTED,
+                    "FunctionClass \"Q2\": only the 2-D scalar case with 9-node elements is executable upstream");
+        else
+            REQUIRE(mesh->nn == (1 << ndim), SMFEM_ERR_INVALID, "FunctionClass \"Q1\" needs 2^ndim nodes per element");
         // the reference loops 1:ne^ndim (src/fem.jl:179) and ignores size(IEN,1)
         int64_t want = 1;
         for (int d = 0; d < ndim; ++d) want *= ne;

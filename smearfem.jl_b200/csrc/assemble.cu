@@ -15,12 +15,13 @@ __constant__ double c_w3[8];
 __constant__ double c_dN2[4][4][2];
 __constant__ double c_N2[4][4];
 __constant__ double c_w2[4];
+__constant__ double c_dNq2[4][9][2];  // Q2 9-node quad gradients at the 2x2 Gauss points (src/fem.jl:90-110, :161-164)
 
 void mesh_upload_tables() {
     double xi[2], w[2];
     smfem_host_gauss(-1, 1, 2, xi, w);
     const int ix[8] = {0, 1, 1, 0, 0, 1, 1, 0}, iy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, iz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
-    double dN3[8][8][3], w3[8], dN2[4][4][2], N2[4][4], w2[4];
+    double dN3[8][8][3], w3[8], dN2[4][4][2], N2[4][4], w2[4], dNq2[4][9][2];
     for (int g = 0; g < 8; ++g) {
         double N[8], dN[24];
         int nn;
@@ -38,12 +39,17 @@ void mesh_upload_tables() {
             for (int d = 0; d < 2; ++d) dN2[g][a][d] = dN[d * 4 + a];
         }
         w2[g] = w[ix[g]] * w[iy[g]];
+        double Nq[9], dNq[18];
+        smfem_host_basis(2, SMFEM_Q2, xi[ix[g]], xi[iy[g]], 0, Nq, dNq, &nn);
+        for (int a = 0; a < 9; ++a)
+            for (int d = 0; d < 2; ++d) dNq2[g][a][d] = dNq[d * 9 + a];
     }
     CUDA_CHECK(cudaMemcpyToSymbol(c_dN3, dN3, sizeof dN3));
     CUDA_CHECK(cudaMemcpyToSymbol(c_w3, w3, sizeof w3));
     CUDA_CHECK(cudaMemcpyToSymbol(c_dN2, dN2, sizeof dN2));
     CUDA_CHECK(cudaMemcpyToSymbol(c_N2, N2, sizeof N2));
     CUDA_CHECK(cudaMemcpyToSymbol(c_w2, w2, sizeof w2));
+    CUDA_CHECK(cudaMemcpyToSymbol(c_dNq2, dNq2, sizeof dNq2));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -463,16 +469,17 @@ struct Material {
     double d11, lam, mu;  // D(1,1), D(1,2), shear
 };
 
-template <int NDIM, int NDOF>
+template <int NDIM, int NDOF, int NN = (1 << NDIM)>  // NN = 9: the reference's Q2 quad (2-D, scalar, 2x2 under-integration)
 __global__ void __launch_bounds__(128)
 k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64_t *__restrict__ rowptr,
                 const int32_t *__restrict__ colind, double *__restrict__ val, Material mat) {
-    constexpr int NN = 1 << NDIM, NGP = 1 << NDIM;
+    constexpr int NGP = 1 << NDIM;
     __shared__ double s_dN[NGP][NN][NDIM];
     __shared__ double s_w[NGP];
     for (int t = threadIdx.x; t < NGP * NN * NDIM; t += blockDim.x) {
         int g = t / (NN * NDIM), rem = t % (NN * NDIM);
-        s_dN[g][rem / NDIM][rem % NDIM] = (NDIM == 3) ? c_dN3[g][rem / NDIM][rem % NDIM] : c_dN2[g][rem / NDIM][rem % NDIM];
+        s_dN[g][rem / NDIM][rem % NDIM] = (NDIM == 3) ? c_dN3[g][(rem / NDIM) % 8][rem % NDIM]
+                                          : (NN == 9 ? c_dNq2[g][rem / NDIM][rem % NDIM] : c_dN2[g][(rem / NDIM) % 4][rem % NDIM]);
     }
     if (threadIdx.x < NGP) s_w[threadIdx.x] = (NDIM == 3) ? c_w3[threadIdx.x] : c_w2[threadIdx.x];
     __syncthreads();
@@ -608,9 +615,11 @@ void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Y
         CUDA_CHECK(cudaMemsetAsync(K->val, 0, sizeof(double) * K->nnz_l, ctx->stream));
         Conn C = make_conn(mesh);
         DofMap D = make_dofmap(mesh, K);
-        const int nn = 1 << ndim;
+        const int nn = mesh->nn;
         unsigned grid = (unsigned)((C.nEl * nn + 127) / 128);
-        if (ndim == 3 && nDof == 3)
+        if (ndim == 2 && nDof == 1 && nn == 9)
+            LAUNCH(ctx, (k_values_atomic<2, 1, 9>), grid, 128, 0, C, D, mesh->coords, K->rowptr, K->colind, K->val, mat);
+        else if (ndim == 3 && nDof == 3)
             LAUNCH(ctx, (k_values_atomic<3, 3>), grid, 128, 0, C, D, mesh->coords, K->rowptr, K->colind, K->val, mat);
         else if (ndim == 3 && nDof == 1)
             LAUNCH(ctx, (k_values_atomic<3, 1>), grid, 128, 0, C, D, mesh->coords, K->rowptr, K->colind, K->val, mat);

@@ -149,6 +149,41 @@ def test_scalar_laplace(ndim, ne):  # nDof = 1: raw node ids, no ID (src/fem.jl:
     assert np.abs(y).max() <= 1e-12 * np.abs(Ko.nzval).max()
 
 
+def _q2_mesh(ne):
+    """Structured 9-node quad mesh on [0,1]^2 in the reference's local ordering (src/fem.jl:80-88: corners CCW,
+    then bottom / right / top / left mid-sides, then centre).  The reference ships no Q2 mesh generator."""
+    n = 2 * ne + 1
+    xs = np.arange(n) / (n - 1)
+    jj, ii = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    NL = np.asfortranarray(np.vstack([xs[ii.ravel()], xs[jj.ravel()]]))
+    nid = lambda i, j: j * n + i + 1
+    IEN = np.zeros((ne * ne, 9), dtype=np.int64)
+    e = 0
+    for ej in range(ne):
+        for ei in range(ne):
+            i0, j0 = 2 * ei, 2 * ej
+            IEN[e] = [nid(i0, j0), nid(i0 + 2, j0), nid(i0 + 2, j0 + 2), nid(i0, j0 + 2), nid(i0 + 1, j0), nid(i0 + 2, j0 + 1),
+                      nid(i0 + 1, j0 + 2), nid(i0, j0 + 1), nid(i0 + 1, j0 + 1)]
+            e += 1
+    return NL, IEN
+
+
+@pytest.mark.parametrize("ne", [1, 3, 6])
+def test_q2_scalar_quads(ne):
+    """FunctionClass "Q2": 2-D scalar, 9-node quads, the reference's 2x2 (under-)integration (src/fem.jl:77-111, :199-208)."""
+    NL, IEN = _q2_mesh(ne)
+    rng = np.random.default_rng(ne)
+    NL[:, :] += rng.uniform(-0.02, 0.02, NL.shape) / ne  # non-affine elements
+    K = sf.assemble_system(ne, NL, IEN, 2, "Q2", 1)
+    Ko = o.assemble_system_literal(ne, NL, IEN, 2, "Q2", 1)
+    assert_csc_parity(K, Ko)
+    assert np.abs(K.spmv(np.ones(K.shape[0]))).max() <= 1e-11 * np.abs(Ko.nzval).max()  # constants in the null space
+    with pytest.raises(sf.SmearFEMError):  # upstream Q2 is scalar-only
+        sf.assemble_system(ne, NL, IEN, 2, "Q2", 2, np.arange(1, 2 * NL.shape[1] + 1).reshape(2, -1).T.copy())
+    with pytest.raises(sf.SmearFEMError):  # Q1 with 9-node connectivity
+        sf.assemble_system(ne, NL, IEN, 2, "Q1", 1)
+
+
 def test_jittered_mesh_no_uniform_shortcut():
     ne = 10
     NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
@@ -276,7 +311,7 @@ def test_error_codes():
     IDbad[0, 0] = IDbad[1, 0]
     with pytest.raises(sf.SmearFEMError):  # not a bijection
         sf.assemble_system(3, NL, IEN, 3, "Q1", 3, IDbad, 40, 0.4)
-    with pytest.raises(sf.SmearFEMError):
+    with pytest.raises(sf.SmearFEMError):  # Q2 is 2-D scalar only
         sf.assemble_system(3, NL, IEN, 3, "Q2", 3, ID, 40, 0.4)
     with pytest.raises(sf.SmearFEMError):  # 1-D branch is not executable upstream either
         sf.assemble_system(3, NL[:1], IEN[:, :2], 1)
