@@ -15,7 +15,12 @@
 //            K_ab = lam G + mu G' + mu tr(G) I   (D(1,1) on the diagonal, src/fem.jl:230), and store the
 //            node's three CSR rows; every stored entry of K is written exactly once (no memset, no
 //            atomics, fold order fixed -> bit-reproducible).
+#include <cmath>
 #include <cstdlib>
+#include <map>
+#include <queue>
+#include <tuple>
+#include <vector>
 
 #include "smfem_internal.cuh"
 
@@ -49,9 +54,14 @@ struct Tile {
     static constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY * 3;  // node-plane coordinate buffer (with halo)
     // the staging area aliases the ring slot of the element layer that is dead after the main loop when it fits (4x4)
     static constexpr bool ALIAS = TX * TY * STAGE_NODE <= LAYER;
+    // per-warp buffer for the CSR-ordered column indices of a run (<= 972 + 3 alignment entries), only where it still
+    // allows 2 CTAs/SM (4x4 tile); the 8x4 tile reuses the staging region and waits for the bulk store instead
+    static constexpr int COLBUF = ALIAS ? 976 : 0;  // int32 per warp
     static constexpr size_t SMEM_BYTES =
-        sizeof(double) * (2 * LAYER + (ALIAS ? 0 : TX * TY * STAGE_NODE) + 8 * 8 * 3 + 8 + 4 * PLANE);
+        sizeof(double) * (2 * LAYER + (ALIAS ? 0 : TX * TY * STAGE_NODE) + 8 * 8 * 3 + 8 + 4 * PLANE) + sizeof(int32_t) * COLBUF * (NTH / 32);
 };
+
+constexpr int MAX_CHUNKS = 24;
 
 struct TileArgs {
     Lattice L;
@@ -61,8 +71,11 @@ struct TileArgs {
     int32_t *colind;  // non-null: the output phase also writes the pattern's column indices (fused assembly)
     double *diag;
     Material mat;
-    int tiles_x, tiles_y, nchunks, chunk;
-    int skip;  // ablation bitmask (env SMFEM_TILE_SKIP; profiling only): 1 phase 1, 2 main loop, 4 combine, 8 output
+    int tiles_x, tiles_y, nchunks;
+    int zb[MAX_CHUNKS + 1];  // chunk c of a tile column = owned planes [zb[c], zb[c+1]) (offsets from L.k0, longest first)
+    int out_mode;  // 0: direct 3x3 block stores, 1: CSR-ordered run in shared memory + coalesced stores, 2: + TMA bulk store
+    int skip;  // ablation bitmask (env SMFEM_TILE_SKIP; profiling only): 1 phase 1, 2 main loop, 4 combine, 8 output,
+               // 16 / 32: column-index / value stores collapsed onto a small cache-resident window (no DRAM traffic)
     double gp[8][3];     // the 8 Gauss points in the reference's order (src/fem.jl:174-176)
     double w[8];
 };
@@ -174,7 +187,66 @@ __device__ __forceinline__ void phase1(const TileArgs &A, const double *s_gp, co
     }
 }
 
-template <class T, int MINB>
+
+// column indices of the <= 4 nodes (jx0.., jy, k) of a warp in CSR order -> Ri[0 .. run_len)
+__device__ __forceinline__ void write_colind_run(const TileArgs &A, int32_t *Ri, bool row_ok, int jx0, int jy, int k, int cy, int cz,
+                                                 int dx, int dy, int dz, int lane) {
+    const Lattice &L = A.L;
+    int off = 0;
+    for (int jn = 0; jn < 4; ++jn) {
+        const int jx = jx0 + jn;
+        if (!(row_ok && jx < L.n1)) break;
+        const int cx = 1 + (jx > 0) + (jx < L.n1 - 1);
+        const int TR = 3 * cx * cy * cz;
+        const int nx = jx + dx, ny = jy + dy, nz = k + dz;
+        if (lane < 27 && nx >= 0 && ny >= 0 && nz >= 0 && nx < L.n1 && ny < L.n1 && nz < L.n1) {
+            const int rank = ((dz + (k > 0)) * cy + (dy + (jy > 0))) * cx + (dx + (jx > 0));
+            const int32_t col = (int32_t)(L.lnode(nx, ny, nz) * 3);
+            int32_t *dst = Ri + off + 3 * rank;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) dst[c * TR + j] = col + j;
+        }
+        off += 3 * TR;
+    }
+}
+
+// ... and out to K.colind[run_base .. run_base + run_len) with one TMA bulk store (16-byte aligned middle; <= 3 + 3
+// head / tail entries by plain stores).  Returns after the bulk copy has finished READING the region.
+template <bool DEFER>
+__device__ __forceinline__ void emit_colind_run(const TileArgs &A, int32_t *Ri, int64_t run_base, int run_len, bool row_ok, int jx0,
+                                                int jy, int k, int cy, int cz, int dx, int dy, int dz, int lane) {
+    const int par4 = (int)(run_base & 3);  // the region mirrors the 16-byte phase of the destination
+    if (A.skip & 16) run_base = par4 + 1024 * (threadIdx.x >> 5);  // ablation: same stores, collapsed onto a cache-resident window
+    // DEFER: Ri is a buffer of its own; the bulk store of the previous plane has had a whole plane of compute to drain
+    if (DEFER && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    write_colind_run(A, Ri + par4, row_ok, jx0, jy, k, cy, cz, dx, dy, dz, lane);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const int64_t a0 = (run_base + 3) & ~(int64_t)3, a1 = (run_base + run_len) & ~(int64_t)3;
+    if (a1 > a0) {
+        if (lane == 0) {
+            const unsigned src = (unsigned)__cvta_generic_to_shared(Ri + par4 + (a0 - run_base));
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(A.colind + a0), "r"(src),
+                         "r"((unsigned)((a1 - a0) * 4))
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (!DEFER) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        } else if (lane < 4) {  // unaligned head (lanes 1..3) ...
+            const int64_t t = run_base + (lane - 1);
+            if (t < a0) A.colind[t] = Ri[par4 + (lane - 1)];
+        } else if (lane < 7) {  // ... and tail (lanes 4..6)
+            const int64_t t = a1 + (lane - 4);
+            if (t < run_base + run_len) A.colind[t] = Ri[par4 + (t - run_base)];
+        }
+    } else {
+        for (int t = lane; t < run_len; t += 32) A.colind[run_base + t] = Ri[par4 + t];
+    }
+}
+
+template <class T, int MINB, int OUT>
 __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_constant__ TileArgs A) {
     constexpr int TX = T::TX, TY = T::TY, NTH = T::NTH, NEL = T::NELP /* ring stride */, EX = T::EX, LAYER = T::LAYER;
     extern __shared__ double smem[];
@@ -183,6 +255,7 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
     double *s_dN = stage_own + (T::ALIAS ? 0 : TX * TY * STAGE_NODE);  // [gp][3]: Gauss-point coordinates (xi, eta, zeta)
     double *s_w = s_dN + 8 * 8 * 3;   // sqrt of the Gauss weights
     double *s_xyz = s_w + 8;          // [4][PLANE] node-plane coordinate ring
+    int32_t *s_col = reinterpret_cast<int32_t *>(s_xyz + 4 * T::PLANE);  // [warp][COLBUF]
     const Lattice &L = A.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int t = tid; t < 8 * 3; t += NTH) s_dN[t] = (&A.gp[0][0])[t];
@@ -194,8 +267,7 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
     const int tiy = bid % A.tiles_y;
     const int chunk_id = bid / A.tiles_y;
     const int X0 = tix * TX, Y0 = tiy * TY;
-    const int zs = L.k0 + chunk_id * A.chunk;
-    const int ze = min(zs + A.chunk, L.k1);
+    const int zs = L.k0 + A.zb[chunk_id], ze = L.k0 + A.zb[chunk_id + 1];
 
     // phase-2 identity of this thread
     const int s = lane & 7, nt = warp * 4 + (lane >> 3);
@@ -275,49 +347,157 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
             const int b = obz * 4 + (oby ? (obx ? 2 : 3) : (obx ? 1 : 0));  // reference local numbering
             if (!(A.skip & 4)) {
                 double *dst = my_stage + soff[beta];
-                if ((s & beta) == 0) {
+                if (beta == 0) {
 #pragma unroll
                     for (int m = 0; m < 9; ++m) dst[m] = G[b][m];
                 } else {
+                    // branch-free: a divergent store / read-modify-write pair would issue the 9 stores twice per round
+                    // (first-touch lanes read a stale value that the select discards)
+                    const bool first = (s & beta) == 0;
+                    double old[9];
 #pragma unroll
-                    for (int m = 0; m < 9; ++m) dst[m] += G[b][m];
+                    for (int m = 0; m < 9; ++m) old[m] = dst[m];
+#pragma unroll
+                    for (int m = 0; m < 9; ++m) dst[m] = first ? G[b][m] : old[m] + G[b][m];
                 }
             }
             __syncwarp();
         }
         // ---- output: lane q < 27 owns neighbour q of each of the warp's 4 nodes -----------------------------
-        if (lane < 27 && !(A.skip & 8)) {
+        // The warp's 4 nodes are consecutive in x, so their 12 CSR rows are ONE contiguous run of K.val (<= 972 entries).
+        // out_mode 0: every lane stores its 3x3 block straight to global memory (8-byte pieces with a 24-byte lane stride:
+        //             each warp store touches 21 sectors partially -> 3x the L2 write requests of the data).
+        // out_mode 1: the blocks are first permuted into CSR order IN PLACE in the warp's staging region (node jn's final
+        //             range [243 jn, 243 jn + 243) only overlaps the staging of nodes <= jn, which are consumed by then),
+        //             then the run leaves with full-sector coalesced stores.
+        // out_mode 2: same, but the run is written by one TMA bulk store (cp.async.bulk.global.shared::cta).
+        if (!(A.skip & 8)) {
             const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
-            for (int jn = 0; jn < 4; ++jn) {
-                const int n2 = warp * 4 + jn;
-                const int jx = X0 + n2 % TX, jy = Y0 + n2 / TX;
-                if (jx >= L.n1 || jy >= L.n1) continue;
-                const int nx = jx + dx, ny = jy + dy, nz = k + dz;
-                if (nx < 0 || ny < 0 || nz < 0 || nx >= L.n1 || ny >= L.n1 || nz >= L.n1) continue;
-                const int cx = 1 + (jx > 0) + (jx < L.n1 - 1), cy = 1 + (jy > 0) + (jy < L.n1 - 1),
-                          cz = 1 + (k > 0) + (k < L.n1 - 1);
-                const int rank = ((dz + (k > 0)) * cy + (dy + (jy > 0))) * cx + (dx + (jx > 0));
-                const int T = 3 * cx * cy * cz;
-                const int64_t row = (((int64_t)(k - L.k0) * L.n1 + jy) * L.n1 + jx) * 3;
-                const int64_t pairs = pre1(k) * S1 * S1 + (int64_t)cz * (pre1(jy) * S1 + (int64_t)cy * pre1(jx)) - pairs_base;
-                const int64_t base = 9 * pairs + 3 * rank;
-                const double *g = stage + n2 * STAGE_NODE + out_off;
-                const double tr = g[0] + g[4] + g[8];
+            const int jy = Y0 + (warp * 4) / TX, jx0 = X0 + (warp * 4) % TX;
+            const int cy = 1 + (jy > 0) + (jy < L.n1 - 1), cz = 1 + (k > 0) + (k < L.n1 - 1);
+            const bool row_ok = jy < L.n1 && jx0 < L.n1;
+            const int64_t run_base =
+                9 * (pre1(k) * S1 * S1 + (int64_t)cz * (pre1(jy) * S1 + (int64_t)cy * pre1(jx0)) - pairs_base);
+            double *R = stage + warp * 4 * STAGE_NODE;
+            if (OUT == 0 || OUT == 3) {
+                int64_t base_n = run_base;
+                if (lane < 27 && row_ok) {
+                    for (int jn = 0; jn < 4; ++jn) {
+                        const int n2 = warp * 4 + jn, jx = jx0 + jn;
+                        if (jx >= L.n1) break;
+                        const int cx = 1 + (jx > 0) + (jx < L.n1 - 1);
+                        const int TR = 3 * cx * cy * cz;
+                        const int nx = jx + dx, ny = jy + dy, nz = k + dz;
+                        if (nx >= 0 && ny >= 0 && nz >= 0 && nx < L.n1 && ny < L.n1 && nz < L.n1) {
+                            const int rank = ((dz + (k > 0)) * cy + (dy + (jy > 0))) * cx + (dx + (jx > 0));
+                            const int64_t row = (((int64_t)(k - L.k0) * L.n1 + jy) * L.n1 + jx) * 3;
+                            const int64_t base = ((A.skip & 32) ? (base_n & 1023) + 1024 * warp : base_n) + 3 * rank;  // 32: ablation
+                            const double *g = stage + n2 * STAGE_NODE + out_off;
+                            const double tr = g[0] + g[4] + g[8];
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
+                            for (int c = 0; c < 3; ++c)
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const double gij = g[c * 3 + j], gji = g[j * 3 + c];
-                        const double v = (c == j) ? A.mat.d11 * gij + A.mat.mu * (tr - gij) : A.mat.lam * gij + A.mat.mu * gji;
-                        A.val[base + (int64_t)c * T + j] = v;
-                        if (lane == 13 && c == j) A.diag[row + c] = v;
-                        if (A.colind) A.colind[base + (int64_t)c * T + j] = (int32_t)(L.lnode(nx, ny, nz) * 3 + j);
+                                for (int j = 0; j < 3; ++j) {
+                                    const double gij = g[c * 3 + j], gji = g[j * 3 + c];
+                                    const double v =
+                                        (c == j) ? A.mat.d11 * gij + A.mat.mu * (tr - gij) : A.mat.lam * gij + A.mat.mu * gji;
+                                    A.val[base + (int64_t)c * TR + j] = v;
+                                    if (lane == 13 && c == j) A.diag[row + c] = v;
+                                    if (OUT == 0 && A.colind)
+                                        A.colind[base + (int64_t)c * TR + j] = (int32_t)(L.lnode(nx, ny, nz) * 3 + j);
+                                }
+                        }
+                        base_n += 3 * TR;
                     }
+                }
+                if (OUT == 3 && A.colind) {
+                    // column indices: built in CSR order in the warp's staging region (dead now) and written by one TMA bulk store
+                    base_n = __shfl_sync(0xffffffffu, base_n, 0);
+                    const int run_len = (int)(base_n - run_base);
+                    if (T::COLBUF)
+                        emit_colind_run<true>(A, s_col + warp * T::COLBUF, run_base, run_len, row_ok, jx0, jy, k, cy, cz, dx, dy, dz, lane);
+                    else
+                        emit_colind_run<false>(A, reinterpret_cast<int32_t *>(R), run_base, run_len, row_ok, jx0, jy, k, cy, cz, dx, dy, dz, lane);
+                }
+            } else {
+                const int par = (int)(run_base & 1);
+                int run_len = 0;
+                for (int jn = 0; jn < 4; ++jn) {
+                    const int n2 = warp * 4 + jn, jx = jx0 + jn;
+                    const bool n_ok = row_ok && jx < L.n1;
+                    const int cx = 1 + (jx > 0) + (jx < L.n1 - 1);
+                    const int TR = 3 * cx * cy * cz;
+                    const int nx = jx + dx, ny = jy + dy, nz = k + dz;
+                    const bool ok = n_ok && lane < 27 && nx >= 0 && ny >= 0 && nz >= 0 && nx < L.n1 && ny < L.n1 && nz < L.n1;
+                    const int rank = ((dz + (k > 0)) * cy + (dy + (jy > 0))) * cx + (dx + (jx > 0));
+                    double v[9];
+                    if (ok) {
+                        const double *g = stage + n2 * STAGE_NODE + out_off;
+                        double gg[9];
+#pragma unroll
+                        for (int m = 0; m < 9; ++m) gg[m] = g[m];
+                        const double tr = gg[0] + gg[4] + gg[8];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+                                const double gij = gg[c * 3 + j], gji = gg[j * 3 + c];
+                                v[c * 3 + j] = (c == j) ? A.mat.d11 * gij + A.mat.mu * (tr - gij) : A.mat.lam * gij + A.mat.mu * gji;
+                            }
+                        if (lane == 13) {
+                            const int64_t row = (((int64_t)(k - L.k0) * L.n1 + jy) * L.n1 + jx) * 3;
+                            A.diag[row] = v[0];
+                            A.diag[row + 1] = v[4];
+                            A.diag[row + 2] = v[8];
+                        }
+                    }
+                    __syncwarp();  // node jn's staging has been read by every lane: its area may now be overwritten
+                    if (ok) {
+                        double *dst = R + par + run_len + 3 * rank;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) dst[c * TR + j] = v[c * 3 + j];
+                    }
+                    if (n_ok) run_len += 3 * TR;
+                }
+                if (OUT == 1) {
+                    __syncwarp();
+                    for (int t = lane; t < run_len; t += 32) A.val[run_base + t] = R[par + t];
+                } else {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && run_len > 0) {
+                        const int64_t a0 = run_base + par, a1 = (run_base + run_len) & ~(int64_t)1;
+                        if (par) A.val[run_base] = R[par];
+                        if (a1 < run_base + run_len) A.val[a1] = R[par + (a1 - run_base)];
+                        if (a1 > a0) {
+                            const unsigned src = (unsigned)__cvta_generic_to_shared(R + 2 * par);
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(A.val + a0), "r"(src),
+                                         "r"((unsigned)((a1 - a0) * 8))
+                                         : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        }
+                    }
+                }
+                if (A.colind) {  // fused assembly: the pattern's column indices take the same route through the region
+                    if (OUT == 1) {
+                        int32_t *Ri = reinterpret_cast<int32_t *>(R);
+                        __syncwarp();
+                        write_colind_run(A, Ri, row_ok, jx0, jy, k, cy, cz, dx, dy, dz, lane);
+                        __syncwarp();
+                        for (int t = lane; t < run_len; t += 32) A.colind[run_base + t] = Ri[t];
+                    } else {
+                        emit_colind_run<false>(A, reinterpret_cast<int32_t *>(R), run_base, run_len, row_ok, jx0, jy, k, cy, cz, dx, dy, dz, lane);
+                    }
+                }
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();  // staging + ring slot (k-1)&1 are reused by the next plane; coordinate plane k+2 has landed
     }
+    if (OUT == 3 && T::COLBUF && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem must outlive the last bulk store
 }
 
 }  // namespace
@@ -327,23 +507,88 @@ bool values_tile_enabled() {
     return !(e && std::string(e) == "atomic");
 }
 
-template <class T, int MINB>
+// Split the owned planes of a tile column into chunks (one CTA each).  The hardware hands CTAs to free slots in blockIdx
+// order (chunk-major here), i.e. list scheduling; CTAs of equal length in a grid that is not a multiple of the resident
+// slot count leave a tail (100^3 on 296 slots: 2704 CTAs of 26 planes = 9.13 waves -> 10).  Candidates: 1..MAX_CHUNKS
+// chunks whose lengths decay geometrically (long chunks first, short ones fill the tail); the makespan of each is
+// simulated with duration = planes + c0 (prologue: one extra element layer, pipeline fill) and the best one is kept
+// (100^3: 55 + 30 + 16 planes, modelled makespan 242 plane-times instead of 270; ideal 231).
+static std::vector<int> plan_chunks(int ntiles, int nown, int slots) {
+    if (const char *e = std::getenv("SMFEM_TILE_CHUNKS")) {  // experiments: explicit comma-separated lengths
+        std::vector<int> len;
+        int sum = 0;
+        for (const char *p = e; *p;) {
+            len.push_back(std::atoi(p));
+            sum += len.back();
+            while (*p && *p != ',') ++p;
+            if (*p == ',') ++p;
+        }
+        if (sum == nown && (int)len.size() <= MAX_CHUNKS) return len;
+    }
+    static std::map<std::tuple<int, int, int>, std::vector<int>> cache;
+    const auto key = std::make_tuple(ntiles, nown, slots);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    double c0 = 1.0;
+    if (const char *e = std::getenv("SMFEM_TILE_C0")) c0 = std::atof(e);
+    const int minlen = 4;
+    const double cap = std::max((double)minlen, (double)ntiles * nown / slots / 4);  // keep >= ~4 rounds of CTAs: the model is idealised
+    std::vector<int> best;
+    double best_t = 1e300;
+    const double ratios[] = {1.0, 0.9, 0.8, 0.7, 0.6, 0.5};
+    for (int nc = 1; nc <= MAX_CHUNKS && nc * minlen <= std::max(nown, minlen); ++nc)
+        for (double r : ratios) {
+            if (nc == 1 && r != 1.0) continue;
+            // lengths proportional to r^i, at least minlen, summing to nown
+            std::vector<int> len(nc, minlen);
+            int rest = nown - nc * minlen;
+            if (rest < 0) { len.assign(1, nown); rest = 0; }
+            double wsum = 0;
+            for (int i = 0; i < (int)len.size(); ++i) wsum += std::pow(r, i);
+            int given = 0;
+            for (int i = 0; i < (int)len.size(); ++i) {
+                const int g = (int)std::floor(rest * std::pow(r, i) / wsum);
+                len[i] += g;
+                given += g;
+            }
+            for (int i = 0; given < rest; i = (i + 1) % (int)len.size(), ++given) ++len[i];
+            if (len[0] > cap && (nc + 1) * minlen <= nown && nc < MAX_CHUNKS) continue;
+            // list scheduling: all CTAs of a chunk have the same duration
+            std::priority_queue<double, std::vector<double>, std::greater<double>> free_at;
+            for (int i = 0; i < slots; ++i) free_at.push(0.0);
+            double span = 0;
+            for (int c = 0; c < (int)len.size(); ++c)
+                for (int t = 0; t < ntiles; ++t) {
+                    const double end = free_at.top() + len[c] + c0;
+                    free_at.pop();
+                    free_at.push(end);
+                    span = std::max(span, end);
+                }
+            if (span < best_t - 1e-9) {
+                best_t = span;
+                best = len;
+            }
+        }
+    cache[key] = best;
+    return best;
+}
+
+template <class T, int MINB, int OUT>
 static void launch_tile(smfem_ctx *ctx, TileArgs &A, int nown) {
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_values_tile<T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(k_values_tile<T, MINB, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES));
         attr_set = true;
     }
     A.tiles_x = (A.L.n1 + T::TX - 1) / T::TX;
     A.tiles_y = (A.L.n1 + T::TY - 1) / T::TY;
     const int ntiles = A.tiles_x * A.tiles_y;
-    int nchunks = (ctx->sms * 8 * MINB + ntiles - 1) / ntiles;  // aim at >= 8 CTAs per resident slot over the run
-    if (nchunks > nown / 6) nchunks = nown / 6;                  // but keep chunks >= 6 planes (prologue layer amortised)
-    if (nchunks < 1) nchunks = 1;
-    A.chunk = (nown + nchunks - 1) / nchunks;
-    A.nchunks = (nown + A.chunk - 1) / A.chunk;
+    const std::vector<int> len = plan_chunks(ntiles, nown, ctx->sms * MINB);
+    A.nchunks = (int)len.size();
+    A.zb[0] = 0;
+    for (int c = 0; c < A.nchunks; ++c) A.zb[c + 1] = A.zb[c] + len[c];
     const unsigned grid = (unsigned)(ntiles * A.nchunks);
-    LAUNCH(ctx, (k_values_tile<T, MINB>), grid, T::NTH, T::SMEM_BYTES, A);
+    LAUNCH(ctx, (k_values_tile<T, MINB, OUT>), grid, T::NTH, T::SMEM_BYTES, A);
 }
 
 void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind) {
@@ -370,10 +615,22 @@ void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Mat
     {
         const char *sk = std::getenv("SMFEM_TILE_SKIP");
         A.skip = sk ? std::atoi(sk) : 0;
+        const char *om = std::getenv("SMFEM_TILE_OUT");
+        A.out_mode = om ? std::atoi(om) : 3;
     }
     const char *e = std::getenv("SMFEM_TILE");
-    if (e && std::string(e) == "8x4")
-        launch_tile<Tile<8, 4>, 1>(ctx, A, A.L.nown());   // 256 threads, 200 KB smem, 1 CTA/SM
-    else
-        launch_tile<Tile<4, 4>, 2>(ctx, A, A.L.nown());   // 128 threads, 108 KB smem, 2 CTAs/SM (phases overlap)
+    const bool big = e && std::string(e) == "8x4";  // 256 threads, 1 CTA/SM; default 4x4: 128 threads, 2 CTAs/SM
+#define SMFEM_TILE_CASE(M)                                              \
+    case M:                                                             \
+        if (big) launch_tile<Tile<8, 4>, 1, M>(ctx, A, A.L.nown());     \
+        else launch_tile<Tile<4, 4>, 2, M>(ctx, A, A.L.nown());         \
+        break;
+    switch (A.out_mode) {
+        SMFEM_TILE_CASE(1)
+        SMFEM_TILE_CASE(2)
+        SMFEM_TILE_CASE(3)
+        default:
+        SMFEM_TILE_CASE(0)
+    }
+#undef SMFEM_TILE_CASE
 }

@@ -254,11 +254,23 @@ def test_tile_and_atomic_value_kernels_agree(monkeypatch):
     monkeypatch.delenv("SMFEM_DEBUG_CLEAR")
     assert_csc_parity(K, Ko)
     assert np.array_equal(K.to_csc()[2], nz1)
+    # every tile shape x output route (0 direct block stores, 1 CSR-ordered run + coalesced stores, 2 TMA bulk store) x chunk
+    # plan writes every entry of val / colind / diag and gives the same bits
+    monkeypatch.setenv("SMFEM_DEBUG_CLEAR", "1")
     for tile in ("8x4", "4x4"):
-        monkeypatch.setenv("SMFEM_TILE", tile)
-        K.reassemble(40, 0.4)
-        assert_csc_parity(K, Ko)
-    monkeypatch.delenv("SMFEM_TILE")
+        for out in ("0", "1", "2", "3"):
+            for chunks in (None, "5,4,5", "14"):
+                monkeypatch.setenv("SMFEM_TILE", tile)
+                monkeypatch.setenv("SMFEM_TILE_OUT", out)
+                if chunks:
+                    monkeypatch.setenv("SMFEM_TILE_CHUNKS", chunks)
+                K.reassemble(40, 0.4)
+                assert_csc_parity(K, Ko)
+                assert np.array_equal(K.to_csc()[2], nz1), (tile, out, chunks)
+                assert np.array_equal(K.diag(), d1), (tile, out, chunks)
+                monkeypatch.delenv("SMFEM_TILE_CHUNKS", raising=False)
+    for v in ("SMFEM_TILE", "SMFEM_TILE_OUT", "SMFEM_DEBUG_CLEAR"):
+        monkeypatch.delenv(v)
     monkeypatch.setenv("SMFEM_VALUES", "atomic")
     K.assemble_values(40, 0.4)
     assert_csc_parity(K, Ko)

@@ -14,3 +14,16 @@ for skip, name in [(0, "full"), (1, "no phase1"), (2, "no main loop"), (4, "no c
     for _ in range(5):
         K.assemble_values(40.0, 0.4)
     print(f"skip={skip:2d} {name:14s}: {ctx.timer_stop()/5:.3f} ms")
+# store ablation: 16 / 32 collapse the column-index / value stores onto a small cache-resident window (same instructions, no DRAM)
+for skip in (0, 16, 32, 48, 8):
+    os.environ["SMFEM_TILE_SKIP"] = str(skip)
+    for _ in range(2):
+        K.reassemble(40.0, 0.4)
+    ctx.timer_start()
+    for _ in range(5):
+        K.reassemble(40.0, 0.4)
+    f = ctx.timer_stop() / 5
+    ctx.timer_start()
+    for _ in range(5):
+        K.assemble_values(40.0, 0.4)
+    print(f"skip={skip:2d}: fused {f:.3f} ms, values {ctx.timer_stop()/5:.3f} ms")
