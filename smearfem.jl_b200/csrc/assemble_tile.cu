@@ -73,7 +73,7 @@ struct TileArgs {
     Material mat;
     int tiles_x, tiles_y, nchunks;
     int zb[MAX_CHUNKS + 1];  // chunk c of a tile column = owned planes [zb[c], zb[c+1]) (offsets from L.k0, longest first)
-    int out_mode;  // 0: direct 3x3 block stores, 1: CSR-ordered run in shared memory + coalesced stores, 2: + TMA bulk store
+    int out_mode;  // output route of the tile kernel (env SMFEM_TILE_OUT): see the output phase
     int skip;  // ablation bitmask (env SMFEM_TILE_SKIP; profiling only): 1 phase 1, 2 main loop, 4 combine, 8 output,
                // 16 / 32: column-index / value stores collapsed onto a small cache-resident window (no DRAM traffic)
     double gp[8][3];     // the 8 Gauss points in the reference's order (src/fem.jl:174-176)
@@ -364,13 +364,15 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
             __syncwarp();
         }
         // ---- output: lane q < 27 owns neighbour q of each of the warp's 4 nodes -----------------------------
-        // The warp's 4 nodes are consecutive in x, so their 12 CSR rows are ONE contiguous run of K.val (<= 972 entries).
-        // out_mode 0: every lane stores its 3x3 block straight to global memory (8-byte pieces with a 24-byte lane stride:
-        //             each warp store touches 21 sectors partially -> 3x the L2 write requests of the data).
-        // out_mode 1: the blocks are first permuted into CSR order IN PLACE in the warp's staging region (node jn's final
-        //             range [243 jn, 243 jn + 243) only overlaps the staging of nodes <= jn, which are consumed by then),
-        //             then the run leaves with full-sector coalesced stores.
-        // out_mode 2: same, but the run is written by one TMA bulk store (cp.async.bulk.global.shared::cta).
+        // The warp's 4 nodes are consecutive in x, so their 12 CSR rows are ONE contiguous run of K.val / K.colind (<= 972 entries).
+        // OUT 0: every lane stores its 3x3 block (values and column indices) straight to global memory.
+        // OUT 2: values and column indices are first permuted into CSR order IN PLACE in the warp's staging region (node
+        //        jn's final range [243 jn, 243 jn + 243) only overlaps the staging of nodes <= jn, which are consumed by
+        //        then) and leave by TMA bulk stores (cp.async.bulk.global.shared::cta).
+        // OUT 3 (default): values as in 0, column indices as CSR-ordered runs in a buffer of their own + TMA bulk store.
+        // Measured at 100^3 (values / fused, ms): 0: 1.39 / 1.72, 2: 1.45 / 1.62, 3: 1.39 / 1.56.  The kernel is bound by
+        // L1TEX wavefronts (shared memory AND global stores): the 4-byte index stores with a 12-byte lane stride are the
+        // expensive ones; for the values the extra shared-memory round trip of 2 costs what the scattered stores cost.
         if (!(A.skip & 8)) {
             const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
             const int jy = Y0 + (warp * 4) / TX, jx0 = X0 + (warp * 4) % TX;
@@ -394,18 +396,20 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
                             const int64_t base = ((A.skip & 32) ? (base_n & 1023) + 1024 * warp : base_n) + 3 * rank;  // 32: ablation
                             const double *g = stage + n2 * STAGE_NODE + out_off;
                             const double tr = g[0] + g[4] + g[8];
+                            {
 #pragma unroll
-                            for (int c = 0; c < 3; ++c)
+                                for (int c = 0; c < 3; ++c)
 #pragma unroll
-                                for (int j = 0; j < 3; ++j) {
-                                    const double gij = g[c * 3 + j], gji = g[j * 3 + c];
-                                    const double v =
-                                        (c == j) ? A.mat.d11 * gij + A.mat.mu * (tr - gij) : A.mat.lam * gij + A.mat.mu * gji;
-                                    A.val[base + (int64_t)c * TR + j] = v;
-                                    if (lane == 13 && c == j) A.diag[row + c] = v;
-                                    if (OUT == 0 && A.colind)
-                                        A.colind[base + (int64_t)c * TR + j] = (int32_t)(L.lnode(nx, ny, nz) * 3 + j);
-                                }
+                                    for (int j = 0; j < 3; ++j) {
+                                        const double gij = g[c * 3 + j], gji = g[j * 3 + c];
+                                        const double v =
+                                            (c == j) ? A.mat.d11 * gij + A.mat.mu * (tr - gij) : A.mat.lam * gij + A.mat.mu * gji;
+                                        A.val[base + (int64_t)c * TR + j] = v;
+                                        if (lane == 13 && c == j) A.diag[row + c] = v;
+                                        if (OUT == 0 && A.colind)
+                                            A.colind[base + (int64_t)c * TR + j] = (int32_t)(L.lnode(nx, ny, nz) * 3 + j);
+                                    }
+                            }
                         }
                         base_n += 3 * TR;
                     }
@@ -461,10 +465,7 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
                     }
                     if (n_ok) run_len += 3 * TR;
                 }
-                if (OUT == 1) {
-                    __syncwarp();
-                    for (int t = lane; t < run_len; t += 32) A.val[run_base + t] = R[par + t];
-                } else {
+                {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0 && run_len > 0) {
@@ -482,15 +483,7 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
                     }
                 }
                 if (A.colind) {  // fused assembly: the pattern's column indices take the same route through the region
-                    if (OUT == 1) {
-                        int32_t *Ri = reinterpret_cast<int32_t *>(R);
-                        __syncwarp();
-                        write_colind_run(A, Ri, row_ok, jx0, jy, k, cy, cz, dx, dy, dz, lane);
-                        __syncwarp();
-                        for (int t = lane; t < run_len; t += 32) A.colind[run_base + t] = Ri[t];
-                    } else {
-                        emit_colind_run<false>(A, reinterpret_cast<int32_t *>(R), run_base, run_len, row_ok, jx0, jy, k, cy, cz, dx, dy, dz, lane);
-                    }
+                    emit_colind_run<false>(A, reinterpret_cast<int32_t *>(R), run_base, run_len, row_ok, jx0, jy, k, cy, cz, dx, dy, dz, lane);
                 }
             }
         }
@@ -626,7 +619,6 @@ void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Mat
         else launch_tile<Tile<4, 4>, 2, M>(ctx, A, A.L.nown());         \
         break;
     switch (A.out_mode) {
-        SMFEM_TILE_CASE(1)
         SMFEM_TILE_CASE(2)
         SMFEM_TILE_CASE(3)
         default:
