@@ -125,6 +125,19 @@ int smfem_mesh_free(smfem_mesh *mesh);
  * The result stays on the device; this rank holds the rows of its owned nodes. */
 int smfem_assemble(smfem_ctx *ctx, smfem_mesh *mesh, int64_t ne, int ndim, int func_class, int nDof, double Young,
                    double nu, smfem_matrix **K_out);
+/* assemble_system with the reference's HOST arguments in one call (src/fem.jl:135: ne, NodeList, IEN, ndim, FunctionClass,
+ * nDof, ID, Young, nu): smfem_mesh_from_host + smfem_assemble.  When the sizes match meshgrid's hex lattice (examples/
+ * vector3D.jl:10) the transfers and the work overlap: NodeList is copied first and the assembly starts from the
+ * coordinates alone, while IEN and ID (4.7x the bytes) are checked against the lattice numbering - chunks from the front
+ * through PCIe and a check kernel on a second stream, chunks from the back by host threads (env SMFEM_HOST_THREADS, default
+ * min(4, usable cores - 1); 0 = PCIe only); a failed check discards the speculative result and takes the general path.  Returns once
+ * every host array has been read; the matrix may still be in flight on the context's stream (any later call orders behind it).
+ * Outputs: the mesh handle (needed by surface_mass / set_dirichlet_zplanes) and the matrix handle. */
+int smfem_assemble_system(smfem_ctx *ctx, const double *NodeList, const int64_t *IEN, const int64_t *ID, int64_t nNodes,
+                          int64_t nEl, int nLocal, int64_t ne, int ndim, int func_class, int nDof, double Young, double nu,
+                          smfem_mesh **mesh_out, smfem_matrix **K_out);
+/* cumulative bytes moved host->device / device->host by the bulk transfers of the calls above (bench.py's e2e accounting) */
+int smfem_transfer_bytes(smfem_ctx *ctx, int64_t *h2d, int64_t *d2h);
 /* The two halves of smfem_assemble, for timing them separately. */
 int smfem_pattern_build(smfem_ctx *ctx, smfem_mesh *mesh, int ndim, int nDof, smfem_matrix **K_out);
 int smfem_assemble_values(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu);

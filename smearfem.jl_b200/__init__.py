@@ -470,8 +470,21 @@ def assemble_system(ne, NodeList, IEN, ndim, FunctionClass="Q1", nDof=1, ID=None
     ctx = context()
     if nDof > 1 and ID is None:
         raise SmearFEMError(_lib.ERR_INVALID, "ID is required when nDof > 1 (reference: MethodError size(nothing, 2))")
-    mesh = Mesh.from_host(ctx, NodeList, IEN, ID if nDof > 1 else None, ndim, nDof, ne)
-    return SparseMatrixB200.assemble(ctx, mesh, ne, ndim, FunctionClass, nDof, Young, nu)
+    NodeList = np.asfortranarray(NodeList, dtype=np.float64)
+    IEN = np.asfortranarray(IEN, dtype=np.int64)
+    if NodeList.ndim != 2 or NodeList.shape[0] != ndim:
+        raise SmearFEMError(_lib.ERR_INVALID, "NodeList must be ndim x nNodes (reference: DimensionMismatch)")
+    IDa = None if (ID is None or nDof == 1) else np.asfortranarray(ID, dtype=np.int64)
+    if IDa is not None and (IDa.ndim != 2 or IDa.shape[0] != NodeList.shape[1]):
+        raise SmearFEMError(_lib.ERR_INVALID, "ID must be nNodes x nDof")
+    nd = nDof if IDa is None else IDa.shape[1]
+    if nd != nDof:  # size(ID,2) != nDof: let the two-step path report it like before
+        mesh = Mesh.from_host(ctx, NodeList, IEN, IDa, ndim, nDof, ne)
+        return SparseMatrixB200.assemble(ctx, mesh, ne, ndim, FunctionClass, nDof, Young, nu)
+    mh, kh = C.c_void_p(), C.c_void_p()
+    call("smfem_assemble_system", ctx.handle, _pf(NodeList), _pi(IEN), _pi(IDa), NodeList.shape[1], IEN.shape[0], IEN.shape[1],
+         int(ne), int(ndim), _fclass(FunctionClass), int(nDof), float(Young), float(nu), C.byref(mh), C.byref(kh))
+    return SparseMatrixB200(ctx, kh, Mesh(ctx, mh))
 
 
 def apply_boundary_conditions(ne, NodeList, IEN, IEN_top, IEN_btm, ndim, FunctionClass, ID, nDof=3):

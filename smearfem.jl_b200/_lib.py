@@ -51,6 +51,9 @@ SIGNATURES = {
     "smfem_mesh_export": [_vp, _vp, _f64p, _i64p, _i64p, _i64p, _i64p],
     "smfem_mesh_free": [_vp],
     "smfem_assemble": [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(_vp)],
+    "smfem_assemble_system": [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64, C.c_int64, C.c_int,
+                              C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(_vp), C.POINTER(_vp)],
+    "smfem_transfer_bytes": [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     "smfem_pattern_build": [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)],
     "smfem_assemble_values": [_vp, _vp, _vp, C.c_double, C.c_double],
     "smfem_pattern_rebuild": [_vp, _vp, _vp],

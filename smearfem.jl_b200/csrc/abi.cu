@@ -162,6 +162,13 @@ int smfem_init(int device, int rank, int nranks, smfem_ctx **out) {
         CUDA_CHECK(cudaEventCreate(&c->ev1));
         CUDA_CHECK(cudaEventCreate(&c->ev2));
         CUDA_CHECK(cudaEventCreate(&c->ev3));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_nodes, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_check, cudaEventDisableTiming));
+        CUDA_CHECK(cudaMallocHost(&c->h_flags, 4 * sizeof(int)));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_stage[0], cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_stage[1], cudaEventDisableTiming));
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         c->sms = prop.multiProcessorCount;
@@ -181,6 +188,15 @@ int smfem_destroy(smfem_ctx *ctx) {
         cudaEventDestroy(ctx->ev1);
         cudaEventDestroy(ctx->ev2);
         cudaEventDestroy(ctx->ev3);
+        cudaStreamSynchronize(ctx->copy_stream);
+        host_pool_destroy(ctx);
+        cudaEventDestroy(ctx->ev_stage[0]);
+        cudaEventDestroy(ctx->ev_stage[1]);
+        cudaEventDestroy(ctx->ev_fork);
+        cudaEventDestroy(ctx->ev_nodes);
+        cudaEventDestroy(ctx->ev_check);
+        cudaStreamDestroy(ctx->copy_stream);
+        cudaFreeHost(ctx->h_flags);
         cudaStreamDestroy(ctx->stream);
         delete ctx;
     });
@@ -281,6 +297,7 @@ int smfem_mesh_from_host(smfem_ctx *ctx, const double *NodeList, const int64_t *
         // stage the Int64 arrays on the device
         int64_t *d_ien = dev_alloc<int64_t>(nEl * nLocal), *d_id = nullptr;
         CUDA_CHECK(cudaMemcpyAsync(d_ien, IEN, 8 * nEl * nLocal, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += 8 * nEl * nLocal + (ID ? 8 * nNodes * nDof : 0) + 8 * (int64_t)ndim * nNodes;
         if (ID) {
             d_id = dev_alloc<int64_t>(nNodes * nDof);
             CUDA_CHECK(cudaMemcpyAsync(d_id, ID, 8 * nNodes * nDof, cudaMemcpyHostToDevice, ctx->stream));
@@ -582,12 +599,122 @@ int smfem_assemble(smfem_ctx *ctx, smfem_mesh *mesh, int64_t ne, int ndim, int f
         REQUIRE(want == mesh->nEl_g, SMFEM_ERR_INVALID, "ne^ndim must equal the number of elements of the mesh");
     });
     if (rc) return rc;
+    if (ctx && K_out && mesh->structured && ndim == 3 && nDof == 3 && values_tile_enabled())
+        // hex lattice: sizes in closed form, rowptr kernel + ONE tile kernel that writes column indices and values
+        return guarded([&] {
+            CUDA_CHECK(cudaSetDevice(ctx->device));
+            smfem_matrix *K = new_matrix(ctx, mesh, ndim, nDof);
+            try {
+                pattern_prepare_structured(ctx, mesh, K);
+                values_assemble(ctx, mesh, K, Young, nu, /*fuse_pattern=*/true);
+            } catch (...) {
+                smfem_matrix_free(K);
+                throw;
+            }
+            *K_out = K;
+        });
     rc = smfem_pattern_build(ctx, mesh, ndim, nDof, K_out);
     if (rc) return rc;
     rc = smfem_assemble_values(ctx, mesh, *K_out, Young, nu);
     if (rc) {
         smfem_matrix_free(*K_out);
         *K_out = nullptr;
+    }
+    return rc;
+}
+
+// assemble_system(ne, NodeList, IEN, ndim, FunctionClass, nDof, ID, Young, nu) with HOST arrays in ONE call (src/fem.jl:135).
+// For a hex-lattice candidate (sizes match meshgrid's) the work is overlapped: the copy stream moves NodeList first and the
+// main stream assembles speculatively from the coordinates alone, while IEN / ID (4.7x the bytes of NodeList) are checked
+// against the lattice numbering - chunks from the front through PCIe + a check kernel, chunks from the back by host
+// threads where they lie (lattice_check.cu).  The call returns when the check has passed (all host arrays have been read by
+// then); the assembly may still be in flight on the context's stream, like after any other call.  If the check fails, the
+// speculative result is discarded and the general path runs.
+int smfem_assemble_system(smfem_ctx *ctx, const double *NodeList, const int64_t *IEN, const int64_t *ID, int64_t nNodes, int64_t nEl,
+                          int nLocal, int64_t ne, int ndim, int func_class, int nDof, double Young, double nu, smfem_mesh **mesh_out,
+                          smfem_matrix **K_out) {
+    bool speculated = false, lattice_ok = false;
+    int rc = guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(mesh_out);
+        NOTNULL(K_out);
+        NOTNULL(NodeList);
+        NOTNULL(IEN);
+        *mesh_out = nullptr;
+        *K_out = nullptr;
+        const bool candidate = ndim == 3 && nDof == 3 && nLocal == 8 && func_class == SMFEM_Q1 && ID != nullptr && ne >= 1 &&
+                               ne < 2000 && nEl == ne * ne * ne && nNodes == (ne + 1) * (ne + 1) * (ne + 1) && values_tile_enabled();
+        if (!candidate) return;
+        speculated = true;
+        CUDA_CHECK(cudaSetDevice(ctx->device));
+        smfem_mesh *m = new smfem_mesh();
+        smfem_matrix *K = nullptr;
+        int64_t *d_stage = nullptr;
+        int *d_flag = nullptr;
+        double *d_glob = nullptr;
+        try {
+            m->ctx = ctx;
+            set_lattice(ctx, m, ne);
+            d_stage = dev_alloc<int64_t>(2 * LATTICE_CHUNK);
+            d_flag = dev_alloc<int>(4);
+            d_glob = dev_alloc<double>(3 * nNodes);
+            m->coords = dev_alloc<double>(3 * m->nNodes_l);
+            cudaStream_t cs = ctx->copy_stream;
+            // the copy stream starts after everything already queued on the main stream (buffers come from a cache)
+            CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_fork, 0));
+            CUDA_CHECK(cudaMemcpyAsync(d_glob, NodeList, 8 * 3 * nNodes, cudaMemcpyHostToDevice, cs));
+            ctx->h2d_bytes += 8 * 3 * nNodes;
+            CUDA_CHECK(cudaEventRecord(ctx->ev_nodes, cs));
+            CUDA_CHECK(cudaMemsetAsync(d_flag, 0, 16, cs));
+            // main stream: coordinates -> slab layout -> rowptr + fused tile kernel (queued before the check starts)
+            CUDA_CHECK(cudaMemsetAsync(m->coords, 0, 8 * 3 * m->nNodes_l, ctx->stream));
+            CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_nodes, 0));
+            LAUNCH(ctx, k_copy_slab_coords, (unsigned)((m->nNodes_l + 255) / 256), 256, 0, m->lat, (const double *)d_glob, m->coords);
+            K = new_matrix(ctx, m, 3, 3);
+            pattern_prepare_structured(ctx, m, K);
+            values_assemble(ctx, m, K, Young, nu, /*fuse_pattern=*/true);
+            // IEN / ID against the lattice numbering: PCIe + check kernel from the front, host threads from the back
+            const bool host_ok = lattice_check_hybrid(ctx, IEN, ID, nEl, nNodes, (int)ne, d_stage, d_flag);
+            ctx->h_flags[0] = 1;
+            CUDA_CHECK(cudaMemcpyAsync(ctx->h_flags, d_flag, 4, cudaMemcpyDeviceToHost, cs));
+            CUDA_CHECK(cudaEventRecord(ctx->ev_check, cs));
+            CUDA_CHECK(cudaEventSynchronize(ctx->ev_check));
+            lattice_ok = host_ok && ctx->h_flags[0] == 0;
+            // the main stream may still read d_glob: order its reuse behind the work queued so far
+            CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+            CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_fork, 0));
+            if (!lattice_ok) CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        } catch (...) {
+            cudaStreamSynchronize(ctx->copy_stream);
+            cudaStreamSynchronize(ctx->stream);
+            dev_free(d_stage);
+            dev_free(d_flag);
+            dev_free(d_glob);
+            if (K) smfem_matrix_free(K);
+            smfem_mesh_free(m);
+            throw;
+        }
+        dev_free(d_stage);
+        dev_free(d_flag);
+        dev_free(d_glob);
+        if (lattice_ok) {
+            *mesh_out = m;
+            *K_out = K;
+        } else {
+            smfem_matrix_free(K);
+            smfem_mesh_free(m);
+        }
+    });
+    if (rc) return rc;
+    if (speculated && lattice_ok) return SMFEM_OK;
+    // not a lattice (or not the fast element type): the two-step path
+    rc = smfem_mesh_from_host(ctx, NodeList, IEN, ID, nNodes, nEl, nLocal, ndim, nDof, ne, mesh_out);
+    if (rc) return rc;
+    rc = smfem_assemble(ctx, *mesh_out, ne, ndim, func_class, nDof, Young, nu, K_out);
+    if (rc) {
+        smfem_mesh_free(*mesh_out);
+        *mesh_out = nullptr;
     }
     return rc;
 }
@@ -621,6 +748,15 @@ int smfem_matrix_diag(smfem_ctx *ctx, smfem_matrix *K, double *diag_local) {
         REQUIRE(K->diag != nullptr, SMFEM_ERR_INVALID, "matrix has no values yet");
         CUDA_CHECK(cudaMemcpyAsync(diag_local, K->diag, 8 * K->nrows_l, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->d2h_bytes += 8 * K->nrows_l;
+    });
+}
+
+int smfem_transfer_bytes(smfem_ctx *ctx, int64_t *h2d, int64_t *d2h) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        if (h2d) *h2d = ctx->h2d_bytes;
+        if (d2h) *d2h = ctx->d2h_bytes;
     });
 }
 

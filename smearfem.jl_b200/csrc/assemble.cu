@@ -187,7 +187,8 @@ static void matrix_alloc_pattern(smfem_matrix *K) {
     K->rowptr = dev_alloc<int64_t>(K->nrows_l + 1 + 8);  // +8: slack for 16 B-aligned bulk copies (TMA SpMV)
 }
 
-void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
+// sizes of the structured pattern in closed form + buffers; no kernel, no host synchronisation
+void pattern_prepare_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
     const Lattice &L = mesh->lat;
     int nDof = K->nDof;
     K->structured = true;
@@ -200,15 +201,20 @@ void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K)
     K->ncols_l = K->nrows_l + 2 * K->ghost_cols;
     K->row0 = (int64_t)L.k0 * L.plane() * nDof;
     REQUIRE(K->ncols_l < (int64_t)INT32_MAX, SMFEM_ERR_UNSUPPORTED, "local dof count exceeds int32 column indices");
-    const bool first = (K->rowptr == nullptr);
-    if (first) matrix_alloc_pattern(K);
+    if (K->rowptr != nullptr) return;
+    // (row node, column node) pairs of the owned planes: 1-D prefix pre1(i) = #pairs of rows < i (see k_struct_rowptr)
+    auto pre1 = [&](int i) -> int64_t { return i == 0 ? 0 : (i == L.n1 ? 3 * (int64_t)L.n1 - 2 : 3 * (int64_t)i - 1); };
+    K->nnz_l = (int64_t)nDof * nDof * (pre1(L.k1) - pre1(L.k0)) * S1 * S1;
+    matrix_alloc_pattern(K);
+    K->colind = dev_alloc<int32_t>(K->nnz_l + 16);
+    CUDA_CHECK(cudaMemsetAsync(K->colind + K->nnz_l, 0, 16 * sizeof(int32_t), ctx->stream));
+}
+
+void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
+    pattern_prepare_structured(ctx, mesh, K);
+    const Lattice &L = mesh->lat;
+    int nDof = K->nDof;
     LAUNCH(ctx, k_struct_rowptr, (unsigned)((K->nrows_l + 1 + 255) / 256), 256, 0, L, nDof, K->nrows_l, K->rowptr);
-    if (first) {
-        CUDA_CHECK(cudaMemcpyAsync(&K->nnz_l, K->rowptr + K->nrows_l, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        K->colind = dev_alloc<int32_t>(K->nnz_l + 16);
-        CUDA_CHECK(cudaMemsetAsync(K->colind + K->nnz_l, 0, 16 * sizeof(int32_t), ctx->stream));
-    }
     int64_t nOwned = (int64_t)L.nown() * L.plane();
     if (nDof == 3)
         LAUNCH(ctx, (k_struct_colind<3>), (unsigned)((nOwned * 32 + 255) / 256), 256, 0, L, nOwned, (const int64_t *)K->rowptr, K->colind);

@@ -35,6 +35,13 @@ struct smfem_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // user stopwatch (smfem_timer_*)
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;  // internal timing (pcg_solve, bench_spmv)
+    // smfem_assemble_system: host->device copies and the lattice check run on copy_stream beside the assembly
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_nodes = nullptr, ev_check = nullptr;
+    int *h_flags = nullptr;  // pinned, 4 ints
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};  // staging buffers of the chunked lattice check (lattice_check.cu)
+    void *host_pool = nullptr;                     // HostPool*, created on first use
+    int64_t h2d_bytes = 0, d2h_bytes = 0;          // bulk transfers of the reference-facing calls (smfem_transfer_bytes)
     int sms = 148;
     int64_t launches = 0;
     void *flush_buf = nullptr;
@@ -180,7 +187,13 @@ void mesh_generate_structured(smfem_ctx *ctx, smfem_mesh *m, double x0, double x
                               double z1);
 void mesh_inflate(smfem_ctx *ctx, smfem_mesh *m, double x0, double x1, double y0, double y1);
 
+constexpr int64_t LATTICE_CHUNK = 128 * 1024;  // Int64 entries per chunk of the hybrid lattice check (1 MiB)
+bool lattice_check_hybrid(smfem_ctx *ctx, const int64_t *IEN, const int64_t *ID, int64_t nEl, int64_t nNodes, int ne, int64_t *d_stage,
+                          int *d_flag);
+void host_pool_destroy(smfem_ctx *ctx);
+void pattern_prepare_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
 void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
+bool values_tile_enabled();
 void pattern_build_general(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
 void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu, bool fuse_pattern = false);
 void surface_mass(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, const int32_t *faces_dev, int64_t nFaces,

@@ -138,12 +138,19 @@ end
 free!(K::B200SparseMatrix) = (K.h != C_NULL && ccall((:smfem_matrix_free, LIB), Cint, (Ptr{Cvoid},), K.h); K.h = C_NULL)
 
 function assemble_system(ne, NodeList, IEN, ndim, FunctionClass="Q1", nDof=1, ID=nothing, Young=1, ν=0.3)
-    mesh = mesh_from_host(Matrix{Float64}(NodeList), Matrix{Int64}(IEN), nDof > 1 ? Matrix{Int64}(ID) : nothing, ndim, nDof, ne)
-    h = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:smfem_assemble, LIB), Cint,
-                (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint, Cint, Cint, Cdouble, Cdouble, Ptr{Ptr{Cvoid}}),
-                context().h, mesh.h, ne, ndim, fclass(FunctionClass), nDof, Young, ν, h))
-    K = B200SparseMatrix(h[], mesh); finalizer(free!, K); return K
+    NL = Matrix{Float64}(NodeList); IENm = Matrix{Int64}(IEN)
+    IDm = nDof > 1 ? Matrix{Int64}(ID) : nothing
+    idp = IDm === nothing ? Ptr{Int64}(C_NULL) : pointer(IDm)
+    mh = Ref{Ptr{Cvoid}}(C_NULL); kh = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve NL IENm IDm begin      # one call: transfers, lattice check and assembly overlap inside the library
+        check(ccall((:smfem_assemble_system, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Cint, Int64, Cint, Cint, Cint, Cdouble, Cdouble,
+                     Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
+                    context().h, NL, IENm, idp, size(NL, 2), size(IENm, 1), size(IENm, 2), ne, ndim, fclass(FunctionClass), nDof,
+                    Young, ν, mh, kh))
+    end
+    mesh = Mesh(mh[]); finalizer(free!, mesh)
+    K = B200SparseMatrix(kh[], mesh); finalizer(free!, K); return K
 end
 
 function info(K::B200SparseMatrix)

@@ -123,6 +123,34 @@ def test_general_path_shuffled_elements_standard_ids():
     assert rel(q, o.example_problem(ne)["q"]) <= TOL
 
 
+def test_assemble_system_one_call_matches_two_step():
+    """smfem_assemble_system (transfers of IEN / ID overlapped with a speculative lattice assembly) gives the bits of
+    smfem_mesh_from_host + smfem_assemble; a mesh with meshgrid's sizes but another numbering falls back correctly."""
+    ne = 11
+    ctx = sf.context()
+    NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.jitter_nodes(NL, ne, seed=5)
+    for trial in range(3):  # repeated: the copy stream reuses cached buffers of the previous call
+        K1 = sf.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4)
+        assert K1.mesh.info()["structured"]
+        mesh = sf.Mesh.from_host(ctx, NL, IEN, ID, 3, 3, ne)
+        K2 = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
+        for a, b in zip(K1.to_csc(), K2.to_csc()):
+            assert np.array_equal(a, b)
+        assert np.array_equal(K1.diag(), K2.diag())
+    assert_csc_parity(K1, o.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4))
+    # same sizes, two elements swapped: the lattice check fails after the speculative assembly was launched
+    IEN2 = IEN.copy()
+    IEN2[[3, 77]] = IEN2[[77, 3]]
+    K3 = sf.assemble_system(ne, NL, IEN2, 3, "Q1", 3, ID, 40, 0.4)
+    assert not K3.mesh.info()["structured"]
+    assert_csc_parity(K3, o.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4), tol=1e-13)
+    # and a lattice call right after the discarded one
+    K4 = sf.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4)
+    for a, b in zip(K4.to_csc(), K1.to_csc()):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("ne", [2, 4, 9])
 def test_plane_stress_quad4(ne, golden_dir):  # config C1 geometry, src/fem.jl:210-217
     NL, IEN, ID, *_ = sf.meshgrid(0, 1, 0, 1, 0, 1, ne, 2)
