@@ -162,11 +162,15 @@ int smfem_init(int device, int rank, int nranks, smfem_ctx **out) {
         CUDA_CHECK(cudaEventCreate(&c->ev1));
         CUDA_CHECK(cudaEventCreate(&c->ev2));
         CUDA_CHECK(cudaEventCreate(&c->ev3));
-        CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        {  // kernels of the copy stream (lattice check) should slip in beside the assembly kernel
+            int lo_prio = 0, hi_prio = 0;
+            CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+            CUDA_CHECK(cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, hi_prio));
+        }
         CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_nodes, cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_check, cudaEventDisableTiming));
-        CUDA_CHECK(cudaMallocHost(&c->h_flags, 4 * sizeof(int)));
+        CUDA_CHECK(cudaMallocHost(&c->h_flags, 32 * sizeof(int)));
         CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_stage[0], cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_stage[1], cudaEventDisableTiming));
         cudaDeviceProp prop;
@@ -624,8 +628,8 @@ int smfem_assemble(smfem_ctx *ctx, smfem_mesh *mesh, int64_t ne, int ndim, int f
 }
 
 // assemble_system(ne, NodeList, IEN, ndim, FunctionClass, nDof, ID, Young, nu) with HOST arrays in ONE call (src/fem.jl:135).
-// For a hex-lattice candidate (sizes match meshgrid's) the work is overlapped: the copy stream moves NodeList first and the
-// main stream assembles speculatively from the coordinates alone, while IEN / ID (4.7x the bytes of NodeList) are checked
+// For a hex-lattice candidate (sizes match meshgrid's) the work is overlapped: the copy stream moves NodeList in pieces
+// and the tile kernel on the main stream follows the arriving coordinate planes (speculative assembly), while IEN / ID (4.7x the bytes of NodeList) are checked
 // against the lattice numbering - chunks from the front through PCIe + a check kernel, chunks from the back by host
 // threads where they lie (lattice_check.cu).  The call returns when the check has passed (all host arrays have been read by
 // then); the assembly may still be in flight on the context's stream, like after any other call.  If the check fails, the
@@ -650,30 +654,40 @@ int smfem_assemble_system(smfem_ctx *ctx, const double *NodeList, const int64_t 
         smfem_mesh *m = new smfem_mesh();
         smfem_matrix *K = nullptr;
         int64_t *d_stage = nullptr;
-        int *d_flag = nullptr;
-        double *d_glob = nullptr;
+        int *d_flag = nullptr;  // [0] mismatch seen by the device-side check, [1] number of coordinate planes that have arrived
         try {
             m->ctx = ctx;
             set_lattice(ctx, m, ne);
+            const Lattice &L = m->lat;
             d_stage = dev_alloc<int64_t>(2 * LATTICE_CHUNK);
             d_flag = dev_alloc<int>(4);
-            d_glob = dev_alloc<double>(3 * nNodes);
             m->coords = dev_alloc<double>(3 * m->nNodes_l);
             cudaStream_t cs = ctx->copy_stream;
             // the copy stream starts after everything already queued on the main stream (buffers come from a cache)
             CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
             CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_fork, 0));
-            CUDA_CHECK(cudaMemcpyAsync(d_glob, NodeList, 8 * 3 * nNodes, cudaMemcpyHostToDevice, cs));
-            ctx->h2d_bytes += 8 * 3 * nNodes;
-            CUDA_CHECK(cudaEventRecord(ctx->ev_nodes, cs));
+            CUDA_CHECK(cudaMemsetAsync(m->coords, 0, 8 * 3 * m->nNodes_l, cs));  // ghost planes outside the domain
             CUDA_CHECK(cudaMemsetAsync(d_flag, 0, 16, cs));
-            // main stream: coordinates -> slab layout -> rowptr + fused tile kernel (queued before the check starts)
-            CUDA_CHECK(cudaMemsetAsync(m->coords, 0, 8 * 3 * m->nNodes_l, ctx->stream));
+            CUDA_CHECK(cudaEventRecord(ctx->ev_nodes, cs));
+            // NodeList: the planes this rank holds (k0-1 .. k1), in a few pieces with a watermark behind each
+            // (queued BEFORE the kernel that waits for them is launched: a failing copy must not leave a spinning kernel behind)
+            {
+                const int lo = L.k0 - 1 < 0 ? 0 : L.k0 - 1, hi = L.k1 + 1 > L.n1 ? L.n1 : L.k1 + 1;
+                const int parts = std::min(8, hi - lo);
+                for (int sidx = 0; sidx < parts; ++sidx) {
+                    const int p0 = lo + (int)((int64_t)(hi - lo) * sidx / parts), p1 = lo + (int)((int64_t)(hi - lo) * (sidx + 1) / parts);
+                    CUDA_CHECK(cudaMemcpyAsync(m->coords + 3 * (int64_t)(p0 - (L.k0 - 1)) * L.plane(), NodeList + 3 * (int64_t)p0 * L.plane(),
+                                               8 * 3 * (int64_t)(p1 - p0) * L.plane(), cudaMemcpyHostToDevice, cs));
+                    ctx->h_flags[8 + sidx] = p1;
+                    CUDA_CHECK(cudaMemcpyAsync(d_flag + 1, ctx->h_flags + 8 + sidx, 4, cudaMemcpyHostToDevice, cs));
+                }
+                ctx->h2d_bytes += 8 * 3 * (int64_t)(hi - lo) * L.plane();
+            }
+            // main stream: rowptr + fused tile kernel, which follows the arrival of the coordinate planes (d_flag[1])
             CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_nodes, 0));
-            LAUNCH(ctx, k_copy_slab_coords, (unsigned)((m->nNodes_l + 255) / 256), 256, 0, m->lat, (const double *)d_glob, m->coords);
             K = new_matrix(ctx, m, 3, 3);
             pattern_prepare_structured(ctx, m, K);
-            values_assemble(ctx, m, K, Young, nu, /*fuse_pattern=*/true);
+            values_assemble(ctx, m, K, Young, nu, /*fuse_pattern=*/true, d_flag + 1);
             // IEN / ID against the lattice numbering: PCIe + check kernel from the front, host threads from the back
             const bool host_ok = lattice_check_hybrid(ctx, IEN, ID, nEl, nNodes, (int)ne, d_stage, d_flag);
             ctx->h_flags[0] = 1;
@@ -681,7 +695,7 @@ int smfem_assemble_system(smfem_ctx *ctx, const double *NodeList, const int64_t 
             CUDA_CHECK(cudaEventRecord(ctx->ev_check, cs));
             CUDA_CHECK(cudaEventSynchronize(ctx->ev_check));
             lattice_ok = host_ok && ctx->h_flags[0] == 0;
-            // the main stream may still read d_glob: order its reuse behind the work queued so far
+            // the tile kernel may still read d_flag[1]: order the reuse of the block behind the work queued so far
             CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
             CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_fork, 0));
             if (!lattice_ok) CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -690,14 +704,12 @@ int smfem_assemble_system(smfem_ctx *ctx, const double *NodeList, const int64_t 
             cudaStreamSynchronize(ctx->stream);
             dev_free(d_stage);
             dev_free(d_flag);
-            dev_free(d_glob);
             if (K) smfem_matrix_free(K);
             smfem_mesh_free(m);
             throw;
         }
         dev_free(d_stage);
         dev_free(d_flag);
-        dev_free(d_glob);
         if (lattice_ok) {
             *mesh_out = m;
             *K_out = K;

@@ -590,10 +590,10 @@ k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64
     }
 }
 
-void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind);  // assemble_tile.cu
+void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind, const int *ready);  // assemble_tile.cu
 bool values_tile_enabled();
 
-void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu, bool fuse_pattern) {
+void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu, bool fuse_pattern, const int *ready) {
     Material mat;
     const int ndim = K->ndim, nDof = K->nDof;
     if (nDof == 2) {  // plane stress, src/fem.jl:217
@@ -613,7 +613,7 @@ void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Y
     if (mesh->structured && ndim == 3 && nDof == 3 && values_tile_enabled()) {
         if (fuse_pattern)  // rowptr in closed form here, colind written by the tile kernel's output phase
             LAUNCH(ctx, k_struct_rowptr, (unsigned)((K->nrows_l + 1 + 255) / 256), 256, 0, mesh->lat, K->nDof, K->nrows_l, K->rowptr);
-        values_assemble_tile(ctx, mesh, K, mat, fuse_pattern);  // writes every entry and the diagonal: no memset, no extract_diag
+        values_assemble_tile(ctx, mesh, K, mat, fuse_pattern, ready);  // writes every entry and the diagonal: no memset, no extract_diag
         K->values_ready = true;
         return;
     } else {

@@ -69,6 +69,7 @@ struct TileArgs {
     const int64_t *rowptr;
     double *val;
     int32_t *colind;  // non-null: the output phase also writes the pattern's column indices (fused assembly)
+    const int *ready;  // non-null: coordinate planes [0, *ready) have arrived (written by host->device copies while the kernel runs)
     double *diag;
     Material mat;
     int tiles_x, tiles_y, nchunks;
@@ -84,7 +85,7 @@ struct TileArgs {
 template <class T>
 __device__ __forceinline__ void stage_plane(const TileArgs &A, double *s_xyz, int k, int X0, int Y0) {
     const Lattice &L = A.L;
-    if (k < 0 || k >= L.n1) return;
+    if (k < 0 || k >= L.n1 || k > L.k1) return;  // the slab holds planes k0-1 .. k1
     double *dst = s_xyz + (k & 3) * T::PLANE;
     for (int t = threadIdx.x; t < T::PLANE; t += T::NTH) {
         const int c = t % 3, n = t / 3;
@@ -289,6 +290,18 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
     auto pre1 = [](int i) -> int64_t { return i == 0 ? 0 : 3 * (int64_t)i - 1; };
     auto cnt1 = [&](int i) -> int { return 1 + (i > 0) + (i < L.n1 - 1); };
     const int64_t pairs_base = pre1(L.k0) * S1 * S1;
+    // streamed coordinates (smfem_assemble_system): wait until plane p AND p + 1 have landed - the 128-byte line that
+    // straddles the end of plane p must not enter L1 with bytes of p + 1 that the copy engine has not written yet
+    int ready_upto = A.ready ? 0 : 0x7fffffff;
+    auto wait_plane = [&](int p) {
+        const int need = min(p + 2, min(L.k1 + 1, L.n1));  // the slab ends with plane min(k1, n1-1)
+        unsigned spins = 0;
+        while (ready_upto < need) {
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(ready_upto) : "l"(A.ready) : "memory");
+            if (++spins > (1u << 25)) __trap();  // tens of seconds: the copies were queued before this kernel, so never in practice
+        }
+    };
+    wait_plane(zs + 1);
     stage_plane<T>(A, s_xyz, zs - 1, X0, Y0);
     stage_plane<T>(A, s_xyz, zs, X0, Y0);
     stage_plane<T>(A, s_xyz, zs + 1, X0, Y0);
@@ -296,6 +309,7 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_const
     __syncthreads();
 
     for (int k = zs; k < ze; ++k) {
+        if (k + 2 < L.n1 && k + 2 <= L.k1) wait_plane(k + 2);
         stage_plane<T>(A, s_xyz, k + 2, X0, Y0);  // lands during this plane's phase 2; ring slot (k+2)&3 is free
         if (!(A.skip & 1)) {
             if (k == zs && k - 1 >= 0) phase1<T>(A, s_dN, s_w, s_xyz, S, k - 1, X0, Y0);
@@ -584,7 +598,7 @@ static void launch_tile(smfem_ctx *ctx, TileArgs &A, int nown) {
     LAUNCH(ctx, (k_values_tile<T, MINB, OUT>), grid, T::NTH, T::SMEM_BYTES, A);
 }
 
-void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind) {
+void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind, const int *ready) {
     if (!K->diag) K->diag = dev_alloc<double>(K->nrows_l);
     TileArgs A;
     A.L = mesh->lat;
@@ -592,6 +606,7 @@ void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Mat
     A.rowptr = K->rowptr;
     A.val = K->val;
     A.colind = write_colind ? K->colind : nullptr;
+    A.ready = ready;
     A.diag = K->diag;
     A.mat = mat;
     {

@@ -23,8 +23,9 @@ namespace {
 // device side: entries [off, off+len) of IEN (which = 0, column-major nEl x 8) or ID (which = 1, nNodes x 3)
 __global__ void k_check_lattice_range(const int64_t *__restrict__ chunk, int which, int64_t off, int64_t len, int64_t nEl, int ne,
                                       int64_t nNodes, int *__restrict__ mismatch) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= len) return;
+    // small blocks, few registers: these CTAs have to fit beside the resident CTAs of the tile kernel (2 x 128 threads x 246
+    // registers per SM) to run while the assembly is in flight
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t t = off + i;
     int64_t want;
     if (which == 0) {
@@ -38,6 +39,7 @@ __global__ void k_check_lattice_range(const int64_t *__restrict__ chunk, int whi
         want = 3 * (t % nNodes) + t / nNodes + 1;
     }
     if (chunk[i] != want) *mismatch = 1;
+    }
 }
 
 // host side, same predicate, one division per lattice row
@@ -201,7 +203,7 @@ bool lattice_check_hybrid(smfem_ctx *ctx, const int64_t *IEN, const int64_t *ID,
             if (used[slot]) CUDA_CHECK(cudaEventSynchronize(ctx->ev_stage[slot]));
             int64_t *dst = d_stage + (int64_t)slot * LATTICE_CHUNK;
             CUDA_CHECK(cudaMemcpyAsync(dst, (c.which ? ID : IEN) + c.off, 8 * c.len, cudaMemcpyHostToDevice, cs));
-            k_check_lattice_range<<<(unsigned)((c.len + 255) / 256), 256, 0, cs>>>(dst, c.which, c.off, c.len, nEl, ne, nNodes, d_flag);
+            k_check_lattice_range<<<(unsigned)((c.len + 255) / 256), 64, 0, cs>>>(dst, c.which, c.off, c.len, nEl, ne, nNodes, d_flag);
             ctx->launches++;
             CUDA_CHECK(cudaGetLastError());
             CUDA_CHECK(cudaEventRecord(ctx->ev_stage[slot], cs));

@@ -38,7 +38,7 @@ struct smfem_ctx {
     // smfem_assemble_system: host->device copies and the lattice check run on copy_stream beside the assembly
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_nodes = nullptr, ev_check = nullptr;
-    int *h_flags = nullptr;  // pinned, 4 ints
+    int *h_flags = nullptr;  // pinned, 32 ints: [0..3] check verdicts, [8..15] watermarks of the streamed NodeList
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};  // staging buffers of the chunked lattice check (lattice_check.cu)
     void *host_pool = nullptr;                     // HostPool*, created on first use
     int64_t h2d_bytes = 0, d2h_bytes = 0;          // bulk transfers of the reference-facing calls (smfem_transfer_bytes)
@@ -195,7 +195,9 @@ void pattern_prepare_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *
 void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
 bool values_tile_enabled();
 void pattern_build_general(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
-void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu, bool fuse_pattern = false);
+// ready (device int, optional): the coordinate planes [0, *ready) have been written; the tile kernel waits plane by plane
+void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu, bool fuse_pattern = false,
+                     const int *ready = nullptr);
 void surface_mass(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, const int32_t *faces_dev, int64_t nFaces,
                   double beta, bool keep_b);
 void extract_diag(smfem_ctx *ctx, smfem_matrix *K);
