@@ -51,7 +51,11 @@ def asm_bytes(ne, n_planes_owned=None):
     nN, nEl = n1**3 * frac, ne**3 * frac
     values = 8 * nnz + 24 * nN + 64 * nEl + 24 * nN
     total = values + 4 * nnz + 8 * (3 * nN + 1)
-    return values, total
+    # what the tile kernel itself has to move (the lattice path never touches IEN / ID; rowptr comes from its own small kernel):
+    # values + diagonal written, coordinates read; the fused launch also writes the column indices
+    k_values = 8 * nnz + 8 * 3 * nN + 24 * nN
+    k_fused = k_values + 4 * nnz
+    return values, total, k_values, k_fused
 
 
 class ClockSampler(threading.Thread):
@@ -185,6 +189,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    from smearfem_b200 import _lib
+
     ne = args.ne or ne_for(world)
     n1 = ne + 1
     k0, k1 = sd.slab_range(n1, rank, world)
@@ -218,6 +224,9 @@ def main():
     ms_steps = ctx.timer_stop()
     barrier()
     launches = ctx.launches - l0
+    _avg, _used = C.c_float(), C.c_int()
+    _lib.call("smfem_assembly_kernel_ms", ctx.handle, min(args.steps, 64), C.byref(_avg), C.byref(_used))
+    fused_kernel_ms = float(_avg.value)   # average over the timed steps' own launches of k_values_tile (CUDA events inside the library)
     # the dominant kernel alone, same inputs, same events
     ctx.timer_start()
     for _ in range(args.steps):
@@ -225,10 +234,12 @@ def main():
     ms_values = ctx.timer_stop()
     barrier()
     t_step = max_over_ranks(ms_steps / args.steps * 1e-3)
-    t_val = max_over_ranks(ms_values / args.steps * 1e-3)
     value = ne**3 / t_step
-    b_values, b_total = asm_bytes(ne, k1 - k0)
-    roof_val = b_values / t_val / 1e9
+    b_values, b_total, bk_values, bk_fused = asm_bytes(ne, k1 - k0)
+    # the step's dominant kernel: the fused launches of k_values_tile inside the timed steps, one CUDA event pair per launch
+    t_val_kernel = max_over_ranks(ms_values / args.steps * 1e-3)
+    t_fused_kernel = max_over_ranks(fused_kernel_ms * 1e-3)
+    roof_val = bk_fused / t_fused_kernel / 1e9
 
     # ------------------------------------------------------------------ SpMV + PCG (second half of the metric)
     spmv = pcg = None
@@ -265,7 +276,6 @@ def main():
     # ------------------------------------------------------------------ end to end: HOST mesh arrays -> K on device -> diag to host
     K.free()
     K = None
-    from smearfem_b200 import _lib
 
     nN, nEl = n1**3, ne**3
     NL_h = torch.empty((nN, 3), dtype=torch.float64, pin_memory=True)
@@ -354,10 +364,17 @@ def main():
                        "ne": ne, "elements": ne**3, "ndof": 3 * n1**3, "nnz": 9 * (3 * n1 - 2) ** 3, "partition": f"z-slabs x{world}",
                        "step": "device pattern build + element values, every entry of rowptr/colind/val rewritten each step",
                        "l2": "no flush needed: each step writes K (>= 2.9 GB per GPU) >> 126 MB L2"},
-            "roofline": {"bound": "hbm", "kernel": "k_values_tile (element values, smfem_assemble_values)", "achieved": roof_val, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": roof_val / hbm_peak, "traffic": traffic.get("k_values_tile"), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": b_values, "ms_per_launch": t_val * 1e3,
-                         "elements_per_s_values_only": ne**3 / t_val},
+            "roofline": {"bound": "hbm", "kernel": "k_values_tile, fused launch of the step (column indices + values + diagonal)",
+                         "achieved": roof_val, "peak": hbm_peak, "unit": "GB/s", "frac": roof_val / hbm_peak,
+                         "traffic": traffic.get("k_values_tile_fused_colind"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bk_fused, "ms_per_launch": t_fused_kernel * 1e3,
+                         "launches_timed": int(_used.value),
+                         "bytes": "12 B/nnz (value + column index) + 24 B/node coordinates read + 24 B/node diagonal written; "
+                                  "IEN/ID/rowptr of SURVEY 8(d)'s 3.07 KB/element are not touched by this kernel and not counted",
+                         "survey_bytes_per_step": b_total, "survey_GB/s_per_step": b_total / t_step / 1e9,
+                         "values_only": {"ms_per_launch": t_val_kernel * 1e3, "algorithmic_bytes_per_launch": bk_values,
+                                         "achieved": bk_values / t_val_kernel / 1e9, "frac": bk_values / t_val_kernel / 1e9 / hbm_peak,
+                                         "traffic": traffic.get("k_values_tile"), "elements_per_s": ne**3 / t_val_kernel}},
             "spmv": spmv, "pcg": pcg, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(line)

@@ -136,6 +136,10 @@ int smfem_assemble(smfem_ctx *ctx, smfem_mesh *mesh, int64_t ne, int ndim, int f
 int smfem_assemble_system(smfem_ctx *ctx, const double *NodeList, const int64_t *IEN, const int64_t *ID, int64_t nNodes,
                           int64_t nEl, int nLocal, int64_t ne, int ndim, int func_class, int nDof, double Young, double nu,
                           smfem_mesh **mesh_out, smfem_matrix **K_out);
+/* Average duration (CUDA events on the context's stream) of the last `last_n` launches (<= 64; 0 = all recorded) of the
+ * structured assembly kernel k_values_tile - the dominant kernel of smfem_assemble / smfem_reassemble; bench.py's
+ * roofline denominator.  Synchronises with the last of those launches. */
+int smfem_assembly_kernel_ms(smfem_ctx *ctx, int last_n, float *avg_ms, int *n_used);
 /* cumulative bytes moved host->device / device->host by the bulk transfers of the calls above (bench.py's e2e accounting) */
 int smfem_transfer_bytes(smfem_ctx *ctx, int64_t *h2d, int64_t *d2h);
 /* The two halves of smfem_assemble, for timing them separately. */

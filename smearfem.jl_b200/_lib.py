@@ -53,6 +53,7 @@ SIGNATURES = {
     "smfem_assemble": [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(_vp)],
     "smfem_assemble_system": [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int64, C.c_int64, C.c_int,
                               C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(_vp), C.POINTER(_vp)],
+    "smfem_assembly_kernel_ms": [_vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)],
     "smfem_transfer_bytes": [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     "smfem_pattern_build": [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)],
     "smfem_assemble_values": [_vp, _vp, _vp, C.c_double, C.c_double],

@@ -1,5 +1,6 @@
 // extern "C" boundary of libsmearfem_b200.so (see include/smearfem_b200.h).  Every entry point
 // catches C++ exceptions and converts them into status codes + a thread-local message.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -194,6 +195,8 @@ int smfem_destroy(smfem_ctx *ctx) {
         cudaEventDestroy(ctx->ev3);
         cudaStreamSynchronize(ctx->copy_stream);
         host_pool_destroy(ctx);
+        for (cudaEvent_t e : ctx->asm_ev)
+            if (e) cudaEventDestroy(e);
         cudaEventDestroy(ctx->ev_stage[0]);
         cudaEventDestroy(ctx->ev_stage[1]);
         cudaEventDestroy(ctx->ev_fork);
@@ -761,6 +764,25 @@ int smfem_matrix_diag(smfem_ctx *ctx, smfem_matrix *K, double *diag_local) {
         CUDA_CHECK(cudaMemcpyAsync(diag_local, K->diag, 8 * K->nrows_l, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         ctx->d2h_bytes += 8 * K->nrows_l;
+    });
+}
+
+int smfem_assembly_kernel_ms(smfem_ctx *ctx, int last_n, float *avg_ms, int *n_used) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(avg_ms);
+        int n = (int)std::min<int64_t>(ctx->asm_count, smfem_ctx::ASM_RING);
+        if (last_n > 0 && last_n < n) n = last_n;
+        double sum = 0;
+        for (int i = 0; i < n; ++i) {
+            const int slot = (int)((ctx->asm_count - 1 - i) % smfem_ctx::ASM_RING);
+            CUDA_CHECK(cudaEventSynchronize(ctx->asm_ev[2 * slot + 1]));
+            float ms = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->asm_ev[2 * slot], ctx->asm_ev[2 * slot + 1]));
+            sum += ms;
+        }
+        *avg_ms = n ? (float)(sum / n) : 0.f;
+        if (n_used) *n_used = n;
     });
 }
 

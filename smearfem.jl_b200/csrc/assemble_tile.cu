@@ -595,7 +595,15 @@ static void launch_tile(smfem_ctx *ctx, TileArgs &A, int nown) {
     A.zb[0] = 0;
     for (int c = 0; c < A.nchunks; ++c) A.zb[c + 1] = A.zb[c] + len[c];
     const unsigned grid = (unsigned)(ntiles * A.nchunks);
+    const int slot = (int)(ctx->asm_count % smfem_ctx::ASM_RING);
+    if (!ctx->asm_ev[2 * slot]) {
+        CUDA_CHECK(cudaEventCreate(&ctx->asm_ev[2 * slot]));
+        CUDA_CHECK(cudaEventCreate(&ctx->asm_ev[2 * slot + 1]));
+    }
+    CUDA_CHECK(cudaEventRecord(ctx->asm_ev[2 * slot], ctx->stream));
     LAUNCH(ctx, (k_values_tile<T, MINB, OUT>), grid, T::NTH, T::SMEM_BYTES, A);
+    CUDA_CHECK(cudaEventRecord(ctx->asm_ev[2 * slot + 1], ctx->stream));
+    ctx->asm_count++;
 }
 
 void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind, const int *ready) {

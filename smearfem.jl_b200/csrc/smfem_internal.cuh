@@ -42,6 +42,10 @@ struct smfem_ctx {
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};  // staging buffers of the chunked lattice check (lattice_check.cu)
     void *host_pool = nullptr;                     // HostPool*, created on first use
     int64_t h2d_bytes = 0, d2h_bytes = 0;          // bulk transfers of the reference-facing calls (smfem_transfer_bytes)
+    // event pairs around the last ASM_RING launches of the tile kernel (smfem_assembly_kernel_ms: the roofline's denominator)
+    static constexpr int ASM_RING = 64;
+    cudaEvent_t asm_ev[2 * ASM_RING] = {};
+    int64_t asm_count = 0;
     int sms = 148;
     int64_t launches = 0;
     void *flush_buf = nullptr;
