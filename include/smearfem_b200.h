@@ -130,7 +130,7 @@ int smfem_assemble(smfem_ctx *ctx, smfem_mesh *mesh, int64_t ne, int ndim, int f
  * vector3D.jl:10) the transfers and the work overlap: NodeList is copied first and the assembly starts from the
  * coordinates alone, while IEN and ID (4.7x the bytes) are checked against the lattice numbering - chunks from the front
  * through PCIe and a check kernel on a second stream, chunks from the back by host threads (env SMFEM_HOST_THREADS, default
- * min(4, usable cores - 1); 0 = PCIe only); a failed check discards the speculative result and takes the general path.  Returns once
+ * min(4, usable cores - 1); 0 = PCIe only; with several ranks each one checks the part its slab uses); a failed check discards the speculative result and takes the general path.  Returns once
  * every host array has been read; the matrix may still be in flight on the context's stream (any later call orders behind it).
  * Outputs: the mesh handle (needed by surface_mass / set_dirichlet_zplanes) and the matrix handle. */
 int smfem_assemble_system(smfem_ctx *ctx, const double *NodeList, const int64_t *IEN, const int64_t *ID, int64_t nNodes,

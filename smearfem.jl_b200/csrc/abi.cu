@@ -692,7 +692,7 @@ int smfem_assemble_system(smfem_ctx *ctx, const double *NodeList, const int64_t 
             pattern_prepare_structured(ctx, m, K);
             values_assemble(ctx, m, K, Young, nu, /*fuse_pattern=*/true, d_flag + 1);
             // IEN / ID against the lattice numbering: PCIe + check kernel from the front, host threads from the back
-            const bool host_ok = lattice_check_hybrid(ctx, IEN, ID, nEl, nNodes, (int)ne, d_stage, d_flag);
+            const bool host_ok = lattice_check_hybrid(ctx, L, IEN, ID, nEl, nNodes, (int)ne, d_stage, d_flag);
             ctx->h_flags[0] = 1;
             CUDA_CHECK(cudaMemcpyAsync(ctx->h_flags, d_flag, 4, cudaMemcpyDeviceToHost, cs));
             CUDA_CHECK(cudaEventRecord(ctx->ev_check, cs));

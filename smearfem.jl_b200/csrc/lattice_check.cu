@@ -159,15 +159,25 @@ void host_pool_destroy(smfem_ctx *ctx) {
 // Queues the PCIe side on ctx->copy_stream (the verdict of that side lands in d_flag[0]) and runs the host side to
 // completion.  Returns false as soon as the host side has seen a mismatch; true means "host side clean" - the caller still
 // has to read d_flag after the copy stream has drained.  d_stage: 2 * LATTICE_CHUNK device words.
-bool lattice_check_hybrid(smfem_ctx *ctx, const int64_t *IEN, const int64_t *ID, int64_t nEl, int64_t nNodes, int ne, int64_t *d_stage,
-                          int *d_flag) {
+bool lattice_check_hybrid(smfem_ctx *ctx, const Lattice &L, const int64_t *IEN, const int64_t *ID, int64_t nEl, int64_t nNodes, int ne,
+                          int64_t *d_stage, int *d_flag) {
     struct Chunk {
         int which;
         int64_t off, len;
     };
     std::vector<Chunk> chunks;
-    for (int64_t o = 0; o < nEl * 8; o += LATTICE_CHUNK) chunks.push_back({0, o, std::min<int64_t>(LATTICE_CHUNK, nEl * 8 - o)});
-    for (int64_t o = 0; o < nNodes * 3; o += LATTICE_CHUNK) chunks.push_back({1, o, std::min<int64_t>(LATTICE_CHUNK, nNodes * 3 - o)});
+    // this rank answers for what its slab uses: the element layers k0-1 .. k1-1 and the node planes k0-1 .. k1 (the whole
+    // arrays on one GPU).  A rank whose part is not meshgrid's numbering leaves the lattice path on its own.
+    auto add_range = [&](int which, int64_t b, int64_t e) {
+        for (int64_t o = b; o < e; o += LATTICE_CHUNK) chunks.push_back({which, o, std::min<int64_t>(LATTICE_CHUNK, e - o)});
+    };
+    {
+        const int64_t layer = (int64_t)ne * ne, plane = (int64_t)(ne + 1) * (ne + 1);
+        const int64_t l0 = std::max(L.k0 - 1, 0), l1 = std::min(L.k1, ne);          // element layers [l0, l1)
+        const int64_t p0 = std::max(L.k0 - 1, 0), p1 = std::min(L.k1 + 1, ne + 1);  // node planes [p0, p1)
+        for (int a = 0; a < 8; ++a) add_range(0, a * nEl + l0 * layer, a * nEl + l1 * layer);
+        for (int l = 0; l < 3; ++l) add_range(1, l * nNodes + p0 * plane, l * nNodes + p1 * plane);
+    }
     std::atomic<int64_t> lo{0}, hi{(int64_t)chunks.size()};
     std::atomic<int> bad{0};
 

@@ -192,8 +192,8 @@ void mesh_generate_structured(smfem_ctx *ctx, smfem_mesh *m, double x0, double x
 void mesh_inflate(smfem_ctx *ctx, smfem_mesh *m, double x0, double x1, double y0, double y1);
 
 constexpr int64_t LATTICE_CHUNK = 128 * 1024;  // Int64 entries per chunk of the hybrid lattice check (1 MiB)
-bool lattice_check_hybrid(smfem_ctx *ctx, const int64_t *IEN, const int64_t *ID, int64_t nEl, int64_t nNodes, int ne, int64_t *d_stage,
-                          int *d_flag);
+bool lattice_check_hybrid(smfem_ctx *ctx, const Lattice &L, const int64_t *IEN, const int64_t *ID, int64_t nEl, int64_t nNodes, int ne,
+                          int64_t *d_stage, int *d_flag);
 void host_pool_destroy(smfem_ctx *ctx);
 void pattern_prepare_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
 void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);

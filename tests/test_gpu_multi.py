@@ -37,6 +37,23 @@ def _worker(rank, ws, port, ne, q):
         lo, hi = Ko.colptr[c0] - 1, Ko.colptr[c0 + nc] - 1
         out["pattern"] = bool(np.array_equal(colptr - 1 + lo, Ko.colptr[c0:c0 + nc + 1] - 1) and np.array_equal(rowval, Ko.rowval[lo:hi]))
         out["relK"] = float(np.linalg.norm(nzval - Ko.nzval[lo:hi]) / np.linalg.norm(Ko.nzval[lo:hi]))
+        # the reference-facing call with the full HOST arrays on every rank (NodeList streamed, the rank's part of IEN / ID
+        # verified): same slab, same bits as the device-resident route
+        NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+        o.inflate_sphere(NL, 0, 1, 0, 1)
+        Kh = sf.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4)
+        out["host_call_same_bits"] = bool(Kh.mesh.info()["structured"] and all(np.array_equal(a, b) for a, b in zip(Kh.to_csc(), (colptr, rowval, nzval))))
+        # a rank whose own part is not meshgrid's numbering must notice: swap two elements of its first owned layer
+        k0 = info["row0"] // (3 * (ne + 1) ** 2)
+        IEN2 = IEN.copy()
+        e0 = min(k0, ne - 1) * ne * ne
+        IEN2[[e0, e0 + 1]] = IEN2[[e0 + 1, e0]]
+        try:
+            sf.assemble_system(ne, NL, IEN2, 3, "Q1", 3, ID, 40, 0.4)
+            out["bad_part_detected"] = False
+        except sf.SmearFEMError:
+            out["bad_part_detected"] = True   # unstructured meshes are single-GPU only
+        del Kh
         K.add_surface_mass(100.0)
         sd.connect(K)
         K.set_dirichlet_zplanes(0.001)
@@ -95,5 +112,6 @@ def test_slab_partition_matches_oracle(ws, ne):
         assert r["ok"], r
         assert r["pattern"], r
         assert r["relK"] <= 1e-10, r
+        assert r["host_call_same_bits"] and r["bad_part_detected"], r
         assert max(r["relq"]) <= 1e-10, r
         assert r["relq_warm"] <= 1e-10 and r["iters_warm"] <= 25, r
