@@ -11,10 +11,23 @@ for ne in (5, 9):
     mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
     K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
     for tile in ("4x4", "8x4"):
-        os.environ["SMFEM_TILE"] = tile
-        K.reassemble(40, 0.4)
-        nz = K.to_csc()[2]
-        assert np.linalg.norm(nz - r["K"].nzval) <= 1e-12 * np.linalg.norm(nz), tile
+        for out in ("0", "2", "3"):   # output routes: direct stores, all-TMA in place, values direct + column indices by TMA
+            os.environ["SMFEM_TILE"] = tile
+            os.environ["SMFEM_TILE_OUT"] = out
+            K.reassemble(40, 0.4)
+            nz = K.to_csc()[2]
+            assert np.linalg.norm(nz - r["K"].nzval) <= 1e-12 * np.linalg.norm(nz), (tile, out)
+    os.environ.pop("SMFEM_TILE"); os.environ.pop("SMFEM_TILE_OUT")
+    # the one-call host route: streamed NodeList (watermark polling), hybrid lattice check on the copy stream
+    NLh, IENh, IDh, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.inflate_sphere(NLh, 0, 1, 0, 1)
+    for threads in ("0", "2"):
+        os.environ["SMFEM_HOST_THREADS"] = threads
+        Kh = sf.assemble_system(ne, NLh, IENh, 3, "Q1", 3, IDh, 40, 0.4)
+        assert Kh.mesh.info()["structured"]
+        assert np.array_equal(Kh.to_csc()[2], nz)
+        Kh.free()
+    os.environ.pop("SMFEM_HOST_THREADS")
     K.add_surface_mass(100.0).set_dirichlet_zplanes(0.001)
     for v in (4, 3, 2, 1, 0):
         K.set_spmv_variant(v)
@@ -34,4 +47,10 @@ y = Kg.spmv(np.ones(Kg.shape[0]))
 NL2, IEN2, ID2, *_ = sf.meshgrid(0, 1, 0, 1, 0, 1, 6, 2)
 K2 = sf.assemble_system(6, NL2, IEN2, 2, "Q1", 2, ID2, 40, 0.4)
 Ks = sf.assemble_system(6, NL2, IEN2, 2)
+# Q2 9-node scalar quads (general path)
+n = 2 * 3 + 1
+xs = np.arange(n) / (n - 1)
+NLq = np.array([[x, y] for y in xs for x in xs]).T.copy()
+IENq = np.array([[2 * j * n + 2 * i + a + 1 for a in (0, 2, 2 * n + 2, 2 * n, 1, n + 2, 2 * n + 1, n, n + 1)] for j in range(3) for i in range(3)])
+Kq = sf.assemble_system(3, NLq, IENq, 2, "Q2", 1)
 print("sanitize target ok")
