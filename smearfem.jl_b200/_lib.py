@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmearfem_b200.so")
+LIB_PATH = os.environ.get("SMEARFEM_B200_LIB") or os.path.join(_HERE, "libsmearfem_b200.so")  # same override as the Julia shim
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_SINGULAR = 0, 1, 2, 3, 4
 Q1, Q2 = 1, 2
