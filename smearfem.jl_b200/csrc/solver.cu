@@ -849,16 +849,31 @@ __global__ void __launch_bounds__(256, 3) k_spmv_group(SpmvArgs A) {
                 for (int q = 0; q < G; ++q) acc[q] += v0[(int64_t)q * cL + s] * x1;
             }
         }
+        // MASK: Dirichlet rows are NOT masked here any more: p = 0 on them, so p'Ap is unaffected, and
+        // k_pcg_update_xr pins r = 0 where dinv == 0 (no per-group load of the flag in the hot loop).
+        if (G == 3 && !DOT) {
+            // three row sums with 6 instead of 15 double shuffles: halve the lanes AND the set of rows per step
+            const bool up = lane & 16, up8 = lane & 8;
+            const double t0 = __shfl_xor_sync(0xffffffffu, up ? acc[0] : acc[G - 1], 16);
+            const double t1 = __shfl_xor_sync(0xffffffffu, acc[1 % G], 16);
+            const double u0 = (up ? acc[G - 1] : acc[0]) + t0;  // lanes 0-15: row 0, lanes 16-31: row 2 (pair sums)
+            const double u1 = up ? 0.0 : acc[1 % G] + t1;         // lanes 0-15: row 1
+            const double t2 = __shfl_xor_sync(0xffffffffu, up8 ? u0 : u1, 8);
+            double v = (up8 ? u1 : u0) + t2;                     // lanes 0-7 row 0, 8-15 row 1, 16-23 row 2, 24-31 nothing
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if ((lane & 7) == 0 && lane < 24) A.y[r0 + (lane >> 3)] = v;
+        } else {
 #pragma unroll
-        for (int q = 0; q < G; ++q) acc[q] = warp_sum(acc[q]);  // xor-shuffles: every lane holds the row sums
-        if (lane < G) {
-            double yv = acc[0];
+            for (int q = 0; q < G; ++q) acc[q] = warp_sum(acc[q]);  // xor-shuffles: every lane holds the row sums
+            if (lane < G) {
+                double yv = acc[0];
 #pragma unroll
-            for (int q = 1; q < G; ++q)
-                if (lane == q) yv = acc[q];
-            // MASK: Dirichlet rows are NOT masked here any more: p = 0 on them, so p'Ap is unaffected, and
-            // k_pcg_update_xr pins r = 0 where dinv == 0 (no per-group load of the flag in the hot loop).
-            A.y[r0 + lane] = yv;
+                for (int q = 1; q < G; ++q)
+                    if (lane == q) yv = acc[q];
+                A.y[r0 + lane] = yv;
+            }
         }
         if (DOT) {
             // x_row (= p on the group's own rows) is among the gathered values: the diagonal columns
@@ -880,7 +895,8 @@ __global__ void __launch_bounds__(256, 3) k_spmv_group(SpmvArgs A) {
                 }
             }
         }
-        // rotate the pipeline
+        // rotate the pipeline (a ping-pong of the two register sets instead of these copies was measured 40 % slower:
+        // the compiler then serialises the streams of the next group behind the reduction)
         cg = ng_;
         cb0 = nb0;
         cL = nL;
