@@ -23,10 +23,7 @@
 #include <vector>
 
 #include "smfem_internal.cuh"
-
-struct Material {
-    double d11, lam, mu;
-};
+#include "tile_args.cuh"
 
 namespace {
 
@@ -60,43 +57,6 @@ struct Tile {
     static constexpr size_t SMEM_BYTES =
         sizeof(double) * (2 * LAYER + (ALIAS ? 0 : TX * TY * STAGE_NODE) + 8 * 8 * 3 + 8 + 4 * PLANE) + sizeof(int32_t) * COLBUF * (NTH / 32);
 };
-
-constexpr int MAX_CHUNKS = 24;
-
-struct TileArgs {
-    Lattice L;
-    const double *coords;
-    const int64_t *rowptr;
-    double *val;
-    int32_t *colind;  // non-null: the output phase also writes the pattern's column indices (fused assembly)
-    const int *ready;  // non-null: coordinate planes [0, *ready) have arrived (written by host->device copies while the kernel runs)
-    double *diag;
-    Material mat;
-    int tiles_x, tiles_y, nchunks;
-    int zb[MAX_CHUNKS + 1];  // chunk c of a tile column = owned planes [zb[c], zb[c+1]) (offsets from L.k0, longest first)
-    int out_mode;  // output route of the tile kernel (env SMFEM_TILE_OUT): see the output phase
-    int skip;  // ablation bitmask (env SMFEM_TILE_SKIP; profiling only): 1 phase 1, 2 main loop, 4 combine, 8 output,
-               // 16 / 32: column-index / value stores collapsed onto a small cache-resident window (no DRAM traffic)
-    double gp[8][3];     // the 8 Gauss points in the reference's order (src/fem.jl:174-176)
-    double w[8];
-};
-
-// asynchronous copy of node plane k (tile + 1-node halo, clipped to the lattice) into the coordinate ring
-template <class T>
-__device__ __forceinline__ void stage_plane(const TileArgs &A, double *s_xyz, int k, int X0, int Y0) {
-    const Lattice &L = A.L;
-    if (k < 0 || k >= L.n1 || k > L.k1) return;  // the slab holds planes k0-1 .. k1
-    double *dst = s_xyz + (k & 3) * T::PLANE;
-    for (int t = threadIdx.x; t < T::PLANE; t += T::NTH) {
-        const int c = t % 3, n = t / 3;
-        const int px = n % T::PX, py = n / T::PX;
-        const int gx = X0 - 1 + px, gy = Y0 - 1 + py;
-        if (gx < 0 || gy < 0 || gx >= L.n1 || gy >= L.n1) continue;
-        const double *src = A.coords + 3 * L.lnode(gx, gy, k) + c;
-        unsigned d = (unsigned)__cvta_generic_to_shared(dst + t);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
-    }
-}
 
 // element layer `layer` of the footprint -> ring slot.  g_b = dN_b adj(J) * sign(det) * sqrt(wp / |det|)
 // ( = sqrt(wp |det|) * dN_b J^-1, src/fem.jl:192-196 ).  Register-only formulation of the Q1 gradients:
@@ -520,7 +480,7 @@ bool values_tile_enabled() {
 // chunks whose lengths decay geometrically (long chunks first, short ones fill the tail); the makespan of each is
 // simulated with duration = planes + c0 (prologue: one extra element layer, pipeline fill) and the best one is kept
 // (100^3: 55 + 30 + 16 planes, modelled makespan 242 plane-times instead of 270; ideal 231).
-static std::vector<int> plan_chunks(int ntiles, int nown, int slots) {
+std::vector<int> plan_chunks(int ntiles, int nown, int slots) {
     if (const char *e = std::getenv("SMFEM_TILE_CHUNKS")) {  // experiments: explicit comma-separated lengths
         std::vector<int> len;
         int sum = 0;
@@ -606,9 +566,8 @@ static void launch_tile(smfem_ctx *ctx, TileArgs &A, int nown) {
     ctx->asm_count++;
 }
 
-void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind, const int *ready) {
+void tile_fill_args(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind, const int *ready, TileArgs &A) {
     if (!K->diag) K->diag = dev_alloc<double>(K->nrows_l);
-    TileArgs A;
     A.L = mesh->lat;
     A.coords = mesh->coords;
     A.rowptr = K->rowptr;
@@ -628,12 +587,16 @@ void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Mat
             A.w[g] = w[ix[g]] * w[iy[g]] * w[iz[g]];
         }
     }
-    {
-        const char *sk = std::getenv("SMFEM_TILE_SKIP");
-        A.skip = sk ? std::atoi(sk) : 0;
-        const char *om = std::getenv("SMFEM_TILE_OUT");
-        A.out_mode = om ? std::atoi(om) : 3;
-    }
+    const char *sk = std::getenv("SMFEM_TILE_SKIP");
+    A.skip = sk ? std::atoi(sk) : 0;
+    const char *om = std::getenv("SMFEM_TILE_OUT");
+    A.out_mode = om ? std::atoi(om) : 3;
+}
+
+void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind, const int *ready) {
+    TileArgs A;
+    tile_fill_args(ctx, mesh, K, mat, write_colind, ready, A);
+    if (values_assemble_mma(ctx, A, A.L.nown())) return;  // DMMA kernel (assemble_mma.cu), selected by SMFEM_TILE=mma*
     const char *e = std::getenv("SMFEM_TILE");
     const bool big = e && std::string(e) == "8x4";  // 256 threads, 1 CTA/SM; default 4x4: 128 threads, 2 CTAs/SM
 #define SMFEM_TILE_CASE(M)                                              \
