@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_mma(const __grid_consta
             adj[7] = J[1] * J[6] - J[0] * J[7];
             adj[8] = J[0] * J[4] - J[1] * J[3];
             const double det = J[0] * adj[0] + J[1] * adj[3] + J[2] * adj[6];
-            const double sc = copysign(rsqrt(fabs(det)), det) * sqrt(A.w[g]);
+            const double sc = copysign(rsqrt(fabs(det)), det) * A.sw[g];
             double2 *dst = reinterpret_cast<double2 *>(s_adj + t * ADJ);
             dst[0] = make_double2(adj[0] * sc, adj[1] * sc);
             dst[1] = make_double2(adj[2] * sc, adj[3] * sc);
@@ -184,11 +184,12 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_mma(const __grid_consta
             double g[3][2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const double2 *ad = reinterpret_cast<const double2 *>(s_adj + ((fy * EX + fx) * 8 + q + 4 * u) * ADJ);
-                const double2 m01 = ad[0], m23 = ad[1], m45 = ad[2], m67 = ad[3], m8 = ad[4];
-                g[0][u] = dN[u][0] * m01.x + dN[u][1] * m23.y + dN[u][2] * m67.x;
-                g[1][u] = dN[u][0] * m01.y + dN[u][1] * m45.x + dN[u][2] * m67.y;
-                g[2][u] = dN[u][0] * m23.x + dN[u][1] * m45.y + dN[u][2] * m8.x;
+                const double *ad = s_adj + ((fy * EX + fx) * 8 + q + 4 * u) * ADJ;
+                double m[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) m[t] = ad[t];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) g[c][u] = dN[u][0] * m[c] + dN[u][1] * m[3 + c] + dN[u][2] * m[6 + c];
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u)
@@ -211,12 +212,13 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_mma(const __grid_consta
                 const bool first = !((i == oxa && later_x) || (dy == 0 && later_y) || later_z);
                 double Kv[9];
                 const double tr = C[0][0][i] + C[1][1][i] + C[2][2][i];
+                const double mtr = A.mat.mu * tr, dm = A.mat.d11 - A.mat.mu;
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
                     for (int j = 0; j < 3; ++j) {
                         const double gij = C[c][j][i], gji = C[j][c][i];
-                        Kv[c * 3 + j] = (c == j) ? A.mat.d11 * gij + A.mat.mu * (tr - gij) : A.mat.lam * gij + A.mat.mu * gji;
+                        Kv[c * 3 + j] = (c == j) ? fma(dm, gij, mtr) : fma(A.mat.lam, gij, A.mat.mu * gji);
                     }
                 double *p = np + off[i];
                 double old[9];
@@ -244,10 +246,16 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_mma(const __grid_consta
         }
     };
 
-    // ---- output of the completed node plane k
+    // ---- output of the completed node plane k: lanes 0..26 own (dx, dy, j) and walk the dz sections of the three rows
+    const int o_r = lane / 3, o_j = lane - 3 * o_r;
+    const int o_dy = o_r / 3 - 1, o_dx = o_r - 3 * (o_r / 3) - 1;                       // interior nodes (27 neighbours)
+    const int o_src = 9 * (SLOT_LX * o_dx + SLOT_LY * o_dy + SLOT_C0 - SLOT_LZ) + o_j;  // staging offset of (dz = -1, c = 0)
+    const int o_col = 3 * (o_dx + o_dy * L.n1) + o_j;
     auto output = [&](int k) {
+        if (A.skip & 8) return;
         const double *sp = stage + (k & 1) * T::SP;
         const int lowz = k > 0, cz = 1 + lowz + (k < L.n1 - 1);
+        const int64_t zbase = pre1(k) * S1 * S1 - pairs_base;
 #pragma unroll 1
         for (int n = warp; n < TX * TY; n += T::NW) {
             const int ty = n / TX, tx = n - ty * TX;
@@ -255,14 +263,41 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_mma(const __grid_consta
             if (jx >= L.n1 || jy >= L.n1) continue;
             const int lowx = jx > 0, lowy = jy > 0;
             const int cx = 1 + lowx + (jx < L.n1 - 1), cy = 1 + lowy + (jy < L.n1 - 1);
+            const int64_t base = 9 * (zbase + (int64_t)cz * (pre1(jy) * S1 + (int64_t)cy * pre1(jx)));
+            const int64_t row = (((int64_t)(k - L.k0) * L.n1 + jy) * L.n1 + jx) * 3;
+            const double *nsrc = sp + ty * T::SR + tx * T::SN;
+            if (cx * cy * cz == 27) {  // interior node: everything but the two base addresses is a lane constant
+                if (lane < 27) {
+                    const double *src = nsrc + o_src;
+                    double *vp = A.val + base + lane;
+                    double v[9];
+#pragma unroll
+                    for (int rz = 0; rz < 3; ++rz)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) v[rz * 3 + c] = src[9 * SLOT_LZ * rz + 3 * c];
+#pragma unroll
+                    for (int rz = 0; rz < 3; ++rz)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) vp[c * 81 + rz * 27] = v[rz * 3 + c];
+                    if (A.colind) {
+                        int32_t *cp = A.colind + base + lane;
+                        const int32_t col0 = (int32_t)(L.lnode(jx, jy, k - 1) * 3) + o_col;
+                        const int32_t zstep = (int32_t)(3 * L.plane());
+#pragma unroll
+                        for (int rz = 0; rz < 3; ++rz)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) cp[c * 81 + rz * 27] = col0 + rz * zstep;
+                    }
+                    if (o_dx == 0 && o_dy == 0) A.diag[row + o_j] = o_j == 0 ? v[3] : (o_j == 1 ? v[4] : v[5]);  // dz = 0, c = j
+                }
+                continue;
+            }
             const int SL = 3 * cx * cy, TR = SL * cz;
             if (lane >= SL) continue;
-            const int64_t base = 9 * (pre1(k) * S1 * S1 + (int64_t)cz * (pre1(jy) * S1 + (int64_t)cy * pre1(jx)) - pairs_base);
-            const int64_t row = (((int64_t)(k - L.k0) * L.n1 + jy) * L.n1 + jx) * 3;
             const int r = lane / 3, j = lane - 3 * r;
             const int ry = r / cx, rx = r - ry * cx;
             const int dxn = rx - lowx, dyn = ry - lowy;
-            const double *src = sp + ty * T::SR + tx * T::SN + 9 * (SLOT_LX * dxn + SLOT_LY * dyn + SLOT_C0) + j;
+            const double *src = nsrc + 9 * (SLOT_LX * dxn + SLOT_LY * dyn + SLOT_C0) + j;
             const bool on_diag_col = dxn == 0 && dyn == 0;
             for (int rz = 0; rz < cz; ++rz) {
                 const int dzn = rz - lowz;
@@ -291,7 +326,7 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_mma(const __grid_consta
         if (k + 2 < L.n1 && k + 2 <= L.k1) wait_plane(k + 2);
         stage_plane<T>(A, s_xyz, k + 2, X0, Y0);  // lands during this layer; ring slot (k+2)&3 is free
         if (k < L.ne) do_layer(k, true, k + 1 < ze);
-        if (!(A.skip & 8)) output(k);
+        output(k);
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();  // staging plane k&1 is reused by layer k+1; coordinate plane k+2 has landed
     }
@@ -329,10 +364,8 @@ bool values_assemble_mma(smfem_ctx *ctx, TileArgs &A, int nown) {
     const char *e = std::getenv("SMFEM_TILE");
     const std::string v = e ? e : "";
     if (v == "mma84") launch_mma<MTile<8, 4, 16>, 1>(ctx, A, nown);
-    else if (v == "mma84w15") launch_mma<MTile<8, 4, 15>, 1>(ctx, A, nown);
     else if (v == "mma75") launch_mma<MTile<7, 5, 12>, 1>(ctx, A, nown);
     else if (v == "mma44") launch_mma<MTile<4, 4, 8>, 2>(ctx, A, nown);
-    else if (v == "mma44w9") launch_mma<MTile<4, 4, 9>, 2>(ctx, A, nown);
     else return false;
     return true;
 }

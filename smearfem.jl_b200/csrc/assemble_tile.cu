@@ -585,6 +585,7 @@ void tile_fill_args(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material 
             A.gp[g][1] = xi[iy[g]];
             A.gp[g][2] = xi[iz[g]];
             A.w[g] = w[ix[g]] * w[iy[g]] * w[iz[g]];
+            A.sw[g] = std::sqrt(A.w[g]);
         }
     }
     const char *sk = std::getenv("SMFEM_TILE_SKIP");

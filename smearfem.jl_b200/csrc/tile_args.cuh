@@ -26,6 +26,7 @@ struct TileArgs {
                // 16 / 32: column-index / value stores collapsed onto a small cache-resident window (no DRAM traffic)
     double gp[8][3];     // the 8 Gauss points in the reference's order (src/fem.jl:174-176)
     double w[8];
+    double sw[8];        // sqrt(w)
 };
 
 // asynchronous copy of node plane k (tile + 1-node halo, clipped to the lattice) into the coordinate ring

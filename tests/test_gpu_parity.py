@@ -297,7 +297,24 @@ def test_tile_and_atomic_value_kernels_agree(monkeypatch):
                 assert np.array_equal(K.to_csc()[2], nz1), (tile, out, chunks)
                 assert np.array_equal(K.diag(), d1), (tile, out, chunks)
                 monkeypatch.delenv("SMFEM_TILE_CHUNKS", raising=False)
-    for v in ("SMFEM_TILE", "SMFEM_TILE_OUT", "SMFEM_DEBUG_CLEAR"):
+    # the fp64 tensor-core (DMMA) kernel, opt-in: same pattern, same values to rounding (the fold order differs),
+    # every entry rewritten, bit-reproducible for every tile shape and chunk plan
+    monkeypatch.delenv("SMFEM_TILE_OUT")
+    for tile in ("mma75", "mma84", "mma44"):
+        ref = None
+        for chunks in (None, "5,4,5", "1,13"):
+            monkeypatch.setenv("SMFEM_TILE", tile)
+            if chunks:
+                monkeypatch.setenv("SMFEM_TILE_CHUNKS", chunks)
+            K.reassemble(40, 0.4)
+            assert_csc_parity(K, Ko)
+            nz = K.to_csc()[2]
+            assert rel(nz, nz1) <= 1e-14 and rel(K.diag(), d1) <= 1e-14, (tile, chunks)
+            if ref is None:
+                ref = nz
+            assert np.array_equal(nz, ref), (tile, chunks)
+            monkeypatch.delenv("SMFEM_TILE_CHUNKS", raising=False)
+    for v in ("SMFEM_TILE", "SMFEM_DEBUG_CLEAR"):
         monkeypatch.delenv(v)
     monkeypatch.setenv("SMFEM_VALUES", "atomic")
     K.assemble_values(40, 0.4)

@@ -17,7 +17,13 @@ for ne in (5, 9):
             K.reassemble(40, 0.4)
             nz = K.to_csc()[2]
             assert np.linalg.norm(nz - r["K"].nzval) <= 1e-12 * np.linalg.norm(nz), (tile, out)
-    os.environ.pop("SMFEM_TILE"); os.environ.pop("SMFEM_TILE_OUT")
+    os.environ.pop("SMFEM_TILE_OUT")
+    for tile in ("mma75", "mma84", "mma44"):   # fp64 tensor-core (DMMA) kernel, opt-in
+        os.environ["SMFEM_TILE"] = tile
+        K.reassemble(40, 0.4)
+        nzm = K.to_csc()[2]
+        assert np.linalg.norm(nzm - r["K"].nzval) <= 1e-12 * np.linalg.norm(nzm), tile
+    os.environ.pop("SMFEM_TILE")
     # the one-call host route: streamed NodeList (watermark polling), hybrid lattice check on the copy stream
     NLh, IENh, IDh, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
     o.inflate_sphere(NLh, 0, 1, 0, 1)
