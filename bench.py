@@ -372,6 +372,13 @@ def main():
                          "bytes": "12 B/nnz (value + column index) + 24 B/node coordinates read + 24 B/node diagonal written; "
                                   "IEN/ID/rowptr of SURVEY 8(d)'s 3.07 KB/element are not touched by this kernel and not counted",
                          "survey_bytes_per_step": b_total, "survey_GB/s_per_step": b_total / t_step / 1e9,
+                         # the fp64 pipe is the co-equal ceiling of this kernel.  Algorithmic flops per element with the
+                         # post-quadrature material: G = sum_gp g_a g_b' 8 x 64 x 9 FMA = 9216, gradients
+                         # (J, adj, det, dN J^-1) ~350 x 8 gp = 2800, material ~570  -> 12.6 kflop; peak = DFMA rate measured by
+                         # tools/microbench/peaks.cu / dmma.cu on this pool (34-37 TFLOP/s; DMMA runs at the same rate)
+                         "fp64": {"flop_per_element": 12600, "achieved": 12600.0 * (ne**3 / world) / t_fused_kernel / 1e12, "peak": 36.5,
+                                  "unit": "TFLOP/s", "frac": 12600.0 * (ne**3 / world) / t_fused_kernel / 1e12 / 36.5,
+                                  "peak_source": "measured DFMA microbenchmark (tools/microbench), not in MEASURED_PEAKS.json"},
                          "values_only": {"ms_per_launch": t_val_kernel * 1e3, "algorithmic_bytes_per_launch": bk_values,
                                          "achieved": bk_values / t_val_kernel / 1e9, "frac": bk_values / t_val_kernel / 1e9 / hbm_peak,
                                          "traffic": traffic.get("k_values_tile"), "elements_per_s": ne**3 / t_val_kernel}},

@@ -108,6 +108,12 @@ int smfem_mesh_set_nodelist(smfem_ctx *ctx, smfem_mesh *mesh, const double *Node
  * owned node count */
 int smfem_mesh_info(smfem_mesh *mesh, int64_t *nNodes, int64_t *nEl, int *nLocal, int *ndim, int *structured,
                     int64_t *node0_owned, int64_t *nNodes_owned);
+/* Element colouring of a general (IEN) mesh, built on first use and cached in the mesh: elements of one colour share no
+ * node, so the value scatter of assemble_system (src/fem.jl:236-249) runs colour by colour (one launch per colour, at most
+ * one add per entry and launch) and every entry of K is folded in a fixed order (bit-reproducible).  ncolors = -1: more than 64 colours would be needed, the
+ * atomic scatter is used.  color_sizes (optional): 64 entries, elements per colour.  SMFEM_ERR_INVALID on lattice meshes
+ * (their tiled gather kernel needs no colouring). */
+int smfem_mesh_colors(smfem_ctx *ctx, smfem_mesh *mesh, int *ncolors, int64_t *color_sizes);
 /* Export in Julia layout (caller allocates from smfem_mesh_info; any pointer may be NULL).
  * NodeList: ndim x nNodes_owned of THIS rank's owned nodes; IEN/ID/IEN_top/IEN_btm: global arrays
  * (structured meshes regenerate them; only sensible for small ne, rank 0). */

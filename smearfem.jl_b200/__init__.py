@@ -150,6 +150,14 @@ class Mesh:
         return dict(nNodes=nN.value, nEl=nE.value, nLocal=nl.value, ndim=nd.value, structured=bool(st.value),
                     node0_owned=n0.value, nNodes_owned=nO.value)
 
+    def colors(self):
+        """Element colouring of a general mesh (built on first use): (ncolors, elements per colour); ncolors = -1 when the
+        atomic scatter is used instead."""
+        nc = C.c_int()
+        sizes = np.zeros(64, dtype=np.int64)
+        call("smfem_mesh_colors", self.ctx.handle, self.handle, C.byref(nc), _pi(sizes))
+        return nc.value, sizes[: max(nc.value, 0)].copy()
+
     def inflate_sphere(self, x0, x1, y0, y1):
         call("smfem_inflate_sphere", self.ctx.handle, self.handle, float(x0), float(x1), float(y0), float(y1))
         return self

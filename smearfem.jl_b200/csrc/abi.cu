@@ -448,6 +448,18 @@ int smfem_mesh_info(smfem_mesh *mesh, int64_t *nNodes, int64_t *nEl, int *nLocal
     });
 }
 
+int smfem_mesh_colors(smfem_ctx *ctx, smfem_mesh *mesh, int *ncolors, int64_t *color_sizes) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(mesh);
+        NOTNULL(ncolors);
+        mesh_color_elements(ctx, mesh);
+        *ncolors = mesh->ncolors;
+        if (color_sizes)
+            for (int c = 0; c < 64; ++c) color_sizes[c] = mesh->ncolors > 0 ? mesh->color_off[c + 1] - mesh->color_off[c] : 0;
+    });
+}
+
 int smfem_mesh_export(smfem_ctx *ctx, smfem_mesh *mesh, double *NodeList_owned, int64_t *IEN, int64_t *ID, int64_t *IEN_top,
                       int64_t *IEN_btm) {
     return guarded([&] {
@@ -498,6 +510,7 @@ int smfem_mesh_free(smfem_mesh *mesh) {
         dev_free(mesh->coords);
         dev_free(mesh->ien);
         dev_free(mesh->id);
+        dev_free(mesh->elist);
         delete mesh;
     });
 }

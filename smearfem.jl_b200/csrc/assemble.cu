@@ -1,6 +1,7 @@
 // Assembly side of the path: sparsity pattern on device, element kernels, scatter, surface term,
 // diagonal extraction, CSC export.
 //   reference: src/fem.jl:135-256 (assemble_system), examples/vector3D.jl:175-264 (surface matrix)
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
@@ -437,6 +438,153 @@ void pattern_build_general(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Element colouring of a general mesh (north star: "graph-coloured ... scatter-add").
+// Jones-Plassmann with fixed pseudo-random priorities: in every sweep an uncoloured element whose priority
+// beats all its uncoloured neighbours (elements sharing a node) takes the smallest colour none of its
+// coloured neighbours has.  The sweeps read the previous sweep's colours only (two buffers), so the result
+// does not depend on thread timing; elements are then sorted by colour (stable radix sort).  The value
+// kernel runs colour after colour (one launch each): a fixed fold order per matrix entry = bit-reproducible.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352dU;
+    x ^= x >> 15;
+    x *= 0x846ca68bU;
+    x ^= x >> 16;
+    return x;
+}
+
+__global__ void k_color_sweep(const int32_t *__restrict__ ien, int64_t nEl, int nn, const int64_t *__restrict__ n2e_ptr,
+                              const int32_t *__restrict__ n2e, const int8_t *__restrict__ col_old, int8_t *__restrict__ col_new,
+                              int *__restrict__ flags) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nEl) return;
+    const int8_t c0 = col_old[e];
+    if (c0 >= 0) {
+        col_new[e] = c0;
+        return;
+    }
+    const uint32_t pe = hash32((uint32_t)e);
+    unsigned long long forbidden = 0;
+    bool is_max = true;
+    for (int a = 0; a < nn; ++a) {
+        const int32_t node = ien[(int64_t)a * nEl + e];
+        for (int64_t q = n2e_ptr[node]; q < n2e_ptr[node + 1]; ++q) {
+            const int32_t f = n2e[q];
+            if (f == e) continue;
+            const int8_t cf = col_old[f];
+            if (cf >= 0) {
+                forbidden |= 1ull << cf;
+            } else {
+                const uint32_t pf = hash32((uint32_t)f);
+                if (pf > pe || (pf == pe && f > e)) is_max = false;
+            }
+        }
+    }
+    if (!is_max) {
+        col_new[e] = -1;
+        flags[0] = 1;  // somebody is still uncoloured
+        return;
+    }
+    const int c = __ffsll((long long)~forbidden) - 1;
+    if (c < 0 || c >= 64) {
+        flags[1] = 1;  // more than 64 colours needed
+        col_new[e] = 0;
+        return;
+    }
+    col_new[e] = (int8_t)c;
+}
+
+__global__ void k_color_hist(const int8_t *__restrict__ col, int64_t nEl, int *__restrict__ hist) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nEl) atomicAdd(&hist[col[e]], 1);
+}
+
+__global__ void k_iota32(int64_t n, int32_t *__restrict__ v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int32_t)i;
+}
+
+void mesh_color_elements(smfem_ctx *ctx, smfem_mesh *mesh) {
+    if (mesh->ncolors != 0) return;
+    REQUIRE(!mesh->structured && mesh->ien, SMFEM_ERR_INVALID, "element colouring is for general (IEN) meshes");
+    const int64_t nNodes = mesh->nNodes_g, nEl = mesh->nEl_g;
+    const int nn = mesh->nn;
+    int *cnt = dev_alloc<int>(nNodes + 1), *cursor = dev_alloc<int>(nNodes + 1), *flags = dev_alloc<int>(2 + 64);
+    int64_t *n2e_ptr = dev_alloc<int64_t>(nNodes + 1);
+    int32_t *n2e = dev_alloc<int32_t>(nEl * nn), *ids = dev_alloc<int32_t>(nEl), *sorted = dev_alloc<int32_t>(nEl);
+    int8_t *col[2] = {dev_alloc<int8_t>(nEl), dev_alloc<int8_t>(nEl)};
+    uint8_t *keys_out = dev_alloc<uint8_t>(nEl);
+    void *tmp = nullptr;
+    auto cleanup = [&] {
+        dev_free(cnt);
+        dev_free(cursor);
+        dev_free(flags);
+        dev_free(n2e_ptr);
+        dev_free(n2e);
+        dev_free(ids);
+        dev_free(col[0]);
+        dev_free(col[1]);
+        dev_free(keys_out);
+        if (tmp) dev_cache_free(tmp);
+    };
+    try {
+        CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int) * (nNodes + 1), ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(int) * (nNodes + 1), ctx->stream));
+        const unsigned gE = (unsigned)((nEl * nn + 255) / 256), gEl = (unsigned)((nEl + 127) / 128);
+        LAUNCH(ctx, k_n2e_count, gE, 256, 0, (const int32_t *)mesh->ien, nEl, nn, cnt);
+        exclusive_scan_dev(ctx, cub::TransformInputIterator<int64_t, IntTo64, const int *>(cnt, IntTo64()), n2e_ptr, nNodes + 1);
+        LAUNCH(ctx, k_n2e_fill, gE, 256, 0, (const int32_t *)mesh->ien, nEl, nn, (const int64_t *)n2e_ptr, cursor, n2e);
+        CUDA_CHECK(cudaMemsetAsync(col[0], 0xFF, nEl, ctx->stream));
+        int cur = 0, h[2] = {1, 0}, sweeps = 0;
+        while (h[0]) {
+            REQUIRE(++sweeps <= 1000, SMFEM_ERR_CUDA, "element colouring did not converge");
+            CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * 2, ctx->stream));
+            LAUNCH(ctx, k_color_sweep, gEl, 128, 0, (const int32_t *)mesh->ien, nEl, nn, (const int64_t *)n2e_ptr, (const int32_t *)n2e,
+                   (const int8_t *)col[cur], col[cur ^ 1], flags);
+            CUDA_CHECK(cudaMemcpyAsync(h, flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            cur ^= 1;
+            if (h[1]) break;
+        }
+        if (h[1]) {  // a node of very high valence: keep the atomic scatter
+            mesh->ncolors = -1;
+            dev_free(sorted);
+            cleanup();
+            return;
+        }
+        // elements sorted by colour + colour offsets
+        LAUNCH(ctx, k_iota32, (unsigned)((nEl + 255) / 256), 256, 0, nEl, ids);
+        size_t tmp_bytes = 0;
+        const uint8_t *keys_in = reinterpret_cast<const uint8_t *>(col[cur]);
+        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, (const int32_t *)ids, sorted, nEl, 0, 7, ctx->stream));
+        tmp = dev_cache_alloc(tmp_bytes);
+        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, (const int32_t *)ids, sorted, nEl, 0, 7, ctx->stream));
+        ctx->launches++;
+        int *hist = flags + 2;
+        CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(int) * 64, ctx->stream));
+        LAUNCH(ctx, k_color_hist, gEl, 128, 0, (const int8_t *)col[cur], nEl, hist);
+        int hh[64];
+        CUDA_CHECK(cudaMemcpyAsync(hh, hist, sizeof(int) * 64, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        int nc = 0;
+        mesh->color_off[0] = 0;
+        for (int c = 0; c < 64; ++c) {
+            mesh->color_off[c + 1] = mesh->color_off[c] + hh[c];
+            if (hh[c]) nc = c + 1;
+        }
+        REQUIRE(mesh->color_off[64] == nEl, SMFEM_ERR_CUDA, "element colouring lost elements");
+        mesh->elist = sorted;
+        mesh->ncolors = nc;
+    } catch (...) {
+        dev_free(sorted);
+        cleanup();
+        throw;
+    }
+    cleanup();
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1 + K3, general form: one thread per (element, local node a) computes the a-th block row of
 //   Ke = sum_gp w * B'DB                                   (src/fem.jl:183-233)
 // through the isotropic identity  K_ab = lam * G_ab + mu * G_ab' + mu tr(G_ab) I,
@@ -475,10 +623,14 @@ struct Material {
     double d11, lam, mu;  // D(1,1), D(1,2), shear
 };
 
-template <int NDIM, int NDOF, int NN = (1 << NDIM)>  // NN = 9: the reference's Q2 quad (2-D, scalar, 2x2 under-integration)
+// COLORED: the launch covers the elements elist[0 .. n_list) of ONE colour (no two share a node): every entry of K receives
+// at most one add per launch, so the fold order is the colour order whatever the thread timing (the adds stay L2 reductions:
+// a load-add-store round trip measured 2x slower than RED)
+template <int NDIM, int NDOF, int NN = (1 << NDIM), bool COLORED = false>  // NN = 9: the reference's Q2 quad (2-D, scalar, 2x2 under-integration)
 __global__ void __launch_bounds__(128)
 k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64_t *__restrict__ rowptr,
-                const int32_t *__restrict__ colind, double *__restrict__ val, Material mat) {
+                const int32_t *__restrict__ colind, double *__restrict__ val, Material mat, const int32_t *__restrict__ elist = nullptr,
+                int64_t n_list = 0) {
     constexpr int NGP = 1 << NDIM;
     __shared__ double s_dN[NGP][NN][NDIM];
     __shared__ double s_w[NGP];
@@ -490,8 +642,8 @@ k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64
     if (threadIdx.x < NGP) s_w[threadIdx.x] = (NDIM == 3) ? c_w3[threadIdx.x] : c_w2[threadIdx.x];
     __syncthreads();
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= C.nEl * NN) return;
-    int64_t e = t / NN;
+    if (t >= (COLORED ? n_list : C.nEl) * NN) return;
+    int64_t e = COLORED ? (int64_t)elist[t / NN] : t / NN;
     int a = (int)(t % NN);
     int64_t nodes[NN];
     double X[NN][NDIM];
@@ -565,7 +717,7 @@ k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64
     for (int b = 0; b < NN; ++b) {
         if (NDOF == 1) {
             int64_t pos = csr_find(rowptr, colind, rows[0], D.col(nodes[b], 0));
-            atomicAdd(&val[pos], G[b][0]);
+            atomicAdd(&val[pos], G[b][0]);  // COLORED: the only add to this entry in the launch (RED is cheaper than load-add-store)
         } else {
             double tr = 0;
 #pragma unroll
@@ -622,19 +774,39 @@ void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Y
         Conn C = make_conn(mesh);
         DofMap D = make_dofmap(mesh, K);
         const int nn = mesh->nn;
-        unsigned grid = (unsigned)((C.nEl * nn + 127) / 128);
-        if (ndim == 2 && nDof == 1 && nn == 9)
-            LAUNCH(ctx, (k_values_atomic<2, 1, 9>), grid, 128, 0, C, D, mesh->coords, K->rowptr, K->colind, K->val, mat);
-        else if (ndim == 3 && nDof == 3)
-            LAUNCH(ctx, (k_values_atomic<3, 3>), grid, 128, 0, C, D, mesh->coords, K->rowptr, K->colind, K->val, mat);
-        else if (ndim == 3 && nDof == 1)
-            LAUNCH(ctx, (k_values_atomic<3, 1>), grid, 128, 0, C, D, mesh->coords, K->rowptr, K->colind, K->val, mat);
-        else if (ndim == 2 && nDof == 2)
-            LAUNCH(ctx, (k_values_atomic<2, 2>), grid, 128, 0, C, D, mesh->coords, K->rowptr, K->colind, K->val, mat);
-        else if (ndim == 2 && nDof == 1)
-            LAUNCH(ctx, (k_values_atomic<2, 1>), grid, 128, 0, C, D, mesh->coords, K->rowptr, K->colind, K->val, mat);
-        else
+        // general meshes: colour by colour without atomics (deterministic); SMFEM_VALUES=atomic keeps the atomic scatter
+        const char *ev = std::getenv("SMFEM_VALUES");
+        bool colored = !mesh->structured && mesh->ien && !(ev && std::string(ev) == "atomic");
+        if (colored) {
+            mesh_color_elements(ctx, mesh);
+            colored = mesh->ncolors > 0;
+        }
+#define SMFEM_VALUES_CASE(ND, NDF, NNN)                                                                                              \
+    if (colored) {                                                                                                                   \
+        for (int c = 0; c < mesh->ncolors; ++c) {                                                                                    \
+            const int64_t n_list = mesh->color_off[c + 1] - mesh->color_off[c];                                                      \
+            if (n_list == 0) continue;                                                                                               \
+            LAUNCH(ctx, (k_values_atomic<ND, NDF, NNN, true>), (unsigned)((n_list * nn + 127) / 128), 128, 0, C, D, mesh->coords,    \
+                   K->rowptr, K->colind, K->val, mat, (const int32_t *)(mesh->elist + mesh->color_off[c]), n_list);                  \
+        }                                                                                                                            \
+    } else {                                                                                                                         \
+        LAUNCH(ctx, (k_values_atomic<ND, NDF, NNN, false>), (unsigned)((C.nEl * nn + 127) / 128), 128, 0, C, D, mesh->coords,        \
+               K->rowptr, K->colind, K->val, mat, (const int32_t *)nullptr, (int64_t)0);                                            \
+    }
+        if (ndim == 2 && nDof == 1 && nn == 9) {
+            SMFEM_VALUES_CASE(2, 1, 9)
+        } else if (ndim == 3 && nDof == 3) {
+            SMFEM_VALUES_CASE(3, 3, 8)
+        } else if (ndim == 3 && nDof == 1) {
+            SMFEM_VALUES_CASE(3, 1, 8)
+        } else if (ndim == 2 && nDof == 2) {
+            SMFEM_VALUES_CASE(2, 2, 4)
+        } else if (ndim == 2 && nDof == 1) {
+            SMFEM_VALUES_CASE(2, 1, 4)
+        } else {
             throw SmfemError(SMFEM_ERR_UNSUPPORTED, "assemble_system: supported (ndim,nDof) are (3,3) (3,1) (2,2) (2,1)");
+        }
+#undef SMFEM_VALUES_CASE
     }
     K->values_ready = true;
     extract_diag(ctx, K);

@@ -117,6 +117,10 @@ struct smfem_mesh {
     int nDof_id = 0;
     bool std_id = false;     // ID is the standard node-major map (or absent): dof = nDof*node + comp
     int64_t ndof_id = 0;  // max(ID)
+    // element colouring (general meshes; built on first use by mesh_color_elements): elements of one colour share no node
+    int32_t *elist = nullptr;  // element ids sorted by colour
+    int ncolors = 0;           // 0: not built, -1: not colourable with <= 64 colours (atomic scatter is used)
+    int64_t color_off[65] = {};
     // surface faces for general meshes are passed to smfem_surface_mass directly
 };
 
@@ -199,6 +203,7 @@ void pattern_prepare_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *
 void pattern_build_structured(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
 bool values_tile_enabled();
 void pattern_build_general(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K);
+void mesh_color_elements(smfem_ctx *ctx, smfem_mesh *mesh);  // assemble.cu
 // ready (device int, optional): the coordinate planes [0, *ready) have been written; the tile kernel waits plane by plane
 void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Young, double nu, bool fuse_pattern = false,
                      const int *ready = nullptr);

@@ -123,6 +123,46 @@ def test_general_path_shuffled_elements_standard_ids():
     assert rel(q, o.example_problem(ne)["q"]) <= TOL
 
 
+def test_general_path_coloured_scatter_is_deterministic(monkeypatch):
+    """General meshes are assembled colour by colour, one add per entry and launch: the colouring is valid (no two
+    elements of a colour share a node), covers every element, and two assemblies give the same bits; the atomic scatter
+    (SMFEM_VALUES=atomic) agrees to rounding.  Also 2-D Q4 and scalar problems."""
+    ne = 7
+    ctx = sf.context()
+    NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.jitter_nodes(NL, ne, seed=3)
+    rng = np.random.default_rng(21)
+    IENp = IEN[rng.permutation(IEN.shape[0])]
+    IDp = (rng.permutation(ID.size) + 1).reshape(ID.shape).astype(np.int64)
+    for ids in (ID, IDp):
+        mesh = sf.Mesh.from_host(ctx, NL, IENp, ids, 3, 3, ne)
+        assert not mesh.info()["structured"]
+        nc, sizes = mesh.colors()
+        assert 8 <= nc <= 64 and sizes.sum() == ne**3 and sizes.min() > 0
+        K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
+        Ko = o.assemble_system(ne, NL, IENp, 3, "Q1", 3, ids, 40, 0.4)
+        assert_csc_parity(K, Ko, tol=1e-13)
+        nz1 = K.to_csc()[2]
+        for _ in range(3):
+            K.assemble_values(40, 0.4)
+            assert np.array_equal(K.to_csc()[2], nz1), "coloured scatter must be bit-reproducible"
+        monkeypatch.setenv("SMFEM_VALUES", "atomic")
+        K.assemble_values(40, 0.4)
+        monkeypatch.delenv("SMFEM_VALUES")
+        assert rel(K.to_csc()[2], nz1) <= 1e-14
+    # scalar hex and 2-D plane stress on shuffled connectivities
+    Ks = sf.assemble_system(ne, NL, IENp, 3, "Q1", 1)
+    assert_csc_parity(Ks, o.assemble_system(ne, NL, IENp, 3, "Q1", 1), tol=1e-13)
+    NL2, IEN2, ID2, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, 9, 2)
+    IEN2p = IEN2[rng.permutation(IEN2.shape[0])]
+    K2 = sf.assemble_system(9, NL2, IEN2p, 2, "Q1", 2, ID2, 40, 0.4)
+    assert not K2.mesh.info()["structured"] and K2.mesh.colors()[0] >= 4
+    assert_csc_parity(K2, o.assemble_system(9, NL2, IEN2p, 2, "Q1", 2, ID2, 40, 0.4), tol=1e-13)
+    # lattice meshes need no colouring
+    with pytest.raises(sf.SmearFEMError):
+        sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, 3, 3).colors()
+
+
 def test_assemble_system_one_call_matches_two_step():
     """smfem_assemble_system (transfers of IEN / ID overlapped with a speculative lattice assembly) gives the bits of
     smfem_mesh_from_host + smfem_assemble; a mesh with meshgrid's sizes but another numbering falls back correctly."""

@@ -16,11 +16,20 @@ for name, ids in (("standard ID", ID), ("permuted ID", (rng.permutation(ID.size)
     ctx.timer_start()
     K = sf.SparseMatrixB200.pattern(ctx, mesh, 3, 3)
     tp = ctx.timer_stop()
-    K.assemble_values(40, 0.4)
     ctx.timer_start()
-    for _ in range(3):
+    nc, sizes = mesh.colors()
+    tc = ctx.timer_stop()
+    res = {}
+    for mode in ("colored", "atomic"):
+        os.environ["SMFEM_VALUES"] = mode
         K.assemble_values(40, 0.4)
-    ms = ctx.timer_stop() / 3
+        ctx.timer_start()
+        for _ in range(3):
+            K.assemble_values(40, 0.4)
+        res[mode] = ctx.timer_stop() / 3
+    os.environ.pop("SMFEM_VALUES")
+    ms = res["colored"]
+    print(f"  colouring {tc:.1f} ms, {nc} colours (sizes {sizes.min()}..{sizes.max()}); values coloured {res['colored']:.2f} ms, atomic {res['atomic']:.2f} ms")
     t = K.bench_spmv(reps=10, variant=4)
     i = K.info()
     gbs = (12 * i["nnz_local"] + 24 * i["nrows_local"]) / t / 1e6
