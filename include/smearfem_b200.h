@@ -198,6 +198,12 @@ int smfem_set_dirichlet(smfem_ctx *ctx, smfem_matrix *K, const int64_t *dofs, co
 int smfem_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const double *rhs_extra,
                     double *q_out, int *iters_out, double *relres_out);
 
+/* Opt-in: the following smfem_pcg_solve calls on K use CG preconditioned by a geometric multigrid V-cycle instead of
+ * Jacobi (examples/vector3D.jl:315-322 solved in ~20 instead of ~9 ne iterations).  Hex-lattice matrices on one GPU only
+ * (SMFEM_ERR_UNSUPPORTED otherwise); `mesh` is K's mesh and must outlive the solves.  Coarse levels (ceil(ne/2), ... down to
+ * <= 4) take every other node of the finer mesh and are re-assembled with K's own E, nu and surface term; the hierarchy
+ * is built at the first solve and rebuilt after a re-assembly.  enable = 0 returns to Jacobi-PCG. */
+int smfem_pcg_use_multigrid(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, int enable);
 /* Load stepping (examples/vector3D.jl:310-338: the same K̄ solved for 50 prescribed displacements d; q is exactly
  * linear in d): the NEXT smfem_pcg_solve on K starts from scale * (previous solution on the free dofs) instead of 0.
  * Typical use: set_dirichlet_zplanes(d_new); set_warm_start(d_new / d_old); pcg_solve(...) -> 0-2 iterations. */

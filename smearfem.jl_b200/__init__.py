@@ -298,6 +298,11 @@ class SparseMatrixB200:
         call("smfem_pcg_solve", self.ctx.handle, self.handle, float(rtol), int(maxit), _pf(ex), _pf(q), C.byref(it), C.byref(rel))
         return q, int(it.value), float(rel.value)
 
+    def use_multigrid(self, enable=True):
+        """Opt-in: later pcg_solve calls use CG preconditioned by a geometric multigrid V-cycle (hex lattice, one GPU)."""
+        call("smfem_pcg_use_multigrid", self.ctx.handle, self.handle, self.mesh.handle if self.mesh is not None else None, int(bool(enable)))
+        return self
+
     def pcg_stats(self):
         ms, ms2, it = C.c_float(), C.c_float(), C.c_int()
         call("smfem_pcg_stats", self.handle, C.byref(ms), C.byref(ms2), C.byref(it))

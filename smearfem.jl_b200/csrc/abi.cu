@@ -810,6 +810,7 @@ int smfem_transfer_bytes(smfem_ctx *ctx, int64_t *h2d, int64_t *d2h) {
 int smfem_matrix_free(smfem_matrix *K) {
     return guarded([&] {
         if (!K) return;
+        gmg_free(K);
         solver_free(K);
         dev_free(K->rowptr);
         dev_free(K->colind);
@@ -892,7 +893,17 @@ int smfem_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, con
         NOTNULL(ctx);
         NOTNULL(K);
         REQUIRE(rtol > 0 && maxit >= 0, SMFEM_ERR_INVALID, "need rtol > 0, maxit >= 0");
-        pcg_solve(ctx, K, rtol, maxit, rhs_extra, q_out, iters_out, relres_out);
+        if (K->gmg_on) gmg_pcg_solve(ctx, K, rtol, maxit, rhs_extra, q_out, iters_out, relres_out);
+        else pcg_solve(ctx, K, rtol, maxit, rhs_extra, q_out, iters_out, relres_out);
+    });
+}
+
+int smfem_pcg_use_multigrid(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, int enable) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(K);
+        if (enable) NOTNULL(mesh);
+        gmg_enable(ctx, K, mesh, enable != 0);
     });
 }
 

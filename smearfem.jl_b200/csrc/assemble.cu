@@ -758,6 +758,11 @@ void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Y
         mat.lam = nu * f;
         mat.mu = (1 - 2 * nu) / 2 * f;
     }
+    K->Young = Young;
+    K->nu = nu;
+    K->beta_total = 0.0;
+    K->mat_known = true;
+    K->gmg_dirty = true;
     if (!K->val) {
         K->val = dev_alloc<double>(K->nnz_l + 16);
         CUDA_CHECK(cudaMemsetAsync(K->val + K->nnz_l, 0, 16 * sizeof(double), ctx->stream));
@@ -868,6 +873,8 @@ void surface_mass(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, const int32
                K->rowptr, K->colind, K->val, keep_b ? K->bval : (double *)nullptr, beta);
     }
     if (beta != 0.0) extract_diag(ctx, K);
+    K->beta_total += beta;
+    K->gmg_dirty = true;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -161,6 +161,12 @@ struct smfem_matrix {
     double *bval = nullptr;  // surface matrix on the same pattern (only when kept)
     double *diag = nullptr;
     bool values_ready = false;
+    // what the values were assembled from (the multigrid preconditioner re-assembles coarse operators with it)
+    double Young = 0, nu = 0, beta_total = 0;
+    bool mat_known = false;
+    void *gmg = nullptr;            // Gmg* (gmg.cu), built at the first multigrid solve
+    smfem_mesh *gmg_mesh = nullptr;  // not owned
+    bool gmg_on = false, gmg_dirty = true;
     // Dirichlet
     uint8_t *fixed = nullptr;  // nrows_l
     double *qd = nullptr;      // ncols_l (ghost entries filled locally)
@@ -219,6 +225,12 @@ void dirichlet_list(smfem_ctx *ctx, smfem_matrix *K, const int64_t *dofs, const 
 void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const double *rhs_extra, double *q_out,
                int *iters, double *relres);
 void spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y);
+void spmv_device(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y);  // device vectors: x ncols_l (ghost planes), y nrows_l
+// gmg.cu: geometric-multigrid preconditioned CG (single GPU, hex lattice)
+void gmg_enable(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, bool enable);
+void gmg_free(smfem_matrix *K);
+void gmg_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const double *rhs_extra, double *q_out, int *iters,
+                   double *relres);
 void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *ms);
 void comm_export(smfem_ctx *ctx, smfem_matrix *K, void *handle_out);
 void comm_connect(smfem_ctx *ctx, smfem_matrix *K, const void *handles);

@@ -1451,6 +1451,11 @@ static void spmv_apply(smfem_ctx *ctx, smfem_matrix *K, const double *x, double 
     }
 }
 
+void spmv_device(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y) {
+    solver_alloc(ctx, K);  // SpMV setup (row-triple check, stream blocks)
+    spmv_apply(ctx, K, x, y, false);
+}
+
 void spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y) {
     REQUIRE(ctx->nranks == 1, SMFEM_ERR_UNSUPPORTED, "spmv_host is single-GPU");
     REQUIRE(K->values_ready, SMFEM_ERR_INVALID, "matrix has no values yet");
