@@ -43,6 +43,10 @@ for ne in (5, 9):
     K.set_dirichlet_zplanes(0.002)
     q, it, rel = K.pcg_solve(rtol=1e-12, maxit=2000, warm_scale=2.0)
     assert it <= 25
+    K.use_multigrid(True)   # multigrid-preconditioned CG (odd ne coarsens too: 5 -> 3, 9 -> 5 -> 3)
+    qg, itg, relg = K.pcg_solve(rtol=1e-12, maxit=200)
+    assert np.linalg.norm(qg - 2 * r["q"]) <= 1e-9 * np.linalg.norm(qg) and itg < 60, itg
+    K.use_multigrid(False)
     K.free(); mesh.free()
 # general path (permuted ids), 2-D, scalar
 NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, 4, 3)
@@ -50,6 +54,8 @@ rng = np.random.default_rng(1)
 IDp = (rng.permutation(ID.size) + 1).reshape(ID.shape)
 Kg = sf.assemble_system(4, NL, IEN[rng.permutation(64)], 3, "Q1", 3, IDp, 40, 0.4)
 y = Kg.spmv(np.ones(Kg.shape[0]))
+assert Kg.mesh.colors()[0] >= 8   # coloured scatter (default on general meshes); the atomic one:
+os.environ["SMFEM_VALUES"] = "atomic"; Kg.assemble_values(40, 0.4); os.environ.pop("SMFEM_VALUES")
 NL2, IEN2, ID2, *_ = sf.meshgrid(0, 1, 0, 1, 0, 1, 6, 2)
 K2 = sf.assemble_system(6, NL2, IEN2, 2, "Q1", 2, ID2, 40, 0.4)
 Ks = sf.assemble_system(6, NL2, IEN2, 2)
