@@ -198,6 +198,15 @@ int smfem_set_dirichlet(smfem_ctx *ctx, smfem_matrix *K, const int64_t *dofs, co
 int smfem_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const double *rhs_extra,
                     double *q_out, int *iters_out, double *relres_out);
 
+/* Per-load-step post-processing of the example on the device (examples/vector3D.jl:325-329): for the listed nodes
+ * (1-based ids, e.g. BorderNodesList[1]) returns  NodeList_new[:, ids] = NodeList[:, ids] + motion[:, ids]  with
+ * motion = q[ID]' taken from K's last smfem_pcg_solve (K = NULL or not solved yet: motion = 0), and its projection
+ * back_project(NodeList_new[:, ids], CameraMatrix) (src/PostProcess.jl:131-152: R = [1 0 0; 0 0 1; 0 -1 0],
+ * t = [0; -0.5; 2], perspective divide, CameraMatrix' * p, rows 1:2).  CameraMatrix: 3 x 3 column-major.  Outputs are
+ * 3 x n and 2 x n column-major, either may be NULL.  One GPU.  The hull / spline / plotting steps of extract_borders
+ * and fit_curve remain host code (PostProcess.jl unchanged). */
+int smfem_project_nodes(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, const int64_t *node_ids, int64_t n,
+                        const double *CameraMatrix, double *nodes3d_out, double *nodes2d_out);
 /* Opt-in: the following smfem_pcg_solve calls on K use CG preconditioned by a geometric multigrid V-cycle instead of
  * Jacobi (examples/vector3D.jl:315-322 solved in ~20 instead of ~9 ne iterations).  Hex-lattice matrices on one GPU only
  * (SMFEM_ERR_UNSUPPORTED otherwise); `mesh` is K's mesh and must outlive the solves.  Coarse levels (ceil(ne/2), ... down to

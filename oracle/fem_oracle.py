@@ -630,6 +630,16 @@ def example_problem(ne, d=0.001, Young=40, nu=0.4, beta=100, inflate=True, liter
                 q_d=q_d, free=free, q=q)
 
 
+def back_project(NodeList, CameraMatrix):
+    """src/PostProcess.jl:131-152: camera-frame transform, perspective divide, CameraMatrix' * p, rows 1:2."""
+    R = np.array([[1.0, 0, 0], [0, 0, 1], [0, -1, 0]])  # :134
+    t = np.array([[0.0], [-0.5], [2.0]])                 # :135
+    NodeListTrans = R @ np.asarray(NodeList, dtype=np.float64) + t  # :137
+    NodeListNorm = NodeListTrans / NodeListTrans[2:3, :]            # :141-145
+    NodeListProj = np.asarray(CameraMatrix, dtype=np.float64).T @ NodeListNorm  # :147
+    return NodeListProj[0:2, :]                                      # :149
+
+
 def jitter_nodes(NodeList, ne, seed=1234, amp=0.2):
     """Robustness input: seeded jitter U(-amp*h, amp*h) of INTERIOR nodes of the unit
     cube lattice (boundary nodes fixed so the z == 0 / z == 1 Dirichlet tests still hit)."""

@@ -298,6 +298,16 @@ class SparseMatrixB200:
         call("smfem_pcg_solve", self.ctx.handle, self.handle, float(rtol), int(maxit), _pf(ex), _pf(q), C.byref(it), C.byref(rel))
         return q, int(it.value), float(rel.value)
 
+    def project_nodes(self, node_ids, CameraMatrix):
+        """examples/vector3D.jl:325-329 on the device: (NodeList_new[:, ids], back_project(NodeList_new[:, ids], CameraMatrix))
+        with the displacement of the last pcg_solve; node_ids are 1-based."""
+        ids = np.ascontiguousarray(node_ids, dtype=np.int64).ravel()
+        cam = np.asfortranarray(CameraMatrix, dtype=np.float64)
+        p3 = np.zeros((3, ids.size), order="F")
+        p2 = np.zeros((2, ids.size), order="F")
+        call("smfem_project_nodes", self.ctx.handle, self.mesh.handle, self.handle, _pi(ids), ids.size, _pf(cam), _pf(p3), _pf(p2))
+        return p3, p2
+
     def use_multigrid(self, enable=True):
         """Opt-in: later pcg_solve calls use CG preconditioned by a geometric multigrid V-cycle (hex lattice, one GPU)."""
         call("smfem_pcg_use_multigrid", self.ctx.handle, self.handle, self.mesh.handle if self.mesh is not None else None, int(bool(enable)))

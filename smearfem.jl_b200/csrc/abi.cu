@@ -907,6 +907,15 @@ int smfem_pcg_use_multigrid(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, i
     });
 }
 
+int smfem_project_nodes(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, const int64_t *node_ids, int64_t n,
+                        const double *CameraMatrix, double *nodes3d_out, double *nodes2d_out) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(mesh);
+        project_nodes(ctx, mesh, K, node_ids, n, CameraMatrix, nodes3d_out, nodes2d_out);
+    });
+}
+
 int smfem_pcg_set_warm_start(smfem_matrix *K, double scale) {
     return guarded([&] {
         NOTNULL(K);

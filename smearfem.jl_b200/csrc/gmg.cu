@@ -394,6 +394,7 @@ void gmg_refresh(smfem_ctx *ctx, Gmg *G, smfem_matrix *K) {
 }  // namespace
 
 void gmg_free(smfem_matrix *K) {
+    if (K->gmg && K->sol_x == static_cast<Gmg *>(K->gmg)->xs) K->sol_x = nullptr;
     gmg_destroy(static_cast<Gmg *>(K->gmg));
     K->gmg = nullptr;
 }
@@ -474,6 +475,7 @@ void gmg_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, cons
     CUDA_CHECK(cudaEventSynchronize(ctx->ev3));
     CUDA_CHECK(cudaEventElapsedTime(&K->last_ms, ctx->ev2, ctx->ev3));
     K->last_iters = it;
+    K->sol_x = G->xs;
     if (extra) dev_free(extra);
     if (iters) *iters = it;
     if (relres) *relres = bnorm2 > 0 ? std::sqrt(res2 / bnorm2) : 0.0;

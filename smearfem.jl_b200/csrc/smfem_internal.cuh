@@ -182,6 +182,7 @@ struct smfem_matrix {
     CommView comm;
     void *peer_maps[SMFEM_MAX_RANKS] = {nullptr};
     bool comm_connected = false;
+    const double *sol_x = nullptr;  // free part of the last solve's solution (device, nrows_l; q = q_d + x)
     double warm_scale = 0.0;  // next solve starts from warm_scale * (previous solution); reset after use
     int spmv_variant = 4;  // 4 = row-triple (default; falls back to 2), 2 = CSR-stream, 3 = CSR-stream via TMA, 1 = warp/row, 0 = warp/3 rows
     int32_t *blk_row = nullptr;  // CSR-stream row blocks
@@ -226,6 +227,8 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
                int *iters, double *relres);
 void spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y);
 void spmv_device(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y);  // device vectors: x ncols_l (ghost planes), y nrows_l
+void project_nodes(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, const int64_t *ids, int64_t n, const double *cam,
+                   double *nodes3d_out, double *nodes2d_out);  // postprocess.cu
 // gmg.cu: geometric-multigrid preconditioned CG (single GPU, hex lattice)
 void gmg_enable(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, bool enable);
 void gmg_free(smfem_matrix *K);

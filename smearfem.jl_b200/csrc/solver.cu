@@ -1612,6 +1612,7 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
     CUDA_CHECK(cudaEventSynchronize(ctx->ev3));
     CUDA_CHECK(cudaEventElapsedTime(&K->last_ms, ctx->ev2, ctx->ev3));
     K->last_iters = it;
+    K->sol_x = K->x;
     if (extra) dev_free(extra);
     if (iters) *iters = it;
     if (relres) *relres = bnorm2 > 0 ? std::sqrt(res2 / bnorm2) : 0.0;

@@ -397,6 +397,33 @@ def test_multigrid_pcg_matches_oracle(ne):
     assert rel(q3, q2) <= 1e-10 and it3 > it2
 
 
+def test_project_nodes_matches_postprocess_restatement():
+    """motion, NodeList_new and back_project of the border nodes on the device
+    (examples/vector3D.jl:325-329, src/PostProcess.jl:131-152) against the NumPy restatement."""
+    ne = 8
+    ctx = sf.context()
+    r = o.example_problem(ne)
+    NL, IEN, ID, top, btm, borders = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.inflate_sphere(NL, 0, 1, 0, 1)
+    CM = np.array([[8 * 2048 / 7.07, 0.0, 2048 / 2], [0.0, 8 * 1536 / 5.3, 1536 / 2], [0.0, 0.0, 1.0]]).T  # examples/vector3D.jl:281
+    ids = np.concatenate([np.asarray(b, dtype=np.int64).ravel() for b in borders])
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4).add_surface_mass(100.0)
+    p3, p2 = K.project_nodes(ids, CM)  # before any solve: motion = 0
+    assert np.array_equal(p3, NL[:, ids - 1]) and rel(p2, o.back_project(NL[:, ids - 1], CM)) <= 1e-15
+    K.set_dirichlet_zplanes(0.001)
+    for mg in (False, True):
+        K.use_multigrid(mg)
+        q, _, _ = K.pcg_solve(rtol=1e-13, maxit=5000)
+        motion = np.vstack([q[ID[:, c] - 1] for c in range(3)])  # examples/vector3D.jl:325
+        new = NL + motion
+        p3, p2 = K.project_nodes(ids, CM)
+        assert rel(p3, new[:, ids - 1]) <= 1e-15 and rel(p2, o.back_project(new[:, ids - 1], CM)) <= 1e-15
+        assert rel(p3, (NL + np.vstack([r["q"][ID[:, c] - 1] for c in range(3)]))[:, ids - 1]) <= 1e-10
+    with pytest.raises(sf.SmearFEMError):
+        K.project_nodes([0], CM)
+
+
 def test_manufactured_solution_general_dirichlet():
     """u* ~ N(0,1) (seed 4321), rhs = K̄u*; Dirichlet on an arbitrary dof set."""
     ne = 12

@@ -126,3 +126,16 @@ def test_setboundarycond_and_patch():
     rhs = -(K[fdof][:, ~fdof] @ u[~fdof])
     uf = np.linalg.solve(K[fdof][:, fdof].toarray(), rhs)
     assert np.abs(uf - u[fdof]).max() < 1e-13
+
+
+def test_back_project_known_answer():
+    """src/PostProcess.jl:131-152 with the example's CameraMatrix (examples/vector3D.jl:281): the origin maps to
+    (0, -0.5, 2) in the camera frame, i.e. to (cx, cy - fy/4) in the image; a point on the optical axis maps to (cx, cy)."""
+    fx, fy, cx, cy = 8 * 2048 / 7.07, 8 * 1536 / 5.3, 2048 / 2, 1536 / 2
+    CM = np.array([[fx, 0.0, cx], [0.0, fy, cy], [0.0, 0.0, 1.0]]).T
+    P = np.array([[0.0, 0.0, 0.0], [0.0, 1.0, 0.5], [0.25, 0.0, 0.5]]).T
+    out = o.back_project(P, CM)
+    assert out.shape == (2, 3)
+    assert np.allclose(out[:, 0], [cx, cy - fy / 4], rtol=0, atol=1e-12)
+    assert np.allclose(out[:, 1], [cx, cy], rtol=0, atol=1e-12)          # (0, 1, 0.5) -> camera (0, 0, 1)
+    assert np.allclose(out[:, 2], [cx + fx * 0.125, cy], rtol=0, atol=1e-12)  # (0.25, 0, 0.5) -> camera (0.25, 0, 2)
