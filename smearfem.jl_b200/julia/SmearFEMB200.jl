@@ -19,6 +19,7 @@ using SparseArrays, LinearAlgebra
 export assemble_system, gaussian_quadrature, basis_function, greet_fem
 export meshgrid, setboundaryCond, apply_boundary_conditions, inflate_sphere, solve
 export B200SparseMatrix, SurfaceMatrix
+export use_multigrid!, project_nodes, element_colors
 
 const LIB = get(ENV, "SMEARFEM_B200_LIB", joinpath(@__DIR__, "..", "libsmearfem_b200.so"))
 const Q1, Q2 = Cint(1), Cint(2)
@@ -218,6 +219,31 @@ function solve(K̄::B200SparseMatrix, q_d, C; rtol=1e-12, maxit=20000, warm_scal
                 (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}, Ptr{Cdouble}),
                 context().h, K̄.h, rtol, maxit, C_NULL, q, it, rel))
     return q
+end
+
+# ---- opt-in: CG preconditioned by a geometric multigrid V-cycle for the following solve(K̄, ...) calls (hex lattice, one GPU)
+function use_multigrid!(K̄::B200SparseMatrix, enable::Bool=true)
+    check(ccall((:smfem_pcg_use_multigrid, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint), context().h, K̄.h, K̄.mesh.h, enable))
+    return K̄
+end
+
+# ---- examples/vector3D.jl:325-329 on the device: NodeList_new[:, ids] and back_project(NodeList_new[:, ids], CameraMatrix)
+#      (src/PostProcess.jl:131-152) with the displacement of the last solve; feed the result to the unchanged
+#      extract_borders / fit_curve in place of their own back_project call
+function project_nodes(K̄::B200SparseMatrix, ids, CameraMatrix)
+    idv = Vector{Int64}(vec(ids)); cam = Matrix{Float64}(CameraMatrix)
+    p3 = zeros(3, length(idv)); p2 = zeros(2, length(idv))
+    check(ccall((:smfem_project_nodes, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                context().h, K̄.mesh.h, K̄.h, idv, length(idv), cam, p3, p2))
+    return p3, p2
+end
+
+# ---- element colouring of a general mesh (deterministic scatter): number of colours and elements per colour
+function element_colors(K::B200SparseMatrix)
+    nc = Ref{Cint}(0); sizes = zeros(Int64, 64)
+    check(ccall((:smfem_mesh_colors, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cint}, Ptr{Int64}), context().h, K.mesh.h, nc, sizes))
+    return Int(nc[]), sizes[1:max(nc[], 0)]
 end
 
 end # module
