@@ -261,7 +261,7 @@ def main():
                 "traffic": traffic.get("k_spmv_group3"), "GB/s_per_gpu": gbs4, "ms": ms4, "variant": 4,
                 "bytes_per_spmv_per_gpu": b_spmv, "nnz_per_gpu": info["nnz_local"], "variants": tried,
                 "note": "achieved = CSR-algorithmic bytes (12 B/nnz + 24 B/row) / time; the kernel reads colind once per row triple "
-                        "(9.33 B/nnz of real traffic, see `traffic`), and a read-only stream runs above the copy peak (DESIGN.md 4)"}
+                        "and interior lattice rows need no colind at all (8.3 B/nnz of real traffic, see `traffic`), and a read-only stream runs above the copy peak (DESIGN.md 4)"}
         K.set_spmv_variant(4)
         K.set_dirichlet_zplanes(0.001)
         sd.barrier(ctx)
