@@ -210,6 +210,18 @@ __global__ void k_update_xr(int64_t n, int64_t ghost, double alpha, const double
     x[t] += alpha * p[t + ghost];
     r[t] -= alpha * Ap[t];
 }
+// warm start (load stepping, examples/vector3D.jl:310-338: q is linear in d): x = w * x_prev, also as SpMV input
+__global__ void k_warm(int64_t n, int64_t ghost, double w, const double *__restrict__ prev, double *__restrict__ x, double *__restrict__ p) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double v = w * prev[t];
+    x[t] = v;
+    p[t + ghost] = v;
+}
+__global__ void k_sub_masked(int64_t n, const double *__restrict__ y, const uint8_t *__restrict__ fixed, double *__restrict__ r) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && !(fixed && fixed[t])) r[t] -= y[t];
+}
 __global__ void k_scale_copy(int64_t n, int64_t ghost, double s, const double *__restrict__ y, const double *__restrict__ dinv,
                              double *__restrict__ x) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -426,7 +438,8 @@ void gmg_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, cons
         K->gmg_dirty = false;
     }
     Gmg *G = static_cast<Gmg *>(K->gmg);
-    K->warm_scale = 0.0;
+    const double warm = K->sol_x ? K->warm_scale : 0.0;
+    K->warm_scale = 0.0;  // applies to one solve
     CUDA_CHECK(cudaEventRecord(ctx->ev2, ctx->stream));
     gmg_refresh(ctx, G, K);
     GmgLevel &V = G->lev[0];
@@ -440,10 +453,17 @@ void gmg_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, cons
     const bool bc = K->has_bc && K->qd;
     if (bc) spmv_device(ctx, K, K->qd, V.y);
     LAUNCH(ctx, k_rhs, g, NT, 0, n, (const double *)(bc ? V.y : nullptr), (const double *)extra, (const uint8_t *)V.fixed, G->r);
-    CUDA_CHECK(cudaMemsetAsync(G->xs, 0, 8 * n, ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(G->p, 0, 8 * V.ncols, ctx->stream));
     const double bnorm2 = dot(ctx, G, n, G->r, G->r);
     double res2 = bnorm2, rz_old = 0.0;
+    if (warm != 0.0) {  // x0 = warm * previous solution (of either solver), r0 = b - A x0
+        LAUNCH(ctx, k_warm, g, NT, 0, n, gh, warm, K->sol_x, G->xs, G->p);
+        spmv_device(ctx, K, G->p, V.y);
+        LAUNCH(ctx, k_sub_masked, g, NT, 0, n, (const double *)V.y, (const uint8_t *)V.fixed, G->r);
+        res2 = dot(ctx, G, n, G->r, G->r);
+    } else {
+        CUDA_CHECK(cudaMemsetAsync(G->xs, 0, 8 * n, ctx->stream));
+    }
     int it = 0;
     bool breakdown = false;
     if (bnorm2 > 0.0) {

@@ -392,6 +392,11 @@ def test_multigrid_pcg_matches_oracle(ne):
     K.set_dirichlet_zplanes(0.011)
     q2, it2, _ = K.pcg_solve(rtol=1e-13, maxit=500)
     assert rel(q2, 11 * r["q"]) <= 1e-9 and it2 <= 40
+    # warm-started load step (q is linear in d, examples/vector3D.jl:310-338): converged after a couple of iterations
+    K.set_dirichlet_zplanes(0.021)
+    q4, it4, _ = K.pcg_solve(rtol=1e-12, maxit=500, warm_scale=21.0 / 11.0)
+    assert rel(q4, 21 * r["q"]) <= 1e-9 and it4 <= 3, it4
+    K.set_dirichlet_zplanes(0.011)
     K.use_multigrid(False)
     q3, it3, _ = K.pcg_solve(rtol=1e-13, maxit=5000)
     assert rel(q3, q2) <= 1e-10 and it3 > it2
