@@ -466,11 +466,22 @@ void gmg_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, cons
     }
     int it = 0;
     bool breakdown = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
     if (bnorm2 > 0.0) {
         const double tol2 = rtol * rtol * bnorm2;
+        // the V-cycle is ~130 launches, most of them on tiny coarse levels: captured once, replayed per iteration
+        const int64_t l0 = ctx->launches;
+        CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        vcycle(ctx, G, 0);
+        const int64_t per_cycle = ctx->launches - l0;
+        CUDA_CHECK(cudaStreamEndCapture(ctx->stream, &graph));
+        ctx->launches = l0;  // captured, not launched; counted per replay below
+        CUDA_CHECK(cudaGraphInstantiate(&gexec, graph, 0));
         while (it < maxit && res2 > tol2) {
             // z = M^-1 r: one V-cycle on level 0, whose right-hand side buffer is r itself (result in V.x)
-            vcycle(ctx, G, 0);
+            CUDA_CHECK(cudaGraphLaunch(gexec, ctx->stream));
+            ctx->launches += per_cycle;
             const double rz = dot(ctx, G, n, G->r, V.x + gh);
             const double beta = it == 0 ? 0.0 : rz / rz_old;
             rz_old = rz;
@@ -487,6 +498,8 @@ void gmg_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, cons
             if (!(res2 == res2)) break;
         }
     }
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
     if (q_out) {
         LAUNCH(ctx, k_final, g, NT, 0, n, gh, (const double *)(bc ? K->qd : nullptr), (const double *)G->xs, (const uint8_t *)V.fixed, V.y);
         CUDA_CHECK(cudaMemcpyAsync(q_out, V.y, 8 * n, cudaMemcpyDeviceToHost, ctx->stream));
