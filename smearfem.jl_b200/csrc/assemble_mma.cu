@@ -366,6 +366,7 @@ bool values_assemble_mma(smfem_ctx *ctx, TileArgs &A, int nown) {
     if (v == "mma84") launch_mma<MTile<8, 4, 16>, 1>(ctx, A, nown);
     else if (v == "mma75") launch_mma<MTile<7, 5, 12>, 1>(ctx, A, nown);
     else if (v == "mma44") launch_mma<MTile<4, 4, 8>, 2>(ctx, A, nown);
+    else if (v.rfind("mma", 0) == 0) throw SmfemError(SMFEM_ERR_INVALID, "SMFEM_TILE=" + v + ": unknown DMMA tile (mma75, mma84, mma44)");
     else return false;
     return true;
 }

@@ -7,7 +7,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import smearfem_b200 as sf
 
-VARIANTS = sys.argv[2].split(",") if len(sys.argv) > 2 else ["mma84", "mma84w15", "mma75", "mma44", "mma44w9"]
+VARIANTS = sys.argv[2].split(",") if len(sys.argv) > 2 else ["mma75", "mma84", "mma44"]
 ne_big = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 ctx = sf.context()
 
