@@ -1537,6 +1537,8 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
         launch_spmv<0>(ctx, K, A, variant);
     } else {
         // warm start (load stepping, examples/vector3D.jl:310-338: q is linear in d):  r0 = extra - K (q_d + warm x_prev)
+        if (K->sol_x && K->sol_x != K->x)  // the previous solve was the multigrid one: its solution lives in its own buffer
+            CUDA_CHECK(cudaMemcpyAsync(K->x, K->sol_x, 8 * n, cudaMemcpyDeviceToDevice, ctx->stream));
         {  // b = extra - K q_d is still needed for the stopping test: K q_d -> r (r is rewritten by k_pcg_init)
             SpmvArgs A0 = make_spmv_args(K, K->qd, K->r);
             launch_spmv<0>(ctx, K, A0, variant);

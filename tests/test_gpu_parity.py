@@ -400,6 +400,13 @@ def test_multigrid_pcg_matches_oracle(ne):
     K.use_multigrid(False)
     q3, it3, _ = K.pcg_solve(rtol=1e-13, maxit=5000)
     assert rel(q3, q2) <= 1e-10 and it3 > it2
+    # Jacobi-PCG warm-started from a multigrid solution (the solvers keep their solutions in different buffers)
+    K.use_multigrid(True)
+    K.pcg_solve(rtol=1e-13, maxit=500)
+    K.use_multigrid(False)
+    K.set_dirichlet_zplanes(0.022)
+    q5, it5, _ = K.pcg_solve(rtol=1e-12, maxit=5000, warm_scale=2.0)
+    assert rel(q5, 22 * r["q"]) <= 1e-9 and it5 <= 25, it5
 
 
 def test_project_nodes_matches_postprocess_restatement():
