@@ -537,12 +537,15 @@ def setboundaryCond(NodeList, ne, ndim, FunctionClass, d, nDof=1):
     return q_d, Constraint(ndim * (ne + 1) ** ndim, free)
 
 
-def solve(K_bar, q_d, C_, rtol=1e-12, maxit=20000, return_info=False):
+def solve(K_bar, q_d, C_, rtol=1e-12, maxit=20000, return_info=False, multigrid=None):
     """examples/vector3D.jl:315-322: K_free = C'K̄C; q_f = K_free⁻¹ C'(-K̄ q_d); q = q_d + C q_f,
-    with the dense inverse replaced by Jacobi-PCG on the Dirichlet-masked device operator."""
+    with the dense inverse replaced by Jacobi-PCG on the Dirichlet-masked device operator.
+    multigrid=True/False switches K̄ to / from the multigrid-preconditioned CG first (hex lattice, one GPU); None leaves it."""
     q_d = np.asarray(q_d, dtype=np.float64).reshape(-1)
     fixed = np.setdiff1d(np.arange(1, C_.ndof + 1), C_.free)
     K_bar.set_dirichlet(fixed, q_d[fixed - 1])
+    if multigrid is not None:
+        K_bar.use_multigrid(bool(multigrid))
     q, it, rel = K_bar.pcg_solve(rtol=rtol, maxit=maxit)
     if return_info:
         return q, dict(iters=it, relres=rel)

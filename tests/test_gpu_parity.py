@@ -434,6 +434,12 @@ def test_project_nodes_matches_postprocess_restatement():
         assert rel(p3, (NL + np.vstack([r["q"][ID[:, c] - 1] for c in range(3)]))[:, ids - 1]) <= 1e-10
     with pytest.raises(sf.SmearFEMError):
         K.project_nodes([0], CM)
+    # the reference-shaped call chain with the multigrid switch (general Dirichlet list from setboundaryCond's C)
+    Kh = sf.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4)
+    K_bar = Kh + 100 * sf.apply_boundary_conditions(ne, NL, IEN, top, btm, 3, "Q1", ID)
+    q_d, C = sf.setboundaryCond(NL, ne, 3, "Q1", 0.001, 3)
+    qm, info = sf.solve(K_bar, q_d, C, rtol=1e-13, return_info=True, multigrid=True)
+    assert rel(qm, r["q"]) <= TOL and info["iters"] <= 40
 
 
 def test_manufactured_solution_general_dirichlet():
