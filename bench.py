@@ -109,6 +109,46 @@ def cpu_port_rate(ne_cpu, threads):
     return ne_cpu**3 / dt, dt
 
 
+def cpu_pcg_baseline(ne_cpu, iters=30):
+    """CPU solve baseline beside the GPU one - Jacobi-PCG iterations with SciPy's CSR SpMV (one thread) on the
+    example problem at ne_cpu (the reference's own dense inverse, examples/vector3D.jl:318, is O(n^3) and not timeable here).
+    K comes from the oracle's C port: nothing on this leg touches the GPU library."""
+    import scipy.sparse as sp
+    from oracle import c_oracle, fem_oracle as o
+
+    NL, IEN, ID, top, btm, _ = o.meshgrid(0, 1, 0, 1, 0, 1, ne_cpu, 3)
+    o.inflate_sphere(NL, 0, 1, 0, 1)
+    K = c_oracle.assemble_system(ne_cpu, NL, IEN, 3, "Q1", 3, ID, 40, 0.4, nthreads=c_oracle.max_threads())
+    A = sp.csc_matrix((K.nzval, K.rowval - 1, K.colptr - 1), shape=(K.m, K.n)).tocsr()  # K is symmetric: CSC of K = CSR of K'
+    n1 = ne_cpu + 1
+    kz = np.arange(n1**3) // (n1 * n1)
+    fixed = np.zeros(3 * n1**3, bool)
+    fixed[3 * np.where((kz == 0) | (kz == ne_cpu))[0] + 2] = True
+    qd = np.zeros(3 * n1**3)
+    qd[3 * np.where(kz == ne_cpu)[0] + 2] = -0.001
+    dinv = np.where(fixed, 0.0, 1.0 / A.diagonal())
+    b = np.where(fixed, 0.0, -(A @ qd))
+    x = np.zeros_like(b)
+    r = b.copy()
+    z = dinv * r
+    p = z.copy()
+    rz = r @ z
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        Ap = np.where(fixed, 0.0, A @ p)
+        alpha = rz / (p @ Ap)
+        x += alpha * p
+        r -= alpha * Ap
+        z = dinv * r
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    dt = (time.perf_counter() - t0) / iters
+    bytes_spmv = 12 * A.nnz + 24 * A.shape[0]
+    return {"ms_per_iter": dt * 1e3, "spmv_GB/s": bytes_spmv / dt / 1e9, "cores": 1, "kind": "port", "iters_timed": iters,
+            "sample": f"{ne_cpu}^3, Jacobi-PCG iterations with SciPy CSR SpMV (K without the surface term: same pattern and cost), one thread"}
+
+
 def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -365,6 +405,10 @@ def main():
         rate, dt = cpu_port_rate(ne_cpu, th)
         cpu = {"value": rate, "unit": UNIT, "cores": th, "kind": "port", "seconds": dt,
                "sample": f"{ne_cpu}^3 inflated hex elements, C restatement of src/fem.jl:135-256 + sparse() (Julia not installed)"}
+        try:
+            cpu["solve"] = cpu_pcg_baseline(ne_cpu)
+        except Exception as exc:  # an optional figure must not take the line down
+            cpu["solve"] = {"error": str(exc)[:200]}
 
     if rank == 0:
         line = {
