@@ -525,8 +525,13 @@ def test_full_size_100_properties():
     top = NL[2] == 1.0
     u[2::3][btm] = 0.0
     u[2::3][top] = -0.001
-    q, it, relres = K.pcg_solve(rtol=1e-12, maxit=8000, rhs_extra=K.spmv(u))
+    rhs = K.spmv(u)
+    q, it, relres = K.pcg_solve(rtol=1e-12, maxit=8000, rhs_extra=rhs)
     assert relres <= 1e-12 and rel(q, u) <= 1e-8
+    # the same manufactured problem through the multigrid-preconditioned CG (6 levels: 100 -> 50 -> 25 -> 13 -> 7 -> 4)
+    K.use_multigrid(True)
+    qg, itg, relg = K.pcg_solve(rtol=1e-12, maxit=200, rhs_extra=rhs)
+    assert relg <= 1e-12 and rel(qg, u) <= 1e-8 and itg <= 60 and itg < it / 10, (itg, it)
 
 
 def test_load_stepping_warm_start():
