@@ -166,7 +166,8 @@ int smfem_matrix_info(smfem_matrix *K, int64_t *m, int64_t *n, int64_t *nnz, int
  * when nranks == 1).  colptr: nrows_local+1 entries, 1-based, relative to this slab's first stored
  * entry; rowval: global 1-based row ids; nzval: K[row, col] (true transpose of the device CSR).
  * which: 0 = K as assembled (+ anything added in place), 1 = the surface matrix b of
- * smfem_surface_mass on K's pattern. */
+ * smfem_surface_mass on K's pattern, 2 = K's values exactly as stored (the device's row slab read as columns, i.e. K'
+ * without the transposing search: what which = 0 returns when nranks > 1; for bit-comparisons of 1-GPU and N-GPU runs). */
 int smfem_matrix_export_csc(smfem_ctx *ctx, smfem_matrix *K, int which, int64_t *colptr, int64_t *rowval,
                             double *nzval);
 int smfem_matrix_diag(smfem_ctx *ctx, smfem_matrix *K, double *diag_local);

@@ -630,6 +630,25 @@ def example_problem(ne, d=0.001, Young=40, nu=0.4, beta=100, inflate=True, liter
                 q_d=q_d, free=free, q=q)
 
 
+def plane_stress_problem(ne, d=0.001, Young=40, nu=0.4):
+    """BASELINE config C1: 2-D Q4 plane stress on the unit square.  The reference has no executable 2-D
+    boundary-condition / solve code (setboundaryCond indexes coord[3]; apply_boundary_conditions' 2-D branch is broken), so
+    the conditions are the survey's: clamp the bottom edge y = 0 (u_x = u_y = 0), prescribe u_y = -d on the top edge
+    y = 1, and solve K[free,free] q_f = -(K q_d)[free] with the idiom of examples/vector3D.jl:315-322."""
+    NodeList, IEN, ID, *_ = meshgrid(0, 1, 0, 1, 0, 1, ne, 2)
+    K = assemble_system_literal(ne, NodeList, IEN, 2, "Q1", 2, ID, Young, nu)
+    ndof = 2 * (ne + 1) ** 2
+    y = NodeList[1]
+    nodes = np.arange(1, y.shape[0] + 1)
+    btm, top = nodes[y == 0.0], nodes[y == 1.0]
+    q_d = np.zeros((ndof, 1))
+    q_d[2 * top - 1, 0] = -d                                    # u_y of the top edge (ID[m, 2] = 2 m)
+    fixed = np.concatenate([2 * btm - 1, 2 * btm, 2 * top])     # 1-based dof ids: u_x, u_y bottom; u_y top
+    free = np.setdiff1d(np.arange(1, ndof + 1), fixed)
+    q = solve_reference(K, q_d, free)
+    return dict(NodeList=NodeList, IEN=IEN, ID=ID, K=K, q_d=q_d, fixed=np.sort(fixed), free=free, q=q)
+
+
 def back_project(NodeList, CameraMatrix):
     """src/PostProcess.jl:131-152: camera-frame transform, perspective divide, CameraMatrix' * p, rows 1:2."""
     R = np.array([[1.0, 0, 0], [0, 0, 1], [0, -1, 0]])  # :134

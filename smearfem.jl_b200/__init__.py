@@ -262,11 +262,16 @@ class SparseMatrixB200:
         return d
 
     # -- K_bar = K + beta*b  (examples/vector3D.jl:308), evaluated in place on the device ----------
-    def add_surface_mass(self, beta, IEN_top=None, IEN_btm=None, keep_b=False):
+    def add_surface_mass(self, beta, IEN_top=None, IEN_btm=None, keep_b=False, mesh=None):
+        """K += beta * b in place.  mesh: the mesh whose coordinates b is integrated over (default: K's own);
+        apply_boundary_conditions passes the NodeList IT was given (examples/vector3D.jl:306), which need not be K's."""
         t = None if IEN_top is None else np.asfortranarray(IEN_top, dtype=np.int64)
         b = None if IEN_btm is None else np.asfortranarray(IEN_btm, dtype=np.int64)
         nf = 0 if t is None else t.shape[0]
-        call("smfem_surface_mass", self.ctx.handle, self.handle, self.mesh.handle, _pi(t), _pi(b), nf, float(beta), int(keep_b))
+        m = self.mesh if mesh is None else mesh
+        if m is not self.mesh and m.info()["structured"] != self.mesh.info()["structured"]:
+            raise SmearFEMError(_lib.ERR_INVALID, "apply_boundary_conditions: IEN / ID describe a different kind of mesh than K's")
+        call("smfem_surface_mass", self.ctx.handle, self.handle, m.handle, _pi(t), _pi(b), nf, float(beta), int(keep_b))
         return self
 
     def __add__(self, other):
@@ -366,12 +371,13 @@ class SurfaceMatrix:
     __mul__ = __rmul__
 
     def _add_into(self, K):
-        return K.add_surface_mass(self.beta, self.IEN_top, self.IEN_btm)
+        # b is integrated over the NodeList apply_boundary_conditions received (self.mesh), not over K's mesh
+        return K.add_surface_mass(self.beta, self.IEN_top, self.IEN_btm, mesh=self.mesh)
 
     def to_csc(self):
         """b as SparseMatrixCSC parts with ITS OWN pattern (pairs of dofs of nodes sharing a face)."""
         K = SparseMatrixB200.pattern(self.ctx, self.mesh, 3, 3).assemble_values(0.0, 0.25)
-        K.add_surface_mass(0.0, self.IEN_top, self.IEN_btm, keep_b=True)
+        K.add_surface_mass(0.0, self.IEN_top, self.IEN_btm, keep_b=True)  # K.mesh is self.mesh here
         colptr, rowval, nzval = K.to_csc(which=1)
         K.free()
         # structural entries of b: (dof of node a, dof of node b) with a, b in a common face

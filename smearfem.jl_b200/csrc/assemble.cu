@@ -945,13 +945,13 @@ __global__ void k_export_csc(int64_t nrows, int64_t ghost_cols, int64_t col_off_
 
 void export_csc(smfem_ctx *ctx, smfem_matrix *K, int which, int64_t *colptr, int64_t *rowval, double *nzval) {
     const double *src = which == 1 ? K->bval : K->val;
-    REQUIRE(which == 0 || which == 1, SMFEM_ERR_INVALID, "export: which must be 0 (K) or 1 (b)");
-    REQUIRE(which == 0 || K->bval, SMFEM_ERR_INVALID, "export: surface matrix b was not kept");
+    REQUIRE(which == 0 || which == 1 || which == 2, SMFEM_ERR_INVALID, "export: which must be 0 (K), 1 (b) or 2 (K, stored order)");
+    REQUIRE(which != 1 || K->bval, SMFEM_ERR_INVALID, "export: surface matrix b was not kept");
     int64_t *d_colptr = dev_alloc<int64_t>(K->nrows_l + 1), *d_rowval = dev_alloc<int64_t>(K->nnz_l);
     double *d_nz = (nzval && src) ? dev_alloc<double>(K->nnz_l) : nullptr;
     int64_t col_off_g = K->row0 - K->ghost_cols;
     LAUNCH(ctx, k_export_csc, (unsigned)(((K->nrows_l + 1) * 32 + 255) / 256), 256, 0, K->nrows_l, K->ghost_cols,
-           col_off_g, K->rowptr, K->colind, d_nz ? src : (const double *)nullptr, ctx->nranks == 1 ? 1 : 0, d_colptr,
+           col_off_g, K->rowptr, K->colind, d_nz ? src : (const double *)nullptr, (ctx->nranks == 1 && which != 2) ? 1 : 0, d_colptr,
            d_rowval, d_nz);
     if (colptr) CUDA_CHECK(cudaMemcpyAsync(colptr, d_colptr, 8 * (K->nrows_l + 1), cudaMemcpyDeviceToHost, ctx->stream));
     if (rowval) CUDA_CHECK(cudaMemcpyAsync(rowval, d_rowval, 8 * K->nnz_l, cudaMemcpyDeviceToHost, ctx->stream));

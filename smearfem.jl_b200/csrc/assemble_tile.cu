@@ -149,64 +149,6 @@ __device__ __forceinline__ void phase1(const TileArgs &A, const double *s_gp, co
 }
 
 
-// column indices of the <= 4 nodes (jx0.., jy, k) of a warp in CSR order -> Ri[0 .. run_len)
-__device__ __forceinline__ void write_colind_run(const TileArgs &A, int32_t *Ri, bool row_ok, int jx0, int jy, int k, int cy, int cz,
-                                                 int dx, int dy, int dz, int lane) {
-    const Lattice &L = A.L;
-    int off = 0;
-    for (int jn = 0; jn < 4; ++jn) {
-        const int jx = jx0 + jn;
-        if (!(row_ok && jx < L.n1)) break;
-        const int cx = 1 + (jx > 0) + (jx < L.n1 - 1);
-        const int TR = 3 * cx * cy * cz;
-        const int nx = jx + dx, ny = jy + dy, nz = k + dz;
-        if (lane < 27 && nx >= 0 && ny >= 0 && nz >= 0 && nx < L.n1 && ny < L.n1 && nz < L.n1) {
-            const int rank = ((dz + (k > 0)) * cy + (dy + (jy > 0))) * cx + (dx + (jx > 0));
-            const int32_t col = (int32_t)(L.lnode(nx, ny, nz) * 3);
-            int32_t *dst = Ri + off + 3 * rank;
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) dst[c * TR + j] = col + j;
-        }
-        off += 3 * TR;
-    }
-}
-
-// ... and out to K.colind[run_base .. run_base + run_len) with one TMA bulk store (16-byte aligned middle; <= 3 + 3
-// head / tail entries by plain stores).  Returns after the bulk copy has finished READING the region.
-template <bool DEFER>
-__device__ __forceinline__ void emit_colind_run(const TileArgs &A, int32_t *Ri, int64_t run_base, int run_len, bool row_ok, int jx0,
-                                                int jy, int k, int cy, int cz, int dx, int dy, int dz, int lane) {
-    const int par4 = (int)(run_base & 3);  // the region mirrors the 16-byte phase of the destination
-    if (A.skip & 16) run_base = par4 + 1024 * (threadIdx.x >> 5);  // ablation: same stores, collapsed onto a cache-resident window
-    // DEFER: Ri is a buffer of its own; the bulk store of the previous plane has had a whole plane of compute to drain
-    if (DEFER && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    __syncwarp();
-    write_colind_run(A, Ri + par4, row_ok, jx0, jy, k, cy, cz, dx, dy, dz, lane);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    const int64_t a0 = (run_base + 3) & ~(int64_t)3, a1 = (run_base + run_len) & ~(int64_t)3;
-    if (a1 > a0) {
-        if (lane == 0) {
-            const unsigned src = (unsigned)__cvta_generic_to_shared(Ri + par4 + (a0 - run_base));
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(A.colind + a0), "r"(src),
-                         "r"((unsigned)((a1 - a0) * 4))
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            if (!DEFER) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        } else if (lane < 4) {  // unaligned head (lanes 1..3) ...
-            const int64_t t = run_base + (lane - 1);
-            if (t < a0) A.colind[t] = Ri[par4 + (lane - 1)];
-        } else if (lane < 7) {  // ... and tail (lanes 4..6)
-            const int64_t t = a1 + (lane - 4);
-            if (t < run_base + run_len) A.colind[t] = Ri[par4 + (t - run_base)];
-        }
-    } else {
-        for (int t = lane; t < run_len; t += 32) A.colind[run_base + t] = Ri[par4 + t];
-    }
-}
-
 template <class T, int MINB, int OUT>
 __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile(const __grid_constant__ TileArgs A) {
     constexpr int TX = T::TX, TY = T::TY, NTH = T::NTH, NEL = T::NELP /* ring stride */, EX = T::EX, LAYER = T::LAYER;
@@ -597,6 +539,7 @@ void tile_fill_args(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material 
 void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind, const int *ready) {
     TileArgs A;
     tile_fill_args(ctx, mesh, K, mat, write_colind, ready, A);
+    if (values_assemble_tile2(ctx, A, A.L.nown())) return;  // layer-march kernel (assemble_tile2.cu)
     if (values_assemble_mma(ctx, A, A.L.nown())) return;  // DMMA kernel (assemble_mma.cu), selected by SMFEM_TILE=mma*
     const char *e = std::getenv("SMFEM_TILE");
     const bool big = e && std::string(e) == "8x4";  // 256 threads, 1 CTA/SM; default 4x4: 128 threads, 2 CTAs/SM

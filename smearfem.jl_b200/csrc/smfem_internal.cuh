@@ -126,8 +126,11 @@ struct smfem_mesh {
 
 // all-reduce mailboxes + halo flags, at the start of each rank's peer window
 struct CommHeader {
-    double mbox[2][SMFEM_MAX_RANKS][4];
-    unsigned long long mflag[2][SMFEM_MAX_RANKS];
+    // slot = seq & 3: the (r'z, r'r) sums carry even sequence numbers, p'Ap the odd ones, so each kind alternates between two
+    // slots.  A rank publishes seq + 4 only after it has fetched seq + 2 from every rank, and every rank publishes seq + 2 only
+    // after all its reads of seq (stream order) - also across consecutive solves, which need no host barrier.
+    double mbox[4][SMFEM_MAX_RANKS][4];
+    unsigned long long mflag[4][SMFEM_MAX_RANKS];
     unsigned long long hflag[2];  // [0]: ghost_lo filled up to seq, [1]: ghost_hi
     unsigned long long pad[6];
 };
@@ -137,6 +140,10 @@ struct PcgScalars {
     unsigned long long it;      // global iteration counter (never reset: sequence for flags)
     unsigned long long red;     // global all-reduce sequence counter
     unsigned int ticketA, ticketB, ticketC, breakdown;
+    // per-solve control, written by k_pcg_init: the convergence test runs on the device (every rank sees bitwise identical
+    // sums, so all ranks stop in the same iteration); once `done` is set the remaining kernels of a graph replay are no-ops
+    double rtol2, rr_true;
+    unsigned int iters, maxit, done, pad_;
 };
 
 struct CommView {  // passed by value to kernels
@@ -184,6 +191,10 @@ struct smfem_matrix {
     bool comm_connected = false;
     const double *sol_x = nullptr;  // free part of the last solve's solution (device, nrows_l; q = q_d + x)
     double warm_scale = 0.0;  // next solve starts from warm_scale * (previous solution); reset after use
+    void *pcg_graph = nullptr;  // cudaGraphExec_t of PCG_CHUNK iterations, instantiated once per (matrix, SpMV variant)
+    int pcg_graph_variant = -1;
+    int64_t pcg_graph_launches = 0;
+    double last_relres_rec = 0, last_relres_true = 0;
     int spmv_variant = 4;  // 4 = row-triple (default; falls back to 2), 2 = CSR-stream, 3 = CSR-stream via TMA, 1 = warp/row, 0 = warp/3 rows
     int32_t *blk_row = nullptr;  // CSR-stream row blocks
     int nblk = 0, max_rowlen = 0, ctas_per_sm = 4;

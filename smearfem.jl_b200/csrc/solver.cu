@@ -59,11 +59,11 @@ __device__ __forceinline__ double block_sum(double v, double *smem /* NT/32 doub
 // All-reduce of up to 4 doubles through the peer windows: every rank stores its partial into slot
 // [seq&1][rank] of EVERY rank's mailbox (direct NVLink stores), then releases a flag; readers spin
 // on their own (local) mailbox and add the partials in rank order, so all ranks obtain bitwise
-// identical sums.  Two slots suffice because sequence s+2 can only be published after s+1 has been
-// read from all ranks (see DESIGN.md "Multi-GPU").
+// identical sums.  Four slots (seq & 3), see CommHeader: no host barrier is needed anywhere, not even
+// between consecutive solves.
 // ------------------------------------------------------------------------------------------------
 __device__ void allreduce_publish(const CommView &cv, unsigned long long seq, int nv, const double *vals) {
-    int slot = (int)(seq & 1ull);
+    int slot = (int)(seq & 3ull);
     for (int q = 0; q < cv.nranks; ++q) {
         CommHeader *h = cv.peer[q];
         for (int v = 0; v < nv; ++v) h->mbox[slot][cv.rank][v] = vals[v];
@@ -73,7 +73,7 @@ __device__ void allreduce_publish(const CommView &cv, unsigned long long seq, in
 }
 
 __device__ void allreduce_fetch(const CommView &cv, unsigned long long seq, int nv, double *out) {
-    int slot = (int)(seq & 1ull);
+    int slot = (int)(seq & 3ull);
     for (int v = 0; v < nv; ++v) out[v] = 0.0;
     for (int q = 0; q < cv.nranks; ++q) {
         while (ld_acquire_sys(&cv.self->mflag[slot][q]) != seq) {
@@ -172,10 +172,18 @@ struct SpmvArgs {
     int64_t rot;  // warp rotation so that boundary-plane rows run last
     int64_t row_begin, row_end;  // k_spmv_group: rows [row_begin, row_end) (multiples of the group size)
     int lat_n1;  // > 0: K is the hex-lattice matrix (nDof 3): the 81 columns of an interior node's rows are closed-form
+    int check_done;                 // inside the PCG graph: return at once when scal->done is set
+    unsigned long long halo_need;   // > 0: wait for this halo sequence number instead of scal->it + 1 (bench_spmv)
 };
+#define SPMV_DONE_CHECK(A)                                 \
+    do {                                                   \
+        if ((A).check_done && (A).scal->done) return;      \
+    } while (0)
+#define SPMV_HALO_NEED(A) ((A).halo_need ? (A).halo_need : (A).scal->it + 1)
 
 template <int RPW, int MODE>
 __global__ void __launch_bounds__(256) k_spmv(SpmvArgs A) {
+    SPMV_DONE_CHECK(A);
     constexpr bool MASK = MODE & 1, DOT = MODE & 2, HALO = MODE & 4;
     __shared__ double s_red[8];
     __shared__ bool s_last;
@@ -189,7 +197,7 @@ __global__ void __launch_bounds__(256) k_spmv(SpmvArgs A) {
         const int nr = (int)((A.nrows - r0) < RPW ? (A.nrows - r0) : RPW);
         if (HALO && A.cv.nranks > 1) {
             // rows of the first / last owned plane read ghost planes written by the neighbours
-            const unsigned long long need = A.scal->it + 1;
+            const unsigned long long need = SPMV_HALO_NEED(A);
             bool lo = (A.cv.rank > 0) && (r0 < A.cv.plane_dofs);
             bool hi = (A.cv.rank < A.cv.nranks - 1) && (r0 + nr > A.nrows - A.cv.plane_dofs);
             if (lane == 0) {
@@ -306,6 +314,7 @@ __device__ __forceinline__ int4 ld_stream_v4s32(const int32_t *p) {
 
 template <int MODE>
 __global__ void __launch_bounds__(SPMV_NT, 4) k_spmv_stream(SpmvArgs A, const int32_t *__restrict__ blk_row, int nblk) {
+    SPMV_DONE_CHECK(A);
     constexpr bool MASK = MODE & 1, DOT = MODE & 2, HALO = MODE & 4;
     // 128-bit streaming loads: a plain read stream with 8 B/lane loads tops out at 4.84 TB/s on B200, with
     // 16 B/lane at 6.86 TB/s (tools/microbench/peaks.cu).  A block [p0, p0+n) is read as aligned quads starting at
@@ -376,7 +385,7 @@ __global__ void __launch_bounds__(SPMV_NT, 4) k_spmv_stream(SpmvArgs A, const in
             const bool lo = (A.cv.rank > 0) && (R0 < A.cv.plane_dofs);
             const bool hi = (A.cv.rank < A.cv.nranks - 1) && (R1 > A.nrows - A.cv.plane_dofs);
             if ((lo || hi) && tid == 0) {
-                const unsigned long long need = A.scal->it + 1;
+                const unsigned long long need = SPMV_HALO_NEED(A);
                 if (lo)
                     while (ld_acquire_sys(&A.cv.self->hflag[0]) < need) {
                     }
@@ -522,6 +531,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 
 template <int MODE>
 __global__ void __launch_bounds__(TMA_NT, 2) k_spmv_tma(SpmvArgs A, const int32_t *__restrict__ blk_row, int nblk) {
+    SPMV_DONE_CHECK(A);
     constexpr bool MASK = MODE & 1, DOT = MODE & 2, HALO = MODE & 4;
     constexpr int PER = (SPMV_CH + SPMV_SLACK + SPMV_NT - 1) / SPMV_NT;  // 9
     constexpr int RPT = SPMV_MAXROWS / SPMV_NT;
@@ -608,7 +618,7 @@ __global__ void __launch_bounds__(TMA_NT, 2) k_spmv_tma(SpmvArgs A, const int32_
             const bool lo = (A.cv.rank > 0) && (R0 < A.cv.plane_dofs);
             const bool hi = (A.cv.rank < A.cv.nranks - 1) && (R1 > A.nrows - A.cv.plane_dofs);
             if ((lo || hi) && tid == 0) {
-                const unsigned long long need = A.scal->it + 1;
+                const unsigned long long need = SPMV_HALO_NEED(A);
                 if (lo)
                     while (ld_acquire_sys(&A.cv.self->hflag[0]) < need) {
                     }
@@ -742,6 +752,7 @@ __global__ void k_check_group3(int64_t ngroups, const int64_t *__restrict__ rowp
 
 template <int MODE, int G>
 __global__ void __launch_bounds__(256, 3) k_spmv_group(SpmvArgs A) {
+    SPMV_DONE_CHECK(A);
     // G = 3: row triples sharing one column pattern (k_check_group3);  G = 1: any CSR matrix, one row per warp step.
     constexpr bool MASK = MODE & 1, DOT = MODE & 2, HALO = MODE & 4;
     __shared__ double s_red[8];
@@ -803,7 +814,7 @@ __global__ void __launch_bounds__(256, 3) k_spmv_group(SpmvArgs A) {
             const bool hi = (A.cv.rank < A.cv.nranks - 1) && (r0 + G > A.nrows - A.cv.plane_dofs);
             if (lo || hi) {
                 if (lane == 0) {
-                    const unsigned long long need = A.scal->it + 1;
+                    const unsigned long long need = SPMV_HALO_NEED(A);
                     if (lo)
                         while (ld_acquire_sys(&A.cv.self->hflag[0]) < need) {
                         }
@@ -999,6 +1010,8 @@ static SpmvArgs make_spmv_args(smfem_matrix *K, const double *x, double *y) {
     A.rot = 0;
     A.row_begin = 0;
     A.row_end = K->nrows_l;
+    A.check_done = 0;
+    A.halo_need = 0;
     static const bool lattice_cols = [] {
         const char *e = std::getenv("SMFEM_SPMV_LATTICE");
         return !(e && e[0] == '0');
@@ -1060,21 +1073,33 @@ __global__ void __launch_bounds__(VEC_NT)
 k_pcg_update_p(int64_t n, int64_t ghost_cols, const double *__restrict__ r, const double *__restrict__ dinv,
                double *__restrict__ p, PcgScalars *scal, CommView cv, unsigned long long it_start_unused) {
     __shared__ double s_beta;
-    __shared__ bool s_last;
+    __shared__ bool s_last, s_stop;
+    if (scal->done) return;  // set by an earlier launch: the rest of the graph replay is a no-op
     const unsigned long long it = scal->it;
     if (threadIdx.x == 0) {
-        double v[2];
-        allreduce_fetch(cv, 2ull * it, 2, v);  // (rz_k, rr_k) published by the previous C / init
+        const bool first = scal->spare != 0.0;  // spare != 0 marks the first iteration of a solve
+        double v[3];
+        allreduce_fetch(cv, 2ull * it, first ? 3 : 2, v);  // (rz_k, rr_k [, ||b||^2]) published by the previous C / init
+        const double bn2 = first ? v[2] : scal->bnorm2;
+        // the stopping test: every CTA of every rank evaluates it on bitwise identical numbers
+        const bool stop = !(v[1] > scal->rtol2 * bn2) || scal->iters >= scal->maxit || scal->breakdown != 0;
         double rz_prev = scal->rzs[(it + 1ull) & 1ull];  // parity slots: [it-1]
-        double beta = (scal->spare != 0.0) ? 0.0 : v[0] / rz_prev;  // spare != 0 marks the first iteration
+        double beta = first ? 0.0 : v[0] / rz_prev;
         s_beta = beta;
+        s_stop = stop;
         if (blockIdx.x == 0) {
             scal->rzs[it & 1ull] = v[0];
             scal->rr = v[1];
+            if (first) scal->bnorm2 = v[2];
             scal->beta = beta;
+            if (stop) {
+                __threadfence();
+                scal->done = 1;
+            }
         }
     }
     __syncthreads();
+    if (s_stop) return;
     const double beta = s_beta;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     double *po = p + ghost_cols;
@@ -1112,6 +1137,7 @@ k_pcg_update_xr(int64_t n, int64_t ghost_cols, const double *__restrict__ p, con
     __shared__ double s_alpha;
     __shared__ double s_red[VEC_NT / 32];
     __shared__ bool s_last;
+    if (scal->done) return;
     const unsigned long long it = scal->it;
     if (threadIdx.x == 0) {
         double pAp;
@@ -1162,6 +1188,7 @@ k_pcg_update_xr(int64_t n, int64_t ghost_cols, const double *__restrict__ p, con
         if (threadIdx.x == 0) {
             scal->ticketC = 0;
             scal->spare = 0.0;  // first-iteration marker cleared
+            scal->iters += 1;
             double v[2] = {t1, t2};
             allreduce_publish(cv, 2ull * it + 2ull, 2, v);
             __threadfence();
@@ -1175,7 +1202,7 @@ __global__ void __launch_bounds__(VEC_NT)
 k_pcg_init(int64_t n, const double *__restrict__ Kqd, const double *__restrict__ Kq0, const double *__restrict__ extra,
            const double *__restrict__ diag,
            const uint8_t *__restrict__ fixed, double *__restrict__ x, double *__restrict__ r, double *__restrict__ dinv,
-           double *__restrict__ partials, PcgScalars *scal, CommView cv, double warm) {
+           double *__restrict__ partials, PcgScalars *scal, CommView cv, double warm, double rtol2, unsigned maxit) {
     __shared__ double s_red[VEC_NT / 32];
     __shared__ bool s_last;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -1223,6 +1250,10 @@ k_pcg_init(int64_t n, const double *__restrict__ Kqd, const double *__restrict__
             scal->ticketC = 0;
             scal->spare = 1.0;  // marks "first iteration": beta = 0
             scal->breakdown = 0;
+            scal->rtol2 = rtol2;
+            scal->maxit = maxit;
+            scal->iters = 0;
+            scal->done = 0;
             double v[3] = {t1, t2, t3};
             allreduce_publish(cv, 2ull * it + 2ull, 3, v);
             __threadfence();
@@ -1248,6 +1279,7 @@ k_pcg_dot(int64_t n, int64_t ghost_cols, const double *__restrict__ p, const dou
           PcgScalars *scal, CommView cv) {
     __shared__ double s_red[VEC_NT / 32];
     __shared__ bool s_last;
+    if (scal->done) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const double *po = p + ghost_cols;
     double acc = 0.0;
@@ -1279,6 +1311,47 @@ __global__ void k_pcg_fetch(PcgScalars *scal, CommView cv, double *out3) {
     out3[0] = v[0];
     out3[1] = v[1];
     out3[2] = v[2];
+}
+
+// true residual at exit:  sum over the free rows of (extra - K (q_d + x))^2  ->  published as sequence 2 it + 1 (the p'Ap
+// slot of the iteration that never ran)
+__global__ void __launch_bounds__(VEC_NT)
+k_true_resid(int64_t n, const double *__restrict__ Kq, const double *__restrict__ extra, const uint8_t *__restrict__ fixed,
+             double *__restrict__ partials, PcgScalars *scal, CommView cv) {
+    __shared__ double s_red[VEC_NT / 32];
+    __shared__ bool s_last;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double rv = fixed[i] ? 0.0 : (extra ? extra[i] : 0.0) - Kq[i];
+        acc += rv * rv;
+    }
+    double s1 = block_sum<VEC_NT>(acc, s_red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = s1;
+        __threadfence();
+        unsigned t = atomicAdd(&scal->ticketB, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double v = 0.0;
+        for (int64_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) v += ld_volatile_f64(partials + i);
+        double tot = block_sum<VEC_NT>(v, s_red);
+        if (threadIdx.x == 0) {
+            scal->ticketB = 0;
+            allreduce_publish(cv, 2ull * scal->it + 1ull, 1, &tot);
+        }
+    }
+}
+// ... fetched by every rank; the iteration counter moves on so that the next solve / halo push uses fresh sequence numbers
+__global__ void k_true_resid_fetch(PcgScalars *scal, CommView cv) {
+    double v;
+    allreduce_fetch(cv, 2ull * scal->it + 1ull, 1, &v);
+    scal->rr_true = v;
+    __threadfence();
+    scal->it = scal->it + 1;
 }
 
 __global__ void k_final_q(int64_t n, int64_t ghost_cols, const double *__restrict__ qd, const double *__restrict__ x,
@@ -1346,7 +1419,8 @@ void solver_alloc(smfem_ctx *ctx, smfem_matrix *K) {
     CUDA_CHECK(cudaMemsetAsync(K->scal, 0, sizeof(PcgScalars), ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(K->qd, 0, sizeof(double) * K->ncols_l, ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(K->fixed, 0, K->nrows_l, ctx->stream));
-    CUDA_CHECK(cudaMallocHost(&K->h_pinned, 64));
+    CUDA_CHECK(cudaMallocHost(&K->h_pinned, 256));
+    static_assert(sizeof(PcgScalars) <= 256, "pinned read-back buffer");
     spmv_stream_setup(ctx, K);
     K->comm = CommView();
     K->comm.rank = ctx->rank;
@@ -1362,6 +1436,8 @@ void solver_alloc(smfem_ctx *ctx, smfem_matrix *K) {
 }
 
 void solver_free(smfem_matrix *K) {
+    if (K->pcg_graph) cudaGraphExecDestroy((cudaGraphExec_t)K->pcg_graph);
+    K->pcg_graph = nullptr;
     for (int q = 0; q < SMFEM_MAX_RANKS; ++q)
         if (K->peer_maps[q]) {
             cudaIpcCloseMemHandle(K->peer_maps[q]);
@@ -1419,8 +1495,11 @@ void comm_connect(smfem_ctx *ctx, smfem_matrix *K, const void *handles) {
 // neighbours.  For the row-group kernel the SpMV is split into an interior launch (no flag code at all: the halo variant
 // costs 46 us even on one GPU) followed by a boundary-plane launch that waits -- stream order gives the overlap of the
 // NVLink transfer with the interior rows for free.  Other variants keep the single rotated launch.
-static void spmv_apply(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y, bool halo) {
+static void spmv_apply(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y, bool halo, bool check_done = false,
+                       unsigned long long halo_need = 0) {
     SpmvArgs A = make_spmv_args(K, x, y);
+    A.check_done = check_done ? 1 : 0;
+    A.halo_need = halo_need;
     const int variant = K->spmv_variant;
     if (!halo || ctx->nranks == 1) {
         launch_spmv<0>(ctx, K, A, variant);
@@ -1489,16 +1568,17 @@ void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *m
     if (const char *e = std::getenv("SMFEM_BENCH_MODE")) dbg_mode = std::atoi(e);
     const int saved_variant = K->spmv_variant;
     K->spmv_variant = variant;
+    int bench_seq = 0;
     auto one = [&](int j) {
         if (ctx->nranks == 1 && dbg_mode == 2) launch_spmv<2>(ctx, K, A, variant);
         else if (ctx->nranks == 1 && dbg_mode == 3) launch_spmv<3>(ctx, K, A, variant);
         else if (ctx->nranks == 1 && dbg_mode == 7) launch_spmv<7>(ctx, K, A, variant);
         else if (ctx->nranks > 1) {
-            unsigned long long seq = it0 + 1;  // SpMV waits for hflag >= scal->it + 1 (it is not advanced here)
+            const unsigned long long seq = it0 + 1 + (unsigned long long)bench_seq++;  // every repetition really waits for its neighbours' push
             int g = (int)((K->comm.plane_dofs + 255) / 256);
             if (g > ctx->sms * 4) g = ctx->sms * 4;
             LAUNCH(ctx, k_halo_push, g, 256, 0, K->nrows_l, K->ghost_cols, (const double *)K->p, K->scal, K->comm, seq);
-            spmv_apply(ctx, K, K->p, K->Ap, true);
+            spmv_apply(ctx, K, K->p, K->Ap, true, false, seq);
         } else {
             spmv_apply(ctx, K, K->p, K->Ap, false);
         }
@@ -1513,6 +1593,44 @@ void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *m
     CUDA_CHECK(cudaEventElapsedTime(&t, ctx->ev2, ctx->ev3));
     *ms = t / reps;
     K->spmv_variant = saved_variant;
+    if (ctx->nranks > 1) {  // later pushes (solver: it + 1) must use larger sequence numbers than the ones used here
+        unsigned long long it_new = it0 + (unsigned long long)bench_seq + 1;
+        CUDA_CHECK(cudaMemcpyAsync(&K->scal->it, &it_new, 8, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+}
+
+constexpr int PCG_CHUNK = 25;  // iterations per CUDA-graph replay (after convergence the rest of a replay is no-op launches)
+
+// capture PCG_CHUNK iterations once per (matrix, SpMV variant); every later solve replays the instantiated graph.  One iteration:
+//   update_p (+ convergence test, halo push) | SpMV (interior, then boundary planes after the halo flags) | p'Ap | update x, r
+static cudaGraphExec_t pcg_graph(smfem_ctx *ctx, smfem_matrix *K, int variant) {
+    if (K->pcg_graph && K->pcg_graph_variant == variant) return (cudaGraphExec_t)K->pcg_graph;
+    if (K->pcg_graph) cudaGraphExecDestroy((cudaGraphExec_t)K->pcg_graph);
+    K->pcg_graph = nullptr;
+    const int64_t n = K->nrows_l;
+    const int vg = vec_grid(ctx, n);
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    const int64_t l0 = ctx->launches;
+    CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    for (int j = 0; j < PCG_CHUNK; ++j) {
+        LAUNCH(ctx, k_pcg_update_p, vg, VEC_NT, 0, n, K->ghost_cols, (const double *)K->r, (const double *)K->dinv, K->p,
+               K->scal, K->comm, 0ull);
+        spmv_apply(ctx, K, K->p, K->Ap, true, /*check_done=*/true);
+        LAUNCH(ctx, k_pcg_dot, vg, VEC_NT, 0, n, K->ghost_cols, (const double *)K->p, (const double *)K->Ap, K->partials,
+               K->scal, K->comm);
+        LAUNCH(ctx, k_pcg_update_xr, vg, VEC_NT, 0, n, K->ghost_cols, (const double *)K->p, (const double *)K->Ap,
+               (const double *)K->dinv, K->x, K->r, K->partials, K->scal, K->comm);
+    }
+    K->pcg_graph_launches = ctx->launches - l0;
+    CUDA_CHECK(cudaStreamEndCapture(ctx->stream, &graph));
+    ctx->launches = l0;  // captured, not launched; counted per replay
+    CUDA_CHECK(cudaGraphInstantiate(&gexec, graph, 0));
+    cudaGraphDestroy(graph);
+    K->pcg_graph = gexec;
+    K->pcg_graph_variant = variant;
+    return gexec;
 }
 
 void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const double *rhs_extra, double *q_out,
@@ -1528,6 +1646,17 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
         CUDA_CHECK(cudaMemcpyAsync(extra, rhs_extra, 8 * n, cudaMemcpyHostToDevice, ctx->stream));
     }
     const int vg = vec_grid(ctx, n);
+    cudaGraphExec_t gexec = pcg_graph(ctx, K, variant);
+    PcgScalars *h = reinterpret_cast<PcgScalars *>(K->h_pinned);
+    auto read_scal = [&]() {
+        CUDA_CHECK(cudaMemcpyAsync(h, K->scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    };
+    auto halo_push = [&](const double *v, unsigned long long seq) {
+        int g = (int)((K->comm.plane_dofs + 255) / 256);
+        if (g > ctx->sms * 4) g = ctx->sms * 4;
+        LAUNCH(ctx, k_halo_push, g, 256, 0, n, K->ghost_cols, v, K->scal, K->comm, seq);
+    };
     CUDA_CHECK(cudaEventRecord(ctx->ev2, ctx->stream));
     const double warm = K->warm_scale;
     K->warm_scale = 0.0;  // applies to one solve
@@ -1546,77 +1675,50 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
         LAUNCH(ctx, k_warm_vector, (unsigned)((K->ncols_l + 255) / 256), 256, 0, n, K->ghost_cols, K->ncols_l, (const double *)K->qd,
                (const double *)K->x, warm, K->p);
         if (ctx->nranks > 1) {
-            unsigned long long it0 = 0;
-            CUDA_CHECK(cudaMemcpyAsync(&it0, &K->scal->it, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-            int g = (int)((K->comm.plane_dofs + 255) / 256);
-            if (g > ctx->sms * 4) g = ctx->sms * 4;
-            LAUNCH(ctx, k_halo_push, g, 256, 0, n, K->ghost_cols, (const double *)K->p, K->scal, K->comm, it0 + 1);
+            read_scal();
+            halo_push(K->p, h->it + 1);
         }
         spmv_apply(ctx, K, K->p, K->Ap, ctx->nranks > 1);
     }
     LAUNCH(ctx, k_pcg_init, vg, VEC_NT, 0, n, (const double *)K->Ap, (const double *)(warm != 0.0 ? K->r : nullptr),
            (const double *)extra, (const double *)K->diag, (const uint8_t *)K->fixed, K->x, K->r, K->dinv, K->partials, K->scal,
-           K->comm, warm);
-    double *d_out2 = K->partials + K->partials_n;  // tail slots (see solver_alloc)
-    auto fetch = [&](double &rz, double &rr) {
-        LAUNCH(ctx, k_pcg_fetch, 1, 1, 0, K->scal, K->comm, d_out2);
-        CUDA_CHECK(cudaMemcpyAsync(K->h_pinned, d_out2, 24, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        rz = K->h_pinned[0];
-        rr = K->h_pinned[1];
-    };
-    double rz, rr;
-    fetch(rz, rr);
-    const double bnorm2 = K->h_pinned[2];  // ||b||^2 (== ||r0||^2 for a cold start)
-    int it = 0;
-    double res2 = rr;
-    if (bnorm2 > 0.0) {
-        const int chunk = 25;
-        cudaGraph_t graph = nullptr;
-        cudaGraphExec_t gexec = nullptr;
-        // capture `chunk` iterations once; replay until converged.  One iteration:
-        //   update_p (+ halo push) | SpMV (interior, then boundary planes after the halo flags) | p'Ap | update x, r
-        const int64_t l0 = ctx->launches;
-        CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        for (int j = 0; j < chunk; ++j) {
-            LAUNCH(ctx, k_pcg_update_p, vg, VEC_NT, 0, n, K->ghost_cols, (const double *)K->r, (const double *)K->dinv, K->p,
-                   K->scal, K->comm, 0ull);
-            spmv_apply(ctx, K, K->p, K->Ap, true);
-            LAUNCH(ctx, k_pcg_dot, vg, VEC_NT, 0, n, K->ghost_cols, (const double *)K->p, (const double *)K->Ap, K->partials,
-                   K->scal, K->comm);
-            LAUNCH(ctx, k_pcg_update_xr, vg, VEC_NT, 0, n, K->ghost_cols, (const double *)K->p, (const double *)K->Ap,
-                   (const double *)K->dinv, K->x, K->r, K->partials, K->scal, K->comm);
-        }
-        const int64_t per_replay = ctx->launches - l0;
-        CUDA_CHECK(cudaStreamEndCapture(ctx->stream, &graph));
-        ctx->launches = l0;  // captured, not launched; counted per replay below
-        CUDA_CHECK(cudaGraphInstantiate(&gexec, graph, 0));
-        const double tol2 = rtol * rtol * bnorm2;
-        while (it < maxit && res2 > tol2) {
-            CUDA_CHECK(cudaGraphLaunch(gexec, ctx->stream));
-            ctx->launches += per_replay;
-            it += chunk;
-            fetch(rz, res2);
-            if (!(res2 == res2)) break;  // NaN guard
-        }
-        cudaGraphExecDestroy(gexec);
-        cudaGraphDestroy(graph);
+           K->comm, warm, rtol * rtol, (unsigned)maxit);
+    // replay until the device-side test (k_pcg_update_p) has set `done`; the host only looks at the flag
+    for (int64_t launched = 0;; launched += PCG_CHUNK) {
+        CUDA_CHECK(cudaGraphLaunch(gexec, ctx->stream));
+        ctx->launches += K->pcg_graph_launches;
+        read_scal();
+        if (h->done) break;
+        REQUIRE(launched <= (int64_t)maxit + PCG_CHUNK, SMFEM_ERR_CUDA, "PCG: the device-side stopping test never fired (internal error)");
     }
-    unsigned brk = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&brk, &K->scal->breakdown, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (q_out) {
-        LAUNCH(ctx, k_final_q, (unsigned)((n + 255) / 256), 256, 0, n, K->ghost_cols, (const double *)K->qd,
-               (const double *)K->x, K->Ap);
-        CUDA_CHECK(cudaMemcpyAsync(q_out, K->Ap, 8 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    const int it = (int)h->iters;
+    const double bnorm2 = h->bnorm2, res2 = h->rr;
+    const unsigned brk = h->breakdown;
+    // true residual  || (extra - K (q_d + x))_free ||  (the recursive one drifts over ~1e3 iterations); K->p, K->Ap are free now
+    double res2_true = res2;
+    {
+        LAUNCH(ctx, k_warm_vector, (unsigned)((K->ncols_l + 255) / 256), 256, 0, n, K->ghost_cols, K->ncols_l, (const double *)K->qd,
+               (const double *)K->x, 1.0, K->p);
+        if (ctx->nranks > 1) halo_push(K->p, h->it + 1);
+        spmv_apply(ctx, K, K->p, K->Ap, ctx->nranks > 1);
+        LAUNCH(ctx, k_true_resid, vg, VEC_NT, 0, n, (const double *)K->Ap, (const double *)extra, (const uint8_t *)K->fixed, K->partials,
+               K->scal, K->comm);
+        LAUNCH(ctx, k_true_resid_fetch, 1, 1, 0, K->scal, K->comm);
+        if (q_out) {  // q = q_d + C q_f on the owned rows is what the SpMV just read (examples/vector3D.jl:322)
+            CUDA_CHECK(cudaMemcpyAsync(q_out, K->p + K->ghost_cols, 8 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        read_scal();
+        res2_true = h->rr_true;
     }
     CUDA_CHECK(cudaEventRecord(ctx->ev3, ctx->stream));
     CUDA_CHECK(cudaEventSynchronize(ctx->ev3));
     CUDA_CHECK(cudaEventElapsedTime(&K->last_ms, ctx->ev2, ctx->ev3));
     K->last_iters = it;
     K->sol_x = K->x;
+    K->last_relres_rec = bnorm2 > 0 ? std::sqrt(res2 / bnorm2) : 0.0;
+    K->last_relres_true = bnorm2 > 0 ? std::sqrt(res2_true / bnorm2) : 0.0;
     if (extra) dev_free(extra);
     if (iters) *iters = it;
-    if (relres) *relres = bnorm2 > 0 ? std::sqrt(res2 / bnorm2) : 0.0;
+    if (relres) *relres = K->last_relres_true;
     REQUIRE(brk == 0, SMFEM_ERR_SINGULAR, "PCG breakdown: p'Ap <= 0 (matrix not SPD on the free dofs; reference: SingularException)");
 }

@@ -55,6 +55,12 @@ def main():
         Ks = o.assemble_system_literal(ne, NL, IEN, 2, "Q1", 1)
         np.savez_compressed(os.path.join(OUT, f"quad_ne{ne}.npz"), NodeList=NL, IEN=IEN, ID=ID, **csc("K", K), **csc("Ks", Ks))
 
+    # config C1: 2-D plane stress solve, ne = 8 (81 nodes, 162 dofs, nnz 2500) and 16
+    for ne in (8, 16):
+        r = o.plane_stress_problem(ne)
+        np.savez_compressed(os.path.join(OUT, f"c1_plane_stress_ne{ne}.npz"), ne=ne, NodeList=r["NodeList"], IEN=r["IEN"], ID=r["ID"],
+                            q_d=r["q_d"], fixed=r["fixed"], free=r["free"], q=r["q"], **csc("K", r["K"]))
+
     # example problem summaries at ne = 8 and 20 (vectorised form; norms only + q at ne=8)
     summ = {}
     for ne in (8, 20):

@@ -88,6 +88,102 @@ def _worker(rank, ws, port, ne, q):
     dist.destroy_process_group()
 
 
+def _worker_large(rank, ws, port, ne, q):
+    """ne = 64: (1) this rank's slab of K is BIT-identical to the same rows of a one-GPU assembly (same device, second
+    context); (2) a smooth manufactured solution u* is recovered to <= 1e-10 by the N-rank Jacobi-PCG; (3) back-to-back
+    solves without any host barrier in between (the mailbox protocol is self-contained)."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws), LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+
+    import smearfem_b200 as sf
+    from smearfem_b200 import distributed as sd
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=ws, device_id=torch.device("cuda", rank))
+    out = {"rank": rank}
+    try:
+        ctx = sf.Context(device=rank, rank=rank, nranks=ws)
+        mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
+        K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4).add_surface_mass(100.0)
+        info = K.info()
+        r0, nr = info["row0"], info["nrows_local"]
+        # one-GPU twin on the same device
+        ctx1 = sf.Context(device=rank, rank=0, nranks=1)
+        mesh1 = sf.Mesh.meshgrid(ctx1, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
+        K1 = sf.SparseMatrixB200.assemble(ctx1, mesh1, ne, 3, "Q1", 3, 40, 0.4).add_surface_mass(100.0)
+        cp1, rv1, nz1 = K1.to_csc(which=2)
+        cp, rv, nz = K.to_csc(which=2)
+        lo, hi = cp1[r0] - 1, cp1[r0 + nr] - 1
+        out["K_bits"] = bool(np.array_equal(cp - 1 + lo, cp1[r0:r0 + nr + 1] - 1) and np.array_equal(rv, rv1[lo:hi]) and np.array_equal(nz, nz1[lo:hi]))
+        out["diag_bits"] = bool(np.array_equal(K.diag(), K1.diag()[r0:r0 + nr]))
+        del cp1, rv1, nz1, cp, rv, nz
+        # smooth manufactured solution through the example's boundary conditions
+        NL = mesh1.nodelist()
+        X, Y, Z = NL
+        us = np.column_stack([0.01 * np.sin(np.pi * X) * np.cos(2 * Y) * Z, 0.01 * np.cos(X) * np.sin(np.pi * Y) * (1 + Z),
+                              -0.001 * Z + 0.02 * np.sin(np.pi * Z) * (1 + X * Y)]).ravel()
+        rhs = K1.spmv(us)
+        sd.connect(K)
+        K.set_dirichlet_zplanes(0.001)
+        ql, it, relres = K.pcg_solve(rtol=1e-13, maxit=20000, rhs_extra=rhs[r0:r0 + nr])
+        out["iters"], out["relres"] = it, relres
+        out["rel_u"] = float(np.linalg.norm(ql - us[r0:r0 + nr]) / np.linalg.norm(us[r0:r0 + nr]))
+        # 1-GPU solve of the same system: same iteration count (bitwise identical sums are not expected: different reduction trees)
+        K1.set_dirichlet_zplanes(0.001)
+        q1, it1, _ = K1.pcg_solve(rtol=1e-13, maxit=20000, rhs_extra=rhs)
+        out["iters_1gpu"] = it1
+        out["rel_vs_1gpu"] = float(np.linalg.norm(ql - q1[r0:r0 + nr]) / np.linalg.norm(q1[r0:r0 + nr]))
+        # consecutive solves with NO host barrier between them (rank-dependent host delays provoke the race the protocol must survive)
+        import time
+        for rep in range(4):
+            time.sleep(0.002 * ((rank + rep) % ws))
+            qr, itr, _ = K.pcg_solve(rtol=1e-13, maxit=20000, rhs_extra=rhs[r0:r0 + nr])
+            assert itr == it and np.array_equal(qr, ql), (rep, itr, it)
+        out["ok"] = True
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        out["ok"] = False
+        out["err"] = repr(e) + traceback.format_exc()[-600:]
+    q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _spawn(target, ws, ne, timeout=900):
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=target, args=(r, ws, port, ne, q)) for r in range(ws)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=timeout) for _ in ps]
+    for p in ps:
+        p.join(timeout=120)
+    return res
+
+
+@pytest.mark.parametrize("ws,ne", [(2, 64), (4, 64), (8, 64)])
+def test_slab_partition_bit_equivalence_and_manufactured_solution(ws, ne):
+    import torch
+
+    if torch.cuda.device_count() < ws:
+        pytest.skip(f"needs {ws} GPUs")
+    res = _spawn(_worker_large, ws, ne)
+    for r in sorted(res, key=lambda r: r["rank"]):
+        print({k: v for k, v in r.items() if k != "err"})
+        assert r["ok"], r
+        assert r["K_bits"] and r["diag_bits"], r
+        assert r["relres"] <= 1e-12 and r["rel_u"] <= 1e-10, r
+        assert r["rel_vs_1gpu"] <= 1e-10 and abs(r["iters"] - r["iters_1gpu"]) <= 2, r
+
+
 @pytest.mark.parametrize("ws,ne", [(2, 8), (2, 13), (4, 12), (8, 16)])
 def test_slab_partition_matches_oracle(ws, ne):
     import torch

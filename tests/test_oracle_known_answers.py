@@ -139,3 +139,28 @@ def test_back_project_known_answer():
     assert np.allclose(out[:, 0], [cx, cy - fy / 4], rtol=0, atol=1e-12)
     assert np.allclose(out[:, 1], [cx, cy], rtol=0, atol=1e-12)          # (0, 1, 0.5) -> camera (0, 0, 1)
     assert np.allclose(out[:, 2], [cx + fx * 0.125, cy], rtol=0, atol=1e-12)  # (0.25, 0, 0.5) -> camera (0.25, 0, 2)
+
+
+@pytest.mark.parametrize("ne", [2, 8, 16])
+def test_plane_stress_problem_c1(ne):
+    """Config C1 (2-D Q4 plane stress, assemble + solve on CPU): the solve satisfies the system and the physics."""
+    r = o.plane_stress_problem(ne)
+    A = r["K"].to_scipy().tocsr()
+    q, f = r["q"], r["free"] - 1
+    assert np.abs((A @ q)[f]).max() <= 1e-12 * np.abs(A @ r["q_d"][:, 0]).max()     # equilibrium on the free dofs
+    assert np.array_equal(q[r["fixed"] - 1], r["q_d"][r["fixed"] - 1, 0])                # prescribed values kept
+    uy = q[1::2].reshape(ne + 1, ne + 1)                                               # [j, i]
+    assert np.all(np.diff(uy.mean(axis=1)) < 0)                                        # compression grows monotonically in y
+    assert np.allclose(uy, uy[:, ::-1], atol=1e-15) and np.allclose(q[0::2].reshape(ne + 1, ne + 1), -q[0::2].reshape(ne + 1, ne + 1)[:, ::-1], atol=1e-15)
+    assert r["K"].nnz == 4 * (3 * (ne + 1) - 2) ** 2
+    if ne == 8:
+        assert (r["K"].m, r["K"].nnz) == (162, 2500)                                   # SURVEY 8(a) sizes for C1
+
+
+@pytest.mark.parametrize("ne", [8, 16])
+def test_plane_stress_problem_matches_golden(golden_dir, ne):
+    g = np.load(f"{golden_dir}/c1_plane_stress_ne{ne}.npz")
+    r = o.plane_stress_problem(ne)
+    assert np.array_equal(r["K"].colptr, g["K_colptr"]) and np.array_equal(r["K"].rowval, g["K_rowval"])
+    assert np.array_equal(r["fixed"], g["fixed"]) and np.array_equal(r["free"], g["free"])
+    assert np.linalg.norm(r["q"] - g["q"]) <= 1e-13 * np.linalg.norm(g["q"])

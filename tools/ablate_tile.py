@@ -3,6 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import smearfem_b200 as sf
 ne = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+os.environ.setdefault("SMFEM_TILE", "4x4")  # this script ablates the first tile kernel; tools/time_tile2.py the layer-march one
 ctx = sf.context()
 mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
 K = sf.SparseMatrixB200.pattern(ctx, mesh, 3, 3)
