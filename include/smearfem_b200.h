@@ -214,6 +214,9 @@ int smfem_project_nodes(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, const
  * <= 4) take every other node of the finer mesh and are re-assembled with K's own E, nu and surface term; the hierarchy
  * is built at the first solve and rebuilt after a re-assembly.  enable = 0 returns to Jacobi-PCG. */
 int smfem_pcg_use_multigrid(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, int enable);
+/* z = M^-1 r: one application of the multigrid V-cycle to a host vector (this rank's rows in, this rank's rows out; constrained
+ * rows are masked).  For tests of the preconditioner itself (linearity, symmetry, 1-GPU == N-GPU); collective over the ranks. */
+int smfem_pcg_apply_preconditioner(smfem_ctx *ctx, smfem_matrix *K, const double *r, double *z);
 /* Load stepping (examples/vector3D.jl:310-338: the same K̄ solved for 50 prescribed displacements d; q is exactly
  * linear in d): the NEXT smfem_pcg_solve on K starts from scale * (previous solution on the free dofs) instead of 0.
  * Typical use: set_dirichlet_zplanes(d_new); set_warm_start(d_new / d_old); pcg_solve(...) -> 0-2 iterations. */

@@ -314,9 +314,17 @@ class SparseMatrixB200:
         return p3, p2
 
     def use_multigrid(self, enable=True):
-        """Opt-in: later pcg_solve calls use CG preconditioned by a geometric multigrid V-cycle (hex lattice, one GPU)."""
+        """Opt-in: later pcg_solve calls use CG preconditioned by a geometric multigrid V-cycle (hex lattice; with several
+        ranks call distributed.connect(K) before the first solve)."""
         call("smfem_pcg_use_multigrid", self.ctx.handle, self.handle, self.mesh.handle if self.mesh is not None else None, int(bool(enable)))
         return self
+
+    def apply_preconditioner(self, r):
+        """z = M^-1 r for the multigrid V-cycle (after use_multigrid(True)); this rank's rows."""
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        z = np.zeros_like(r)
+        call("smfem_pcg_apply_preconditioner", self.ctx.handle, self.handle, _pf(r), _pf(z))
+        return z
 
     def pcg_stats(self):
         ms, ms2, it = C.c_float(), C.c_float(), C.c_int()

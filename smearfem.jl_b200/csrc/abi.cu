@@ -120,9 +120,31 @@ static void set_lattice(smfem_ctx *ctx, smfem_mesh *m, int64_t ne) {
     REQUIRE(m->nNodes_l * 3 < (int64_t)INT32_MAX, SMFEM_ERR_UNSUPPORTED, "slab too large for int32 local indices");
 }
 
+smfem_mesh *mesh_new_lattice(smfem_ctx *ctx, int64_t ne, int k0, int k1) {
+    smfem_mesh *m = new smfem_mesh();
+    m->ctx = ctx;
+    m->structured = true;
+    m->ne = ne;
+    m->ndim = 3;
+    m->nn = 8;
+    m->lat.ne = (int)ne;
+    m->lat.n1 = (int)ne + 1;
+    m->lat.k0 = k0;
+    m->lat.k1 = k1;
+    m->nNodes_g = (int64_t)m->lat.n1 * m->lat.n1 * m->lat.n1;
+    m->nEl_g = ne * ne * ne;
+    m->nNodes_l = m->lat.nodes_local();
+    if (!(k1 > k0 && k0 >= 0 && k1 <= m->lat.n1)) {
+        delete m;
+        throw SmfemError(SMFEM_ERR_INVALID, "mesh_new_lattice: bad slab");
+    }
+    m->coords = dev_alloc<double>(3 * m->nNodes_l);
+    return m;
+}
+
 extern "C" {
 
-int smfem_abi_version(void) { return 1; }
+int smfem_abi_version(void) { return 2; }
 const char *smfem_last_error(void) { return g_last_error.c_str(); }
 
 int smfem_gaussian_quadrature(double a, double b, int n, double *xi, double *w) {
@@ -904,6 +926,16 @@ int smfem_pcg_use_multigrid(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, i
         NOTNULL(K);
         if (enable) NOTNULL(mesh);
         gmg_enable(ctx, K, mesh, enable != 0);
+    });
+}
+
+int smfem_pcg_apply_preconditioner(smfem_ctx *ctx, smfem_matrix *K, const double *r, double *z) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(K);
+        NOTNULL(r);
+        NOTNULL(z);
+        gmg_apply_host(ctx, K, r, z);
     });
 }
 

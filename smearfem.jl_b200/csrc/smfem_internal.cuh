@@ -133,6 +133,13 @@ struct CommHeader {
     unsigned long long mflag[4][SMFEM_MAX_RANKS];
     unsigned long long hflag[2];  // [0]: ghost_lo filled up to seq, [1]: ghost_hi
     unsigned long long pad[6];
+    // multigrid-PCG (gmg.cu): its own halo flags / acknowledgements / all-gather flags / all-reduce mailbox, numbered by
+    // the device counters hseq / gseq / rseq of PcgScalars (every rank runs the same sequence of exchanges)
+    unsigned long long ghflag[2];   // [0]: my ghost_lo holds the lower neighbour's push number >= value, [1]: ghost_hi
+    unsigned long long gaflag[2];   // [0]: the lower neighbour has consumed my push number <= value, [1]: the upper one
+    unsigned long long gathflag[SMFEM_MAX_RANKS];
+    unsigned long long gflag[4][SMFEM_MAX_RANKS];
+    double gbox[4][SMFEM_MAX_RANKS][4];
 };
 
 struct PcgScalars {
@@ -144,6 +151,7 @@ struct PcgScalars {
     // sums, so all ranks stop in the same iteration); once `done` is set the remaining kernels of a graph replay are no-ops
     double rtol2, rr_true;
     unsigned int iters, maxit, done, pad_;
+    unsigned long long hseq, gseq, rseq;  // multigrid-PCG: halo pushes / all-gathers / all-reduces issued so far
 };
 
 struct CommView {  // passed by value to kernels
@@ -174,6 +182,8 @@ struct smfem_matrix {
     void *gmg = nullptr;            // Gmg* (gmg.cu), built at the first multigrid solve
     smfem_mesh *gmg_mesh = nullptr;  // not owned
     bool gmg_on = false, gmg_dirty = true;
+    bool gmg_coarse = false;          // a coarse-level operator owned by a multigrid hierarchy: no peer window region of its own
+    int64_t gmg_region_doubles = 0;   // multi-GPU: doubles reserved behind p in the peer window for the hierarchy's exchanged vectors
     // Dirichlet
     uint8_t *fixed = nullptr;  // nrows_l
     double *qd = nullptr;      // ncols_l (ghost entries filled locally)
@@ -203,6 +213,23 @@ struct smfem_matrix {
     float last_ms = 0, last_ms_spmv = 0;
     int last_iters = 0;
 };
+
+#ifdef __CUDACC__
+// system-scope flag helpers of the peer-memory protocols (solver.cu, gmg.cu)
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile_f64(const double *p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+#endif
 
 // --- functions implemented across translation units ---------------------------------------------
 void smfem_host_gauss(double a, double b, int n, double *xi, double *w);
@@ -240,9 +267,14 @@ void spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y);
 void spmv_device(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y);  // device vectors: x ncols_l (ghost planes), y nrows_l
 void project_nodes(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, const int64_t *ids, int64_t n, const double *cam,
                    double *nodes3d_out, double *nodes2d_out);  // postprocess.cu
-// gmg.cu: geometric-multigrid preconditioned CG (single GPU, hex lattice)
+// abi.cu: a hex-lattice mesh handle for an explicit slab of node planes [k0, k1) (coordinates allocated, not filled)
+smfem_mesh *mesh_new_lattice(smfem_ctx *ctx, int64_t ne, int k0, int k1);
+// gmg.cu: doubles a rank's peer window needs behind p for the multigrid hierarchy of the ne^3 lattice (0 on one GPU)
+int64_t gmg_window_doubles(int ne, int rank, int nranks);
+// gmg.cu: geometric-multigrid preconditioned CG (hex lattice; one GPU or z-slabs over several)
 void gmg_enable(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, bool enable);
 void gmg_free(smfem_matrix *K);
+void gmg_apply_host(smfem_ctx *ctx, smfem_matrix *K, const double *r_host, double *z_host);
 void gmg_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const double *rhs_extra, double *q_out, int *iters,
                    double *relres);
 void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *ms);

@@ -21,20 +21,6 @@ __device__ __forceinline__ int ld_stream_s32(const int32_t *p) {
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ double ld_volatile_f64(const double *p) {
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -76,8 +62,9 @@ __device__ void allreduce_fetch(const CommView &cv, unsigned long long seq, int 
     int slot = (int)(seq & 3ull);
     for (int v = 0; v < nv; ++v) out[v] = 0.0;
     for (int q = 0; q < cv.nranks; ++q) {
-        while (ld_acquire_sys(&cv.self->mflag[slot][q]) != seq) {
-        }
+        unsigned spins = 0;
+        while (ld_acquire_sys(&cv.self->mflag[slot][q]) != seq)
+            if (++spins > (1u << 26)) __trap();  // a peer that died must surface as an error, not as a hang
         for (int v = 0; v < nv; ++v) out[v] += ld_volatile_f64(&cv.self->mbox[slot][q][v]);
     }
 }
@@ -1262,15 +1249,14 @@ k_pcg_init(int64_t n, const double *__restrict__ Kqd, const double *__restrict__
     }
 }
 
-// w = q_d + warm * x_prev on the owned entries (ghost entries: q_d only; neighbours' planes arrive by halo push)
+// w = q_d + warm * x_prev on the OWNED entries only.  The ghost planes of w are the neighbours' to fill (halo push): a faster
+// neighbour may already have pushed when this kernel runs, so they must not be touched here (with one rank they are never read).
 __global__ void k_warm_vector(int64_t n, int64_t ghost_cols, int64_t ncols, const double *__restrict__ qd,
                               const double *__restrict__ x, double warm, double *__restrict__ w) {
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncols) return;
-    double v = qd[c];
-    int64_t r = c - ghost_cols;
-    if (r >= 0 && r < n) v += warm * x[r];
-    w[c] = v;
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    (void)ncols;
+    w[ghost_cols + r] = qd[ghost_cols + r] + warm * x[r];
 }
 
 // p'Ap as its own pass (50 MB of traffic, ~11 us at 100^3): fusing it into the SpMV cost 60 us there
@@ -1399,7 +1385,11 @@ static int vec_grid(smfem_ctx *ctx, int64_t n) {
 
 void solver_alloc(smfem_ctx *ctx, smfem_matrix *K) {
     if (K->window) return;
-    K->window_bytes = sizeof(CommHeader) + sizeof(double) * (size_t)K->ncols_l;
+    // multi-GPU hex lattice: room behind p for the vectors the multigrid hierarchy exchanges (sized from ne alone, so every
+    // rank knows every peer's layout without communication; smfem_pcg_use_multigrid may be enabled at any time)
+    K->gmg_region_doubles = (K->structured && K->ndim == 3 && K->nDof == 3 && ctx->nranks > 1 && !K->gmg_coarse)
+                                ? gmg_window_doubles(K->lat.ne, ctx->rank, ctx->nranks) : 0;
+    K->window_bytes = sizeof(CommHeader) + sizeof(double) * (size_t)(K->ncols_l + K->gmg_region_doubles);
     CUDA_CHECK(cudaMalloc(&K->window, K->window_bytes));
     CUDA_CHECK(cudaMemsetAsync(K->window, 0, K->window_bytes, ctx->stream));
     K->p = (double *)((char *)K->window + sizeof(CommHeader));

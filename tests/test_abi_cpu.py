@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     # and the Python binding table covers them all
     bound = set(_lib.SIGNATURES) | set(_lib.NON_STATUS)
     assert set(names) == bound, set(names) ^ bound
-    assert L.smfem_abi_version() == 1
+    assert L.smfem_abi_version() == 2
 
 
 def test_no_oracle_import_in_product():

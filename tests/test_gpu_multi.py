@@ -76,6 +76,15 @@ def _worker(rank, ws, port, ne, q):
         qg = sd.gather_vector(ql)
         out["relq_warm"] = float(np.linalg.norm(qg - 11 * r["q"]) / np.linalg.norm(11 * r["q"]))
         out["iters_warm"] = it2
+        # multigrid-preconditioned CG on the N ranks (distributed fine levels, replicated coarse hierarchy) vs the oracle
+        K.set_dirichlet_zplanes(0.001)
+        K.use_multigrid(True)
+        for rep in range(2):  # the second solve reuses the hierarchy; no host barrier in between
+            ql, itg, relg = K.pcg_solve(rtol=1e-13, maxit=200)
+        qg = sd.gather_vector(ql)
+        out["relq_gmg"] = float(np.linalg.norm(qg - r["q"]) / np.linalg.norm(r["q"]))
+        out["iters_gmg"], out["relres_gmg"] = itg, relg
+        K.use_multigrid(False)
         # halo path of the SpMV benchmark must run and agree across variants
         out["spmv_ms"] = [K.bench_spmv(reps=3, variant=v) for v in (4, 3, 2, 1, 0)]
         sd.barrier(ctx)
@@ -106,19 +115,24 @@ def _worker_large(rank, ws, port, ne, q):
     try:
         ctx = sf.Context(device=rank, rank=rank, nranks=ws)
         mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
-        K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4).add_surface_mass(100.0)
+        K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
         info = K.info()
         r0, nr = info["row0"], info["nrows_local"]
         # one-GPU twin on the same device
         ctx1 = sf.Context(device=rank, rank=0, nranks=1)
         mesh1 = sf.Mesh.meshgrid(ctx1, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
-        K1 = sf.SparseMatrixB200.assemble(ctx1, mesh1, ne, 3, "Q1", 3, 40, 0.4).add_surface_mass(100.0)
+        K1 = sf.SparseMatrixB200.assemble(ctx1, mesh1, ne, 3, "Q1", 3, 40, 0.4)
         cp1, rv1, nz1 = K1.to_csc(which=2)
         cp, rv, nz = K.to_csc(which=2)
         lo, hi = cp1[r0] - 1, cp1[r0 + nr] - 1
         out["K_bits"] = bool(np.array_equal(cp - 1 + lo, cp1[r0:r0 + nr + 1] - 1) and np.array_equal(rv, rv1[lo:hi]) and np.array_equal(nz, nz1[lo:hi]))
         out["diag_bits"] = bool(np.array_equal(K.diag(), K1.diag()[r0:r0 + nr]))
-        del cp1, rv1, nz1, cp, rv, nz
+        # the surface term is folded in with atomics (<= 16 adds per entry in any order): equal to rounding, not bitwise
+        K.add_surface_mass(100.0)
+        K1.add_surface_mass(100.0)
+        nzb, nzb1 = K.to_csc(which=2)[2], K1.to_csc(which=2)[2][lo:hi]
+        out["Kbar_rel"] = float(np.linalg.norm(nzb - nzb1) / np.linalg.norm(nzb1))
+        del cp1, rv1, nz1, cp, rv, nz, nzb, nzb1
         # smooth manufactured solution through the example's boundary conditions
         NL = mesh1.nodelist()
         X, Y, Z = NL
@@ -135,6 +149,19 @@ def _worker_large(rank, ws, port, ne, q):
         q1, it1, _ = K1.pcg_solve(rtol=1e-13, maxit=20000, rhs_extra=rhs)
         out["iters_1gpu"] = it1
         out["rel_vs_1gpu"] = float(np.linalg.norm(ql - q1[r0:r0 + nr]) / np.linalg.norm(q1[r0:r0 + nr]))
+        # the same system through the multigrid-preconditioned CG on the N ranks
+        K.use_multigrid(True)
+        qm, itm, relm = K.pcg_solve(rtol=1e-13, maxit=200, rhs_extra=rhs[r0:r0 + nr])
+        out["gmg_iters"], out["gmg_relres"], out["gmg_ms"] = itm, relm, K.pcg_stats()["ms_total"]
+        out["gmg_rel_u"] = float(np.linalg.norm(qm - us[r0:r0 + nr]) / np.linalg.norm(us[r0:r0 + nr]))
+        qm2, itm2, _ = K.pcg_solve(rtol=1e-13, maxit=200, rhs_extra=rhs[r0:r0 + nr])
+        out["gmg_ms_2nd"] = K.pcg_stats()["ms_total"]
+        assert itm2 == itm and np.array_equal(qm, qm2)
+        K1.use_multigrid(True)
+        _, itm1, _ = K1.pcg_solve(rtol=1e-13, maxit=200, rhs_extra=rhs)
+        out["gmg_iters_1gpu"] = itm1
+        K.use_multigrid(False)
+        K1.use_multigrid(False)
         # consecutive solves with NO host barrier between them (rank-dependent host delays provoke the race the protocol must survive)
         import time
         for rep in range(4):
@@ -169,7 +196,7 @@ def _spawn(target, ws, ne, timeout=900):
     return res
 
 
-@pytest.mark.parametrize("ws,ne", [(2, 64), (4, 64), (8, 64)])
+@pytest.mark.parametrize("ws,ne", [(2, 64), (2, 81), (4, 64), (4, 81), (8, 64)])  # 81: level 1 (ne = 41) is distributed too
 def test_slab_partition_bit_equivalence_and_manufactured_solution(ws, ne):
     import torch
 
@@ -179,9 +206,10 @@ def test_slab_partition_bit_equivalence_and_manufactured_solution(ws, ne):
     for r in sorted(res, key=lambda r: r["rank"]):
         print({k: v for k, v in r.items() if k != "err"})
         assert r["ok"], r
-        assert r["K_bits"] and r["diag_bits"], r
+        assert r["K_bits"] and r["diag_bits"] and r["Kbar_rel"] <= 1e-14, r
         assert r["relres"] <= 1e-12 and r["rel_u"] <= 1e-10, r
         assert r["rel_vs_1gpu"] <= 1e-10 and abs(r["iters"] - r["iters_1gpu"]) <= 2, r
+        assert r["gmg_rel_u"] <= 1e-10 and r["gmg_relres"] <= 1e-12 and r["gmg_iters"] <= 45 and r["gmg_iters"] <= r["gmg_iters_1gpu"] + 6, r
 
 
 @pytest.mark.parametrize("ws,ne", [(2, 8), (2, 13), (4, 12), (8, 16)])
@@ -211,3 +239,4 @@ def test_slab_partition_matches_oracle(ws, ne):
         assert r["host_call_same_bits"] and r["bad_part_detected"], r
         assert max(r["relq"]) <= 1e-10, r
         assert r["relq_warm"] <= 1e-10 and r["iters_warm"] <= 25, r
+        assert r["relq_gmg"] <= 1e-10 and r["iters_gmg"] <= 40 and r["relres_gmg"] <= 1e-12, r
