@@ -96,17 +96,55 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def cpu_port_rate(ne_cpu, threads):
-    """elements/s of the C restatement of the reference algorithm (element loop -> COO -> sparse())."""
-    from oracle import c_oracle, fem_oracle as o
+def workload_config(ne, world):
+    """`config` of the JSON line: identical for the GPU arm and the reference arm (same workload, same partition)."""
+    n1 = ne + 1
+    return {"workload": f"hex{ne}: 3-D hex elasticity {ne}^3 elements, inflated unit cube (examples/vector3D.jl), E=40 nu=0.4",
+            "ne": ne, "elements": ne**3, "ndof": 3 * n1**3, "nnz": 9 * (3 * n1 - 2) ** 3, "partition": f"z-slabs x{world}",
+            "step": "device pattern build + element values, every entry of rowptr/colind/val rewritten each step",
+            "l2": "no flush needed: each step writes K (>= 2.9 GB per GPU) >> 126 MB L2"}
 
-    NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne_cpu, 3)
+
+def cpu_sample_layers(ne, target_elements=80000):
+    return max(1, min(ne, int(round(target_elements / float(ne * ne)))))
+
+
+def host_mesh_slab(ne, layers):
+    """The first `layers` element layers of the inflated ne^3 lattice in the reference's host layout (meshgrid numbering:
+    examples/vector3D.jl:60-127; inflate_sphere: src/PostProcess.jl:30-44): NodeList 3 x nN, IEN nEl x 8, ID nN x 3."""
+    from oracle import fem_oracle as o
+
+    n1 = ne + 1
+    ax = o._julia_range(0.0, 1.0, n1)
+    kk, jj, ii = np.meshgrid(np.arange(layers + 1), np.arange(n1), np.arange(n1), indexing="ij")
+    NL = np.asfortranarray(np.stack([ax[ii.ravel()], ax[jj.ravel()], ax[kk.ravel()]]))
     o.inflate_sphere(NL, 0, 1, 0, 1)
+    e = np.arange(ne * ne * layers, dtype=np.int64)
+    base = (e // (ne * ne)) * n1 * n1 + ((e // ne) % ne) * n1 + e % ne + 1
+    IEN = np.asfortranarray(np.stack([base + off for off in (0, 1, n1 + 1, n1, n1 * n1, n1 * n1 + 1, n1 * n1 + n1 + 1, n1 * n1 + n1)], axis=1))
+    m = np.arange(NL.shape[1], dtype=np.int64)
+    ID = np.asfortranarray(3 * m[:, None] + np.arange(1, 4, dtype=np.int64)[None, :])
+    return NL, IEN, ID
+
+
+def cpu_slab_rate(ne, layers, threads, mesh=None):
+    """elements/s of the C restatement of the reference algorithm (element loop -> COO triplets -> sparse(), src/fem.jl:135-256)
+    on a bounded sample of the ne^3 workload: its first `layers` element layers."""
+    from oracle import c_oracle
+
+    NL, IEN, ID = mesh if mesh is not None else host_mesh_slab(ne, layers)
+    nEl = ne * ne * layers
     t = time.perf_counter()
-    K = c_oracle.assemble_system(ne_cpu, NL, IEN, 3, "Q1", 3, ID, 40, 0.4, nthreads=threads)
+    K = c_oracle.assemble_system(ne, NL, IEN, 3, "Q1", 3, ID, 40, 0.4, nthreads=threads, nEl=nEl)
     dt = time.perf_counter() - t
-    assert K.nnz == 9 * (3 * (ne_cpu + 1) - 2) ** 3
-    return ne_cpu**3 / dt, dt
+    s1 = 3 * (ne + 1) - 2
+    assert K.nnz == 9 * s1 * s1 * (3 * (layers + 1) - 2), (K.nnz, ne, layers)   # the slab's own lattice pattern
+    return nEl / dt, dt
+
+
+def cpu_sample_text(ne, layers):
+    return (f"the first {layers} element layers ({ne * ne * layers} elements) of the {ne}^3 inflated hex mesh per step: "
+            "element loop -> 576 COO triplets per element -> sparse(), C restatement of src/fem.jl:135-256 (Julia is not installed: no oracle/_ref)")
 
 
 def cpu_pcg_baseline(ne_cpu, iters=30):
@@ -155,24 +193,27 @@ def run_reference(args, emit):
         return
     from oracle import c_oracle
 
-    threads = c_oracle.max_threads()
-    ne_cpu = 40
-    for _ in range(args.warmup):
-        cpu_port_rate(16, threads)
+    threads = c_oracle.max_threads()   # every core this process may use; NOT OMP_NUM_THREADS (torchrun exports 1)
+    ne = args.ne or ne_for(args.gpus)
+    layers = cpu_sample_layers(ne)
+    mesh = host_mesh_slab(ne, layers)
+    for _ in range(max(args.warmup, 1)):
+        cpu_slab_rate(ne, 1, threads, mesh=(mesh[0], mesh[1][: ne * ne], mesh[2]))
     t_tot, n_el = 0.0, 0
     for _ in range(args.steps):
-        r, dt = cpu_port_rate(ne_cpu, threads)
+        r, dt = cpu_slab_rate(ne, layers, threads, mesh=mesh)
         t_tot += dt
-        n_el += ne_cpu**3
+        n_el += ne * ne * layers
     val = n_el / t_tot
-    sample = f"{ne_cpu}^3 inflated hex elements per step (same element type/material as the GPU workload, bounded sample)"
+    one = cpu_slab_rate(ne, 1, 1, mesh=(mesh[0], mesh[1][: ne * ne], mesh[2]))[0]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"hex{ne_for(args.gpus)} (3-D hex elasticity, inflated unit cube, E=40, nu=0.4); CPU arm times a {ne_cpu}^3 sample"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "note": "C restatement of src/fem.jl:135-256 + sparse(); Julia itself is not installed (no oracle/_ref)"},
+        "config": workload_config(ne, args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample_text(ne, layers),
+                         "value_1thread": one, "sample_1thread": f"one element layer ({ne * ne} elements), one thread (the reference's loop is serial, src/fem.jl:179)",
+                         "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -210,6 +251,17 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
     args.warmup = max(args.warmup, 3)
     torch.cuda.set_device(local)
+    affinity = None
+    if world > 1:
+        # several ranks on one host: run this rank (and allocate its pinned buffers: first touch) on the CPUs next to its GPU
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            affinity = len(os.sched_getaffinity(0))
+        except Exception as exc:
+            affinity = f"not set: {str(exc)[:80]}"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -287,21 +339,30 @@ def main():
         K.add_surface_mass(100.0)
         sd.connect(K)
         info = K.info()
-        b_spmv = 12 * info["nnz_local"] + 20 * info["nrows_local"] + 4 * info["nrows_local"]  # int64 rowptr
+        b_spmv = 12 * info["nnz_local"] + 20 * info["nrows_local"] + 4 * info["nrows_local"]  # CSR-algorithmic, int64 rowptr
+        # what the row-triple kernel really has to read: 8 B per stored value; colind only for the rows that are not interior
+        # lattice rows (closed-form columns there), once per row triple; rowptr + y + x once per row (x gathers hit L1/L2)
+        n_int_planes = sum(1 for k in range(k0, k1) if 0 < k < n1 - 1)
+        nnz_interior_rows = 81 * 3 * (n1 - 2) ** 2 * n_int_planes
+        b_spmv_real = 8 * info["nnz_local"] + (4.0 / 3.0) * (info["nnz_local"] - nnz_interior_rows) + 24 * info["nrows_local"]
         names = {4: "row-triple (default)", 2: "csr-stream", 1: "warp-per-row"}
         tried = {}
         for variant in (4, 2, 1):
             barrier()
             ms = max_over_ranks(K.bench_spmv(reps=30, variant=variant))
-            tried[names[variant]] = {"ms": ms, "GB/s": b_spmv / (ms * 1e-3) / 1e9}
+            tried[names[variant]] = {"ms": ms, "GB/s_csr_algorithmic": b_spmv / (ms * 1e-3) / 1e9,
+                                     "frac_csr_algorithmic": b_spmv / (ms * 1e-3) / 1e9 / hbm_peak}
         ms4 = tried[names[4]]["ms"]
-        gbs4 = tried[names[4]]["GB/s"]
+        gbs4 = b_spmv_real / (ms4 * 1e-3) / 1e9
         # roofline of the SpMV the solver uses (always the library default, variant 4; not chosen by timing)
         spmv = {"bound": "hbm", "kernel": "k_spmv_group3", "achieved": gbs4, "peak": hbm_peak, "unit": "GB/s", "frac": gbs4 / hbm_peak,
-                "traffic": traffic.get("k_spmv_group3"), "GB/s_per_gpu": gbs4, "ms": ms4, "variant": 4,
-                "bytes_per_spmv_per_gpu": b_spmv, "nnz_per_gpu": info["nnz_local"], "variants": tried,
-                "note": "achieved = CSR-algorithmic bytes (12 B/nnz + 24 B/row) / time; the kernel reads colind once per row triple "
-                        "and interior lattice rows need no colind at all (8.3 B/nnz of real traffic, see `traffic`), and a read-only stream runs above the copy peak (DESIGN.md 4)"}
+                "traffic": traffic.get("k_spmv_group3"), "traffic_source": "static: ncu --set full capture of the same kernel at this size, profiles/traffic.json (not re-measured in this run)",
+                "GB/s_per_gpu": gbs4, "ms": ms4, "variant": 4,
+                "bytes_per_spmv_per_gpu": b_spmv_real, "nnz_per_gpu": info["nnz_local"], "variants": tried,
+                "csr_algorithmic": {"bytes": b_spmv, "GB/s": b_spmv / (ms4 * 1e-3) / 1e9, "frac": b_spmv / (ms4 * 1e-3) / 1e9 / hbm_peak,
+                                    "note": "BASELINE.md's 12 B/nnz + 24 B/row; exceeds 1.0 only because the kernel does not read colind for interior rows"},
+                "note": "achieved = bytes the kernel must really read / time: 8 B/nnz values, colind (4 B/nnz) once per row triple and only for "
+                        "non-interior rows, 24 B/row for rowptr + x + y; halo push and flag waits included for N > 1"}
         K.set_spmv_variant(4)
         K.set_dirichlet_zplanes(0.001)
         sd.barrier(ctx)
@@ -311,17 +372,51 @@ def main():
         pcg = {"iters": it, "relres": relres, "ms_total": ms_tot, "ms_per_iter": ms_tot / max(it, 1),
                "spmv_GB/s_in_solve_per_gpu": b_spmv / (ms_tot / max(it, 1) * 1e-3) / 1e9, "rtol": 1e-10}
         sd.barrier(ctx)
-        if world == 1:
-            # SURVEY 8(f) row 3 (opt-in, one GPU): the same solve with the geometric-multigrid V-cycle as preconditioner
-            try:
-                K.use_multigrid(True)
-                K.pcg_solve(rtol=1e-10, maxit=500, want_q=False)  # builds the hierarchy
-                _, itg, relg = K.pcg_solve(rtol=1e-10, maxit=500, want_q=False)
-                pcg["multigrid"] = {"iters": itg, "relres": relg, "ms_total": K.pcg_stats()["ms_total"],
-                                    "note": "CG + V-cycle (re-assembled coarse levels, Chebyshev(2) smoothing); Jacobi-PCG above is the north-star path"}
-                K.use_multigrid(False)
-            except Exception as exc:  # never let the optional measurement take the bench line down
-                pcg["multigrid"] = {"error": str(exc)[:200]}
+        # the same solve with the geometric-multigrid V-cycle as preconditioner (distributed fine
+        # levels + replicated coarse hierarchy on several GPUs)
+        try:
+            K.use_multigrid(True)
+            K.pcg_solve(rtol=1e-10, maxit=500, want_q=False)  # builds the hierarchy
+            ms_first = max_over_ranks(K.pcg_stats()["ms_total"])
+            _, itg, relg = K.pcg_solve(rtol=1e-10, maxit=500, want_q=False)
+            pcg["multigrid"] = {"iters": itg, "relres": relg, "ms_total": max_over_ranks(K.pcg_stats()["ms_total"]),
+                                "ms_first_solve_with_hierarchy_build": ms_first,
+                                "note": "CG + V-cycle (re-assembled coarse levels, Chebyshev(2) smoothing); Jacobi-PCG above is the north-star path"}
+            K.use_multigrid(False)
+        except Exception as exc:  # never let the optional measurement take the bench line down
+            pcg["multigrid"] = {"error": str(exc)[:200]}
+            K.use_multigrid(False)
+        # solution check at the bench size: a smooth manufactured field u* through the example's boundary conditions
+        # (u_z = 0 on z = 0, u_z = -d on z = 1); rhs = K_bar u* with the library's own (multi-rank) SpMV; ||u - u*|| / ||u*||
+        try:
+            X, Y, Z = mesh.nodelist()
+            us = np.column_stack([0.01 * np.sin(np.pi * X) * np.cos(2 * Y) * Z, 0.01 * np.cos(X) * np.sin(np.pi * Y) * (1 + Z),
+                                  -0.001 * Z + 0.02 * np.sin(np.pi * Z) * (1 + X * Y)]).ravel()
+            sd.barrier(ctx)
+            rhs = K.spmv(us)
+            sd.barrier(ctx)
+
+            def rel_err(u):
+                num, den = float(np.sum((u - us) ** 2)), float(np.sum(us**2))
+                if dist is not None:
+                    t = torch.tensor([num, den], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(t)
+                    num, den = float(t[0].item()), float(t[1].item())
+                return (num / den) ** 0.5
+
+            man = {"field": "u* = smooth trigonometric field satisfying the example's Dirichlet data; rhs = K_bar u*", "rtol": 1e-13}
+            uj, itj, relj = K.pcg_solve(rtol=1e-13, maxit=20000, rhs_extra=rhs)
+            man["jacobi_pcg"] = {"rel_u": rel_err(uj), "iters": itj, "relres_true": relj, "ms_total": max_over_ranks(K.pcg_stats()["ms_total"])}
+            sd.barrier(ctx)
+            K.use_multigrid(True)
+            ug, itm, relm = K.pcg_solve(rtol=1e-13, maxit=500, rhs_extra=rhs)
+            man["multigrid_pcg"] = {"rel_u": rel_err(ug), "iters": itm, "relres_true": relm, "ms_total": max_over_ranks(K.pcg_stats()["ms_total"])}
+            K.use_multigrid(False)
+            pcg["manufactured_solution"] = man
+            del us, rhs, uj, ug, X, Y, Z
+        except Exception as exc:
+            pcg["manufactured_solution"] = {"error": str(exc)[:300]}
+        sd.barrier(ctx)
     clocks = sampler.stop()
 
     # ------------------------------------------------------------------ end to end: HOST mesh arrays -> K on device -> diag to host
@@ -395,18 +490,84 @@ def main():
                    "partly on the device behind a copy, partly by host threads in place; h2d_bytes_per_step counts what was copied",
            "trace_check": float(diag_h.sum())}
 
+    # e2e leg 2: the whole reference pipeline through the C ABI with HOST arrays in and the SOLUTION on the host out
+    # (examples/vector3D.jl:302-322: assemble_system -> K + beta*b -> setboundaryCond -> solve), multigrid-PCG to rtol 1e-10
+    pipe = None
+    if not args.no_solve:
+        q_h = torch.empty(nrows_local, dtype=torch.float64, pin_memory=True)
+
+        def pipeline():
+            mh, kh = C.c_void_p(), C.c_void_p()
+            t0 = time.perf_counter()
+            _lib.call("smfem_assemble_system", ctx.handle, C.cast(NL_h.data_ptr(), _f), C.cast(IEN_h.data_ptr(), _i),
+                      C.cast(ID_h.data_ptr(), _i), nN, nEl, 8, ne, 3, _lib.Q1, 3, 40.0, 0.4, C.byref(mh), C.byref(kh))
+            Kp = sf.SparseMatrixB200(ctx, kh, sf.Mesh(ctx, mh))
+            Kp.add_surface_mass(100.0)
+            sd.connect(Kp)
+            Kp.set_dirichlet_zplanes(0.001)
+            Kp.use_multigrid(True)
+            it, rel = C.c_int(), C.c_double()
+            _lib.call("smfem_pcg_solve", ctx.handle, kh, 1e-10, 500, None, C.cast(q_h.data_ptr(), _f), C.byref(it), C.byref(rel))
+            ctx.sync()
+            dt = time.perf_counter() - t0
+            solve_ms = Kp.pcg_stats()["ms_total"]
+            Kp.free()
+            Kp.mesh.free()
+            return dt, int(it.value), float(rel.value), solve_ms
+
+        try:
+            pipeline()
+            barrier()
+            dt, itp, relp, solve_ms = pipeline()
+            barrier()
+            dt = max_over_ranks(dt)
+            pipe = {"ms_total": dt * 1e3, "elements_per_s": ne**3 / dt, "pcg_iters": itp, "relres": relp, "solve_ms": max_over_ranks(solve_ms),
+                    "h2d_bytes": host_bytes, "d2h_bytes": int(q_h.numel() * 8 * world), "u_checksum": float(q_h.sum()),
+                    "call": "smfem_assemble_system(host NodeList, IEN, ID) -> smfem_surface_mass -> smfem_set_dirichlet_zplanes -> "
+                            "smfem_pcg_use_multigrid -> smfem_pcg_solve(q on host); includes the multigrid hierarchy build"}
+        except Exception as exc:
+            pipe = {"error": str(exc)[:300]}
+        del q_h
+    e2e["pipeline_to_solution"] = pipe
+    # e2e leg 3: assemble_system RETURNS K -- assembly from host arrays + export of the CSC arrays (what sparse(E,J,V) returned,
+    # src/fem.jl:253) to host memory, at 50^3 (0.37 GB of CSC per call), one GPU
+    if world == 1:
+        try:
+            from oracle import fem_oracle as o50   # host mesh builder only (test infrastructure used to make INPUT arrays)
+
+            NL5, IEN5, ID5, *_ = o50.meshgrid(0, 1, 0, 1, 0, 1, 50, 3)
+            o50.inflate_sphere(NL5, 0, 1, 0, 1)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                K5 = sf.assemble_system(50, NL5, IEN5, 3, "Q1", 3, ID5, 40, 0.4)
+                cp5, rv5, nz5 = K5.to_csc()
+                ts.append(time.perf_counter() - t0)
+                K5.free()
+            e2e["assemble_and_export_csc_50"] = {"ms": min(ts) * 1e3, "elements_per_s": 50**3 / min(ts), "csc_bytes_to_host": int(cp5.nbytes + rv5.nbytes + nz5.nbytes),
+                                                 "call": "assemble_system(50, NodeList, IEN, 3, 'Q1', 3, ID, 40, 0.4) -> SparseMatrixCSC parts on the host (pageable arrays, Python mirror)"}
+            del NL5, IEN5, ID5, cp5, rv5, nz5
+        except Exception as exc:
+            e2e["assemble_and_export_csc_50"] = {"error": str(exc)[:300]}
+
     # ------------------------------------------------------------------ CPU baseline beside it (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1:
         from oracle import c_oracle
 
         th = c_oracle.max_threads()
-        ne_cpu = 40
-        rate, dt = cpu_port_rate(ne_cpu, th)
-        cpu = {"value": rate, "unit": UNIT, "cores": th, "kind": "port", "seconds": dt,
-               "sample": f"{ne_cpu}^3 inflated hex elements, C restatement of src/fem.jl:135-256 + sparse() (Julia not installed)"}
+        layers = cpu_sample_layers(ne, 160000)
+        cmesh = host_mesh_slab(ne, layers)
+        one_layer = (cmesh[0], cmesh[1][: ne * ne], cmesh[2])
+        cpu_slab_rate(ne, 1, th, mesh=one_layer)   # warm-up (page faults of the first allocation)
+        rate, dt = cpu_slab_rate(ne, layers, th, mesh=cmesh)
+        rate1, dt1 = cpu_slab_rate(ne, 1, 1, mesh=one_layer)
+        cpu = {"value": rate, "unit": UNIT, "cores": th, "kind": "port", "seconds": dt, "sample": cpu_sample_text(ne, layers),
+               "value_1thread": rate1, "seconds_1thread": dt1,
+               "sample_1thread": f"one element layer ({ne * ne} elements) of the same mesh, one thread (the reference's element loop is serial, src/fem.jl:179)"}
+        del cmesh, one_layer
         try:
-            cpu["solve"] = cpu_pcg_baseline(ne_cpu)
+            cpu["solve"] = cpu_pcg_baseline(40)
         except Exception as exc:  # an optional figure must not take the line down
             cpu["solve"] = {"error": str(exc)[:200]}
 
@@ -415,13 +576,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"hex{ne}: 3-D hex elasticity {ne}^3 elements, inflated unit cube (examples/vector3D.jl), E=40 nu=0.4",
-                       "ne": ne, "elements": ne**3, "ndof": 3 * n1**3, "nnz": 9 * (3 * n1 - 2) ** 3, "partition": f"z-slabs x{world}",
-                       "step": "device pattern build + element values, every entry of rowptr/colind/val rewritten each step",
-                       "l2": "no flush needed: each step writes K (>= 2.9 GB per GPU) >> 126 MB L2"},
-            "roofline": {"bound": "hbm", "kernel": "k_values_tile, fused launch of the step (column indices + values + diagonal)",
+            "config": workload_config(ne, world),
+            "roofline": {"bound": "hbm", "kernel": "k_values_tile2 (layer-march kernel), fused launch of the step (column indices + values + diagonal)",
                          "achieved": roof_val, "peak": hbm_peak, "unit": "GB/s", "frac": roof_val / hbm_peak,
-                         "traffic": traffic.get("k_values_tile_fused_colind"), "peak_source": peak_src,
+                         "traffic": traffic.get("k_values_tile2_fused_colind", traffic.get("k_values_tile_fused_colind")),
+                         "traffic_source": "static: ncu --set full capture of the same launch at this size, profiles/traffic.json (not re-measured in this run)",
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bk_fused, "ms_per_launch": t_fused_kernel * 1e3,
                          "launches_timed": int(_used.value),
                          "bytes": "12 B/nnz (value + column index) + 24 B/node coordinates read + 24 B/node diagonal written; "
@@ -438,6 +598,7 @@ def main():
                                          "achieved": bk_values / t_val_kernel / 1e9, "frac": bk_values / t_val_kernel / 1e9 / hbm_peak,
                                          "traffic": traffic.get("k_values_tile"), "elements_per_s": ne**3 / t_val_kernel}},
             "spmv": spmv, "pcg": pcg, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "host": {"cpus_visible": len(os.sched_getaffinity(0)), "affinity_after_numa_pin": affinity},
         }
         emit(line)
     if dist is not None:

@@ -222,7 +222,8 @@ int smfem_pcg_apply_preconditioner(smfem_ctx *ctx, smfem_matrix *K, const double
  * Typical use: set_dirichlet_zplanes(d_new); set_warm_start(d_new / d_old); pcg_solve(...) -> 0-2 iterations. */
 int smfem_pcg_set_warm_start(smfem_matrix *K, double scale);
 
-/* y = K x with host vectors of this rank's slab (nranks == 1 only; for tests) */
+/* y = K x with host vectors of this rank's row slab (tests, manufactured right-hand sides).  Several ranks: collective, after
+ * smfem_comm_connect; the ghost planes of x travel through the peer window like in a CG iteration. */
 int smfem_spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y);
 /* Time `reps` back-to-back device-resident SpMVs (x = deterministic pattern, halo exchange
  * included when nranks > 1); returns average ms per SpMV measured with CUDA events on the

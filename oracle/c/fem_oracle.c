@@ -89,11 +89,21 @@ static double det_inv(int nd, const double *J, double *inv) {
  * 1-based; ID nNodes x nDof column-major, 1-based (ignored for nDof == 1, src/fem.jl:204-205).
  * E, J, V must hold nEl*(nn*nDof)^2 entries; V must be zero on entry (src/fem.jl:139-145).
  */
+void oracle_assemble_coo_n(int64_t nEl, int ndim, int nDof, const double *NodeList, const int64_t *IEN, const int64_t *ID,
+                           int64_t nNodes, double Young, double nu, int64_t *E, int64_t *J, double *V, int nthreads);
+
 void oracle_assemble_coo(int64_t ne, int ndim, int nDof, const double *NodeList, const int64_t *IEN,
                          const int64_t *ID, int64_t nNodes, double Young, double nu, int64_t *E, int64_t *J,
                          double *V, int nthreads) {
     int64_t nEl = 1;
-    for (int d = 0; d < ndim; ++d) nEl *= ne;
+    for (int d = 0; d < ndim; ++d) nEl *= ne; /* src/fem.jl:179: the loop runs 1:ne^ndim */
+    oracle_assemble_coo_n(nEl, ndim, nDof, NodeList, IEN, ID, nNodes, Young, nu, E, J, V, nthreads);
+}
+
+/* The same element loop over the first nEl rows of an nEl x nn connectivity (bench.py's CPU arm times a slab of element
+ * layers of the full mesh as a bounded sample of the workload). */
+void oracle_assemble_coo_n(int64_t nEl, int ndim, int nDof, const double *NodeList, const int64_t *IEN, const int64_t *ID,
+                           int64_t nNodes, double Young, double nu, int64_t *E, int64_t *J, double *V, int nthreads) {
     const int nn = 1 << ndim, ngp = 1 << ndim, nd = nn * nDof;
     const int64_t blk = (int64_t)nd * nd;
     double xi[2], wq[2];
@@ -253,6 +263,15 @@ int64_t oracle_sparse(int64_t len, const int64_t *E, const int64_t *J, const dou
     colptr[n] = s;
     free(cnt); free(p1); free(p2);
     return nnz;
+}
+
+/* processors available to this process (not affected by OMP_NUM_THREADS, which launchers such as torchrun set to 1) */
+int oracle_hw_threads(void) {
+#ifdef _OPENMP
+    return omp_get_num_procs();
+#else
+    return 1;
+#endif
 }
 
 int oracle_max_threads(void) {

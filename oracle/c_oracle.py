@@ -27,6 +27,7 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.oracle_sparse.restype = C.c_int64
         _lib.oracle_max_threads.restype = C.c_int
+        _lib.oracle_hw_threads.restype = C.c_int
     return _lib
 
 
@@ -35,7 +36,13 @@ def _p(a, t):
 
 
 def max_threads():
-    return int(lib().oracle_max_threads())
+    """Threads the CPU baseline should use: every processor this process may run on.  OMP_NUM_THREADS is NOT honoured on
+    purpose: torchrun exports OMP_NUM_THREADS=1 to its children, which silently made the N > 1 CPU arm single-threaded."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = int(lib().oracle_hw_threads())
+    return max(1, min(n, int(lib().oracle_hw_threads())))
 
 
 def gaussian_quadrature(a, b, n=2):
@@ -45,23 +52,25 @@ def gaussian_quadrature(a, b, n=2):
     return xi, w
 
 
-def assemble_coo(ne, NodeList, IEN, ndim, nDof, ID, Young, nu, nthreads=1):
-    """NodeList (ndim,nNodes), IEN (nEl,nn), ID (nNodes,nDof) in Julia shapes (any memory order)."""
+def assemble_coo(ne, NodeList, IEN, ndim, nDof, ID, Young, nu, nthreads=1, nEl=None):
+    """NodeList (ndim,nNodes), IEN (nEl,nn), ID (nNodes,nDof) in Julia shapes (any memory order).
+    nEl (optional): IEN holds only nEl elements (a slab of the mesh: bench.py's bounded CPU sample)."""
     NodeList = np.asfortranarray(NodeList, dtype=np.float64)
     IEN = np.asfortranarray(IEN, dtype=np.int64)
     nNodes = NodeList.shape[1]
     if ID is None:
         ID = np.zeros((1, 1), dtype=np.int64)
     ID = np.asfortranarray(ID, dtype=np.int64)
-    nEl = ne**ndim
+    if nEl is None:
+        nEl = ne**ndim
     assert IEN.shape[0] == nEl
     L = nEl * (IEN.shape[1] * nDof) ** 2
     E = np.zeros(L, dtype=np.int64)
     J = np.zeros(L, dtype=np.int64)
     V = np.zeros(L, dtype=np.float64)
-    lib().oracle_assemble_coo(C.c_int64(ne), C.c_int(ndim), C.c_int(nDof), _p(NodeList, C.c_double), _p(IEN, C.c_int64),
-                              _p(ID, C.c_int64), C.c_int64(nNodes), C.c_double(Young), C.c_double(nu),
-                              _p(E, C.c_int64), _p(J, C.c_int64), _p(V, C.c_double), C.c_int(nthreads))
+    lib().oracle_assemble_coo_n(C.c_int64(nEl), C.c_int(ndim), C.c_int(nDof), _p(NodeList, C.c_double), _p(IEN, C.c_int64),
+                                _p(ID, C.c_int64), C.c_int64(nNodes), C.c_double(Young), C.c_double(nu),
+                                _p(E, C.c_int64), _p(J, C.c_int64), _p(V, C.c_double), C.c_int(nthreads))
     return E, J, V
 
 
@@ -80,6 +89,6 @@ def sparse(E, J, V):
     return JuliaCSC(m.value, n.value, colptr, rowval[:nnz].copy(), nzval[:nnz].copy())
 
 
-def assemble_system(ne, NodeList, IEN, ndim, FunctionClass="Q1", nDof=1, ID=None, Young=1, nu=0.3, nthreads=1):
+def assemble_system(ne, NodeList, IEN, ndim, FunctionClass="Q1", nDof=1, ID=None, Young=1, nu=0.3, nthreads=1, nEl=None):
     assert FunctionClass == "Q1"
-    return sparse(*assemble_coo(ne, NodeList, IEN, ndim, nDof, ID, Young, nu, nthreads))
+    return sparse(*assemble_coo(ne, NodeList, IEN, ndim, nDof, ID, Young, nu, nthreads, nEl))

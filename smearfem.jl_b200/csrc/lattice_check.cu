@@ -74,7 +74,9 @@ bool host_check_range(const int64_t *arr, int which, int64_t t0, int64_t t1, int
 
 // CPUs this process may really use: affinity mask and cgroup quota (containers often show all cores of the host in
 // hardware_concurrency() but throttle beyond the quota - measured: 8 checker threads on such a box are 2.5x slower than 4).
-int default_host_threads() {
+// The ranks of one box share its cores: each takes its 1/nranks share (8 ranks x 4 checkers on a 32-core host left no
+// core for the callers, and the end-to-end step scaled at 0.45).
+int default_host_threads(int nranks) {
     int n = (int)std::thread::hardware_concurrency();
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min(n, CPU_COUNT(&set));
@@ -92,6 +94,7 @@ int default_host_threads() {
         }
         if (q > 0 && per > 0) n = std::min<long long>(n, (q + per - 1) / per);
     }
+    if (nranks > 1) n = n / nranks;
     return std::max(1, std::min(4, n - 1));  // the calling thread drives the PCIe side
 }
 
@@ -183,7 +186,7 @@ bool lattice_check_hybrid(smfem_ctx *ctx, const Lattice &L, const int64_t *IEN, 
 
     int nthreads = 0;
     if (const char *e = std::getenv("SMFEM_HOST_THREADS")) nthreads = std::atoi(e);
-    else nthreads = default_host_threads();
+    else nthreads = default_host_threads(ctx->nranks);
     HostPool *pool = static_cast<HostPool *>(ctx->host_pool);
     if (nthreads > 0 && (!pool || (int)pool->threads.size() != nthreads)) {
         delete pool;

@@ -1525,14 +1525,38 @@ void spmv_device(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y) {
     spmv_apply(ctx, K, x, y, false);
 }
 
+// device-side barrier of the ranks (a dummy all-reduce with sequence 2 it + 1), then a fresh sequence number: no rank may
+// push its next halo before every rank has finished reading the current one
+__global__ void k_rank_barrier(PcgScalars *scal, CommView cv) {
+    const double one = 1.0;
+    double v;
+    allreduce_publish(cv, 2ull * scal->it + 1ull, 1, &one);
+    allreduce_fetch(cv, 2ull * scal->it + 1ull, 1, &v);
+    __threadfence();
+    scal->it = scal->it + 1;
+}
+
+// y = K x for host vectors of this rank's row slab.  Several ranks: collective; the ghost planes of x come from the
+// neighbours through the peer window (same push / flag / wait as a CG iteration), so smfem_comm_connect must have run.
 void spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y) {
-    REQUIRE(ctx->nranks == 1, SMFEM_ERR_UNSUPPORTED, "spmv_host is single-GPU");
     REQUIRE(K->values_ready, SMFEM_ERR_INVALID, "matrix has no values yet");
     solver_alloc(ctx, K);
-    CUDA_CHECK(cudaMemsetAsync(K->p, 0, sizeof(double) * K->ncols_l, ctx->stream));
+    REQUIRE(K->comm_connected, SMFEM_ERR_INVALID, "multi-GPU: call smfem_comm_connect first");
+    if (ctx->nranks == 1) CUDA_CHECK(cudaMemsetAsync(K->p, 0, sizeof(double) * K->ncols_l, ctx->stream));
     CUDA_CHECK(cudaMemcpyAsync(K->p + K->ghost_cols, x, sizeof(double) * K->nrows_l, cudaMemcpyHostToDevice, ctx->stream));
-    SpmvArgs A = make_spmv_args(K, K->p, K->Ap);
-    launch_spmv<0>(ctx, K, A, K->spmv_variant);
+    if (ctx->nranks > 1) {
+        PcgScalars *h = reinterpret_cast<PcgScalars *>(K->h_pinned);
+        CUDA_CHECK(cudaMemcpyAsync(h, K->scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        int g = (int)((K->comm.plane_dofs + 255) / 256);
+        if (g > ctx->sms * 4) g = ctx->sms * 4;
+        LAUNCH(ctx, k_halo_push, g, 256, 0, K->nrows_l, K->ghost_cols, (const double *)K->p, K->scal, K->comm, h->it + 1);
+        spmv_apply(ctx, K, K->p, K->Ap, true);
+        LAUNCH(ctx, k_rank_barrier, 1, 1, 0, K->scal, K->comm);
+    } else {
+        SpmvArgs A = make_spmv_args(K, K->p, K->Ap);
+        launch_spmv<0>(ctx, K, A, K->spmv_variant);
+    }
     CUDA_CHECK(cudaMemcpyAsync(y, K->Ap, sizeof(double) * K->nrows_l, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
