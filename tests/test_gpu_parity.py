@@ -477,6 +477,44 @@ def test_layer_march_kernel_matches_oracle_and_tile_kernel(monkeypatch, ne, chun
     mesh.free()
 
 
+@pytest.mark.parametrize("ne", [5, 22, 37])
+def test_layer_march_kernel_variants_same_bits(monkeypatch, ne):
+    """The instantiations of k_values_tile2 (shared-memory layout, compile-time section strides, 64-thread CTAs) only move data
+    differently: values, column indices and diagonal are BIT-identical to the first layer-march version."""
+    ctx = sf.context()
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
+    monkeypatch.setenv("SMFEM_TILE", "v2base")
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
+    ref = K.to_csc() + (K.diag(),)
+    monkeypatch.setenv("SMFEM_DEBUG_CLEAR", "1")
+    for variant in ("v2", "v2l", "v2i", "v2s"):
+        monkeypatch.setenv("SMFEM_TILE", variant)
+        K.reassemble(40, 0.4)
+        got = K.to_csc() + (K.diag(),)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b), variant
+    K.free()
+    mesh.free()
+
+
+@pytest.mark.parametrize("ne", [1, 2, 7, 30])
+def test_side_stream_colind_kernel_same_pattern(monkeypatch, ne):
+    """SMFEM_COLIND_SIDE=1: the column indices are written by the persistent closed-form kernel on the side stream while the value
+    kernel runs without its colind output: same colptr / rowval / nzval bits as the fused launch (buffers cleared to 0xFF first)."""
+    ctx = sf.context()
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
+    ref = K.to_csc(which=2) + (K.diag(),)
+    monkeypatch.setenv("SMFEM_DEBUG_CLEAR", "1")
+    monkeypatch.setenv("SMFEM_COLIND_SIDE", "1")
+    K.reassemble(40, 0.4)
+    got = K.to_csc(which=2) + (K.diag(),)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+    K.free()
+    mesh.free()
+
+
 def test_spmv_variants_and_host_spmv():
     ne = 9
     NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)

@@ -44,6 +44,20 @@ for skip, name in [(1, "no phase1"), (2, "no sweeps"), (4, "no shuffles"), (8, "
     t = run(lambda: K.reassemble(40.0, 0.4), 5)
     print(f"v2 skip={skip:2d} {name:16s}: fused {t:.3f} ms", flush=True)
 os.environ.pop("SMFEM_TILE_SKIP")
+for variant in ("v2base", "v2l", "v2i", "v2", "v2s"):
+    os.environ["SMFEM_TILE"] = variant
+    K.reassemble(40.0, 0.4)
+    ok = bool(np.array_equal(K.diag(), d2))
+    v = run(lambda: K.assemble_values(40.0, 0.4))
+    f = run(lambda: K.reassemble(40.0, 0.4))
+    print(f"variant {variant:7s}: values {v:.3f} ms, fused {f:.3f} ms, same diag bits as v2: {ok}", flush=True)
+for variant in ("v2base", "v2", "v2s"):
+    os.environ["SMFEM_TILE"] = variant
+    os.environ["SMFEM_COLIND_SIDE"] = "1"
+    f = run(lambda: K.reassemble(40.0, 0.4))
+    print(f"variant {variant:7s} + side-stream colind kernel: step {f:.3f} ms", flush=True)
+os.environ.pop("SMFEM_COLIND_SIDE")
+os.environ["SMFEM_TILE"] = "v2"
 for plan in sys.argv[2:]:
     os.environ["SMFEM_TILE_CHUNKS"] = plan
     print(f"v2 chunks={plan}: fused {run(lambda: K.reassemble(40.0, 0.4)):.3f} ms", flush=True)
