@@ -17,9 +17,10 @@
  *     (xyz of a node contiguous); IEN Int64 nEl x nLocal column-major, 1-based; ID Int64
  *     nNodes x nDof column-major, 1-based; sparse results are SparseMatrixCSC parts
  *     (colptr, rowval, nzval), Int64, 1-based.
- *   - one context == one GPU == one process (rank); multi-GPU runs are one process per GPU
- *     (torchrun), the slab partition is by z node planes.  There is no CPU
- *     fallback: without a CUDA device smfem_init fails with SMFEM_ERR_CUDA.
+ *   - one context == one GPU (rank); the slab partition is by z node planes.
+ *     Multi-GPU runs are either one process per GPU (torchrun; peer windows exchanged as CUDA IPC
+ *     handles) or ONE process driving all GPUs through smfem_init_multi (last section).  There is
+ *     no CPU fallback: without a CUDA device smfem_init fails with SMFEM_ERR_CUDA.
  *   - calls are blocking w.r.t. the host unless stated; handles are not thread-safe.
  */
 #ifndef SMEARFEM_B200_H
@@ -171,6 +172,9 @@ int smfem_matrix_info(smfem_matrix *K, int64_t *m, int64_t *n, int64_t *nnz, int
 int smfem_matrix_export_csc(smfem_ctx *ctx, smfem_matrix *K, int which, int64_t *colptr, int64_t *rowval,
                             double *nzval);
 int smfem_matrix_diag(smfem_ctx *ctx, smfem_matrix *K, double *diag_local);
+/* Device-side copy of K (pattern, values, diagonal): `K_bar = K + beta*b` of examples/vector3D.jl:308 leaves K itself intact, so
+ * the host mirrors clone before they add the surface term in place.  Dirichlet data / solver state are not copied. */
+int smfem_matrix_clone(smfem_ctx *ctx, smfem_matrix *K, smfem_matrix **K_out);
 int smfem_matrix_free(smfem_matrix *K);
 
 /* apply_boundary_conditions(ne,NodeList,IEN,IEN_top,IEN_btm,ndim,FunctionClass,ID,nDof)
@@ -243,6 +247,54 @@ int smfem_pcg_stats(smfem_matrix *K, float *ms_total, float *ms_spmv_est, int *i
 #define SMFEM_IPC_HANDLE_BYTES 64
 int smfem_comm_export(smfem_ctx *ctx, smfem_matrix *K, void *handle_out);
 int smfem_comm_connect(smfem_ctx *ctx, smfem_matrix *K, const void *all_handles /* nranks*64 bytes */);
+
+/* ---- one process, several GPUs ----------------------------------------------------------------
+ * The reference host is ONE Julia process (examples/vector3D.jl:266-345 `main()`), so the path must also be drivable from a
+ * single thread of a single process.  smfem_init_multi creates one context per GPU (rank r of n_gpus = z-slab r of the lattice,
+ * on device devices[r]; devices == NULL: 0 .. n_gpus-1) and one worker thread per GPU.  Every smfem_multi_* call below runs the
+ * per-rank call of the same name on all ranks concurrently and returns when all have finished (the first failing rank's status;
+ * smfem_last_error() names the rank).  The peer windows are connected inside the process with cudaDeviceEnablePeerAccess + raw
+ * device pointers (smfem_comm_connect_local) - CUDA IPC handles cannot be opened by the process that exported them.  Kernels,
+ * halo / all-reduce protocols and results are those of the one-process-per-GPU mode (bit-identical; tests/test_gpu_multi.py).
+ * Host vectors (rhs_extra, q) and exported CSC arrays are GLOBAL: rank r reads / writes its row slab of them. */
+typedef struct smfem_multi smfem_multi;
+typedef struct smfem_multi_mesh smfem_multi_mesh;
+typedef struct smfem_multi_matrix smfem_multi_matrix;
+int smfem_init_multi(int n_gpus, const int *devices, smfem_multi **out);
+int smfem_multi_destroy(smfem_multi *m);
+int smfem_multi_size(smfem_multi *m, int *n_gpus);
+int smfem_multi_sync(smfem_multi *m);
+/* the per-rank handles behind the multi handles (any of the outputs may be NULL), for calls this section does not wrap */
+int smfem_multi_rank_handles(smfem_multi *m, smfem_multi_mesh *mesh, smfem_multi_matrix *K, int rank, smfem_ctx **ctx_out,
+                             smfem_mesh **mesh_out, smfem_matrix **K_out);
+/* meshgrid / inflate_sphere (examples/vector3D.jl:10-130, src/PostProcess.jl:30-44): every rank generates its slab on its device */
+int smfem_multi_meshgrid(smfem_multi *m, double x0, double x1, double y0, double y1, double z0, double z1, int64_t ne, int ndim,
+                         smfem_multi_mesh **out);
+int smfem_multi_inflate_sphere(smfem_multi *m, smfem_multi_mesh *mesh, double x0, double x1, double y0, double y1);
+/* assemble_system (src/fem.jl:135-256) from a device-resident mesh / from the reference's host arrays (all ranks read the same
+ * arrays concurrently, each the part its slab uses) */
+int smfem_multi_assemble(smfem_multi *m, smfem_multi_mesh *mesh, int64_t ne, int ndim, int func_class, int nDof, double Young,
+                         double nu, smfem_multi_matrix **K_out);
+int smfem_multi_assemble_system(smfem_multi *m, const double *NodeList, const int64_t *IEN, const int64_t *ID, int64_t nNodes,
+                                int64_t nEl, int nLocal, int64_t ne, int ndim, int func_class, int nDof, double Young, double nu,
+                                smfem_multi_mesh **mesh_out, smfem_multi_matrix **K_out);
+int smfem_multi_reassemble(smfem_multi *m, smfem_multi_mesh *mesh, smfem_multi_matrix *K, double Young, double nu);
+int smfem_multi_matrix_info(smfem_multi *m, smfem_multi_matrix *K, int64_t *mrows, int64_t *ncols, int64_t *nnz);
+/* K + beta*b (examples/vector3D.jl:175-264, :308), setboundaryCond (:133-173), solve (:315-322) */
+int smfem_multi_surface_mass(smfem_multi *m, smfem_multi_matrix *K, smfem_multi_mesh *mesh, double beta);
+int smfem_multi_set_dirichlet_zplanes(smfem_multi *m, smfem_multi_matrix *K, smfem_multi_mesh *mesh, double d);
+int smfem_multi_pcg_use_multigrid(smfem_multi *m, smfem_multi_matrix *K, smfem_multi_mesh *mesh, int enable);
+int smfem_multi_pcg_set_warm_start(smfem_multi *m, smfem_multi_matrix *K, double scale);
+int smfem_multi_pcg_solve(smfem_multi *m, smfem_multi_matrix *K, double rtol, int maxit, const double *rhs_extra_global,
+                          double *q_global, int *iters, double *relres);
+int smfem_multi_pcg_stats(smfem_multi *m, smfem_multi_matrix *K, float *ms_total_max, int *iters);
+/* SparseMatrixCSC(K) of the WHOLE matrix: colptr m+1, rowval / nzval nnz entries, 1-based (what sparse(E,J,V) returned, src/fem.jl:253) */
+int smfem_multi_matrix_export_csc(smfem_multi *m, smfem_multi_matrix *K, int which, int64_t *colptr, int64_t *rowval, double *nzval);
+int smfem_multi_matrix_free(smfem_multi *m, smfem_multi_matrix *K);
+int smfem_multi_mesh_free(smfem_multi *m, smfem_multi_mesh *mesh);
+/* building blocks of the in-process connection: allocate rank's window / map the peers' windows by pointer (all_K[q] = rank q's matrix) */
+int smfem_comm_prepare(smfem_ctx *ctx, smfem_matrix *K);
+int smfem_comm_connect_local(smfem_ctx *ctx, smfem_matrix *K, smfem_matrix *const *all_K, int n);
 
 #ifdef __cplusplus
 }

@@ -274,9 +274,17 @@ class SparseMatrixB200:
         call("smfem_surface_mass", self.ctx.handle, self.handle, m.handle, _pi(t), _pi(b), nf, float(beta), int(keep_b))
         return self
 
+    def clone(self):
+        """Device-side copy (pattern, values, diagonal)."""
+        h = C.c_void_p()
+        call("smfem_matrix_clone", self.ctx.handle, self.handle, C.byref(h))
+        return SparseMatrixB200(self.ctx, h, self.mesh)
+
     def __add__(self, other):
+        """K + beta*b (examples/vector3D.jl:308): a NEW device matrix, K itself stays K as in the reference; use
+        add_surface_mass for the in-place form that saves the copy."""
         if isinstance(other, SurfaceMatrix):
-            return other._add_into(self)
+            return other._add_into(self.clone())
         return NotImplemented
 
     __radd__ = __add__
@@ -349,6 +357,126 @@ class SparseMatrixB200:
     def free(self):
         if self.handle:
             _lib.lib().smfem_matrix_free(self.handle)
+            self.handle = None
+
+
+# ------------------------------------------------------------------------------------------------
+# one process, several GPUs (the reference host is one Julia process: examples/vector3D.jl:266-345)
+# ------------------------------------------------------------------------------------------------
+class MultiContext:
+    """n GPUs driven from this process: rank r = z-slab r on device devices[r]; every method runs on all ranks concurrently
+    (one worker thread per GPU inside the library, smfem_init_multi)."""
+
+    def __init__(self, n_gpus, devices=None):
+        dv = None if devices is None else (C.c_int * n_gpus)(*devices)
+        h = C.c_void_p()
+        call("smfem_init_multi", int(n_gpus), dv, C.byref(h))
+        self.handle, self.n = h, int(n_gpus)
+
+    def meshgrid(self, x0, x1, y0, y1, z0, z1, ne, ndim=3):
+        h = C.c_void_p()
+        call("smfem_multi_meshgrid", self.handle, float(x0), float(x1), float(y0), float(y1), float(z0), float(z1), int(ne), int(ndim), C.byref(h))
+        return MultiMesh(self, h)
+
+    def assemble_system(self, ne, NodeList, IEN, ndim, FunctionClass="Q1", nDof=1, ID=None, Young=1, nu=0.3):
+        """assemble_system(...) of src/fem.jl:135 with the reference's host arrays; returns the n-GPU matrix."""
+        NodeList = np.asfortranarray(NodeList, dtype=np.float64)
+        IEN = np.asfortranarray(IEN, dtype=np.int64)
+        IDa = None if ID is None else np.asfortranarray(ID, dtype=np.int64)
+        mh, kh = C.c_void_p(), C.c_void_p()
+        call("smfem_multi_assemble_system", self.handle, _pf(NodeList), _pi(IEN), _pi(IDa), NodeList.shape[1], IEN.shape[0], IEN.shape[1],
+             int(ne), int(ndim), _fclass(FunctionClass), int(nDof), float(Young), float(nu), C.byref(mh), C.byref(kh))
+        return MultiMatrix(self, kh, MultiMesh(self, mh))
+
+    def sync(self):
+        call("smfem_multi_sync", self.handle)
+
+    def close(self):
+        if self.handle:
+            _lib.lib().smfem_multi_destroy(self.handle)
+            self.handle = None
+
+
+class MultiMesh:
+    def __init__(self, mctx, handle):
+        self.mctx, self.handle = mctx, handle
+
+    def inflate_sphere(self, x0, x1, y0, y1):
+        call("smfem_multi_inflate_sphere", self.mctx.handle, self.handle, float(x0), float(x1), float(y0), float(y1))
+        return self
+
+    def free(self):
+        if self.handle:
+            _lib.lib().smfem_multi_mesh_free(self.mctx.handle, self.handle)
+            self.handle = None
+
+
+class MultiMatrix:
+    """K distributed over the GPUs of a MultiContext (row slabs); host vectors / CSC exports are global."""
+
+    def __init__(self, mctx, handle, mesh):
+        self.mctx, self.handle, self.mesh = mctx, handle, mesh
+
+    @classmethod
+    def assemble(cls, mctx, mesh, ne, ndim, FunctionClass, nDof, Young, nu):
+        h = C.c_void_p()
+        call("smfem_multi_assemble", mctx.handle, mesh.handle, int(ne), int(ndim), _fclass(FunctionClass), int(nDof), float(Young), float(nu), C.byref(h))
+        return cls(mctx, h, mesh)
+
+    def reassemble(self, Young, nu):
+        call("smfem_multi_reassemble", self.mctx.handle, self.mesh.handle, self.handle, float(Young), float(nu))
+        return self
+
+    def info(self):
+        m, n, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        call("smfem_multi_matrix_info", self.mctx.handle, self.handle, C.byref(m), C.byref(n), C.byref(nnz))
+        return dict(m=m.value, n=n.value, nnz=nnz.value)
+
+    def add_surface_mass(self, beta, mesh=None):
+        call("smfem_multi_surface_mass", self.mctx.handle, self.handle, (mesh or self.mesh).handle, float(beta))
+        return self
+
+    def set_dirichlet_zplanes(self, d):
+        call("smfem_multi_set_dirichlet_zplanes", self.mctx.handle, self.handle, self.mesh.handle, float(d))
+        return self
+
+    def use_multigrid(self, enable=True):
+        call("smfem_multi_pcg_use_multigrid", self.mctx.handle, self.handle, self.mesh.handle, int(bool(enable)))
+        return self
+
+    def pcg_solve(self, rtol=1e-12, maxit=20000, rhs_extra=None, warm_scale=0.0):
+        if warm_scale:
+            call("smfem_multi_pcg_set_warm_start", self.mctx.handle, self.handle, float(warm_scale))
+        q = np.zeros(self.info()["m"])
+        ex = None if rhs_extra is None else np.ascontiguousarray(rhs_extra, dtype=np.float64)
+        it, rel = C.c_int(), C.c_double()
+        call("smfem_multi_pcg_solve", self.mctx.handle, self.handle, float(rtol), int(maxit), _pf(ex), _pf(q), C.byref(it), C.byref(rel))
+        return q, int(it.value), float(rel.value)
+
+    def pcg_stats(self):
+        ms, it = C.c_float(), C.c_int()
+        call("smfem_multi_pcg_stats", self.mctx.handle, self.handle, C.byref(ms), C.byref(it))
+        return dict(ms_total=float(ms.value), iters=int(it.value))
+
+    def to_csc(self, which=0):
+        i = self.info()
+        colptr = np.zeros(i["m"] + 1, dtype=np.int64)
+        rowval = np.zeros(i["nnz"], dtype=np.int64)
+        nzval = np.zeros(i["nnz"], dtype=np.float64)
+        call("smfem_multi_matrix_export_csc", self.mctx.handle, self.handle, int(which), _pi(colptr), _pi(rowval), _pf(nzval))
+        return colptr, rowval, nzval
+
+    def rank_matrix(self, rank):
+        """The per-rank objects behind this matrix (borrowed handles: do not free)."""
+        ch, mh, kh = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        call("smfem_multi_rank_handles", self.mctx.handle, self.mesh.handle, self.handle, int(rank), C.byref(ch), C.byref(mh), C.byref(kh))
+        ctx = Context.__new__(Context)
+        ctx.device, ctx.rank, ctx.nranks, ctx.handle = None, rank, self.mctx.n, ch
+        return SparseMatrixB200(ctx, kh, Mesh(ctx, mh))
+
+    def free(self):
+        if self.handle:
+            _lib.lib().smfem_multi_matrix_free(self.mctx.handle, self.handle)
             self.handle = None
 
 

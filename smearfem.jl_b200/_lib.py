@@ -67,6 +67,7 @@ SIGNATURES = {
     "smfem_pcg_apply_preconditioner": [_vp, _vp, _f64p, _f64p],
     "smfem_project_nodes": [_vp, _vp, _vp, _i64p, C.c_int64, _f64p, _f64p, _f64p],
     "smfem_matrix_free": [_vp],
+    "smfem_matrix_clone": [_vp, _vp, C.POINTER(_vp)],
     "smfem_surface_mass": [_vp, _vp, _vp, _i64p, _i64p, C.c_int64, C.c_double, C.c_int],
     "smfem_set_dirichlet_zplanes": [_vp, _vp, _vp, C.c_double],
     "smfem_set_dirichlet": [_vp, _vp, _i64p, _f64p, C.c_int64],
@@ -78,6 +79,31 @@ SIGNATURES = {
     "smfem_pcg_stats": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)],
     "smfem_comm_export": [_vp, _vp, _vp],
     "smfem_comm_connect": [_vp, _vp, _vp],
+    "smfem_comm_prepare": [_vp, _vp],
+    "smfem_comm_connect_local": [_vp, _vp, C.POINTER(_vp), C.c_int],
+    # one process, several GPUs
+    "smfem_init_multi": [C.c_int, C.POINTER(C.c_int), C.POINTER(_vp)],
+    "smfem_multi_destroy": [_vp],
+    "smfem_multi_size": [_vp, C.POINTER(C.c_int)],
+    "smfem_multi_sync": [_vp],
+    "smfem_multi_rank_handles": [_vp, _vp, _vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)],
+    "smfem_multi_meshgrid": [_vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int,
+                             C.POINTER(_vp)],
+    "smfem_multi_inflate_sphere": [_vp, _vp, C.c_double, C.c_double, C.c_double, C.c_double],
+    "smfem_multi_assemble": [_vp, _vp, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(_vp)],
+    "smfem_multi_assemble_system": [_vp, _f64p, _i64p, _i64p, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                    C.c_double, C.c_double, C.POINTER(_vp), C.POINTER(_vp)],
+    "smfem_multi_reassemble": [_vp, _vp, _vp, C.c_double, C.c_double],
+    "smfem_multi_matrix_info": [_vp, _vp, _i64p, _i64p, _i64p],
+    "smfem_multi_surface_mass": [_vp, _vp, _vp, C.c_double],
+    "smfem_multi_set_dirichlet_zplanes": [_vp, _vp, _vp, C.c_double],
+    "smfem_multi_pcg_use_multigrid": [_vp, _vp, _vp, C.c_int],
+    "smfem_multi_pcg_set_warm_start": [_vp, _vp, C.c_double],
+    "smfem_multi_pcg_solve": [_vp, _vp, C.c_double, C.c_int, _f64p, _f64p, C.POINTER(C.c_int), _f64p],
+    "smfem_multi_pcg_stats": [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_int)],
+    "smfem_multi_matrix_export_csc": [_vp, _vp, C.c_int, _i64p, _i64p, _f64p],
+    "smfem_multi_matrix_free": [_vp, _vp],
+    "smfem_multi_mesh_free": [_vp, _vp],
 }
 NON_STATUS = {"smfem_abi_version": (C.c_int, []), "smfem_last_error": (C.c_char_p, [])}
 

@@ -3,10 +3,13 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "smfem_internal.cuh"
 
 static thread_local std::string g_last_error;
+
+void smfem_set_last_error(const char *msg) { g_last_error = msg ? msg : ""; }
 
 template <class F>
 static int guarded(F &&f) {
@@ -829,6 +832,49 @@ int smfem_transfer_bytes(smfem_ctx *ctx, int64_t *h2d, int64_t *d2h) {
     });
 }
 
+// K_bar = K + beta*b must not alias K (examples/vector3D.jl:308 keeps K): a device-side copy of pattern, values and diagonal;
+// Dirichlet data, solver workspace, peer window and multigrid hierarchy are per matrix and start empty in the copy
+int smfem_matrix_clone(smfem_ctx *ctx, smfem_matrix *K, smfem_matrix **out) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(K);
+        NOTNULL(out);
+        REQUIRE(K->rowptr && K->colind, SMFEM_ERR_INVALID, "matrix has no pattern yet");
+        smfem_matrix *C = new smfem_matrix();
+        C->ctx = ctx;
+        C->ndim = K->ndim;
+        C->nDof = K->nDof;
+        C->nn = K->nn;
+        C->structured = K->structured;
+        C->lat = K->lat;
+        C->m_g = K->m_g;
+        C->nnz_g = K->nnz_g;
+        C->row0 = K->row0;
+        C->nrows_l = K->nrows_l;
+        C->ncols_l = K->ncols_l;
+        C->ghost_cols = K->ghost_cols;
+        C->nnz_l = K->nnz_l;
+        C->values_ready = K->values_ready;
+        C->Young = K->Young;
+        C->nu = K->nu;
+        C->beta_total = K->beta_total;
+        C->mat_known = K->mat_known;
+        C->spmv_variant = K->spmv_variant;
+        auto dup = [&](auto *&dst, const auto *src, int64_t n) {
+            using T = std::remove_const_t<std::remove_pointer_t<decltype(src)>>;
+            if (!src) return;
+            dst = dev_alloc<T>(n);
+            CUDA_CHECK(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+        };
+        dup(C->rowptr, (const int64_t *)K->rowptr, K->nrows_l + 1 + 8);
+        dup(C->colind, (const int32_t *)K->colind, K->nnz_l + 16);
+        dup(C->val, (const double *)K->val, K->nnz_l + 16);
+        dup(C->bval, (const double *)K->bval, K->nnz_l);
+        dup(C->diag, (const double *)K->diag, K->nrows_l);
+        *out = C;
+    });
+}
+
 int smfem_matrix_free(smfem_matrix *K) {
     return guarded([&] {
         if (!K) return;
@@ -998,6 +1044,23 @@ int smfem_comm_export(smfem_ctx *ctx, smfem_matrix *K, void *handle_out) {
         NOTNULL(K);
         NOTNULL(handle_out);
         comm_export(ctx, K, handle_out);
+    });
+}
+
+int smfem_comm_prepare(smfem_ctx *ctx, smfem_matrix *K) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(K);
+        solver_alloc(ctx, K);
+    });
+}
+
+int smfem_comm_connect_local(smfem_ctx *ctx, smfem_matrix *K, smfem_matrix *const *all_K, int n) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(K);
+        NOTNULL(all_K);
+        comm_connect_local(ctx, K, all_K, n);
     });
 }
 

@@ -184,6 +184,49 @@ __global__ void __launch_bounds__(256) k_struct_colind(Lattice L, int64_t nOwned
     }
 }
 
+// The same column indices in closed form WITHOUT reading rowptr, as a small persistent kernel (64-thread CTAs, < 64 registers)
+// that fits on every SM beside the two resident CTAs of the value kernel (which leaves 4096 registers and ~30 KB of shared
+// memory free): launched on the side stream, it fills the pattern while the value kernel computes (SMFEM_COLIND_SIDE=1).
+// A warp walks x-lines of nodes; for interior nodes the 243 entries of the node's 3 rows are 3 node + rel(t), rel fixed per lane.
+__global__ void __launch_bounds__(64) k_struct_colind_side(Lattice L, int32_t *__restrict__ colind) {
+    const int lane = threadIdx.x & 31;
+    const int wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * blockDim.x) >> 5);
+    const int n1 = L.n1;
+    int rel[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int t = lane + 32 * m, s = t % 81, q = s / 3, jj = s - 3 * q;
+        rel[m] = 3 * (((q / 9 - 1) * n1 + ((q / 3) % 3 - 1)) * n1 + (q % 3 - 1)) + jj;
+    }
+    const int64_t base = 9 * pairs_before(n1, 0, 0, L.k0);
+    const int nlines = L.nown() * n1;
+    for (int line = wid; line < nlines; line += nw) {
+        const int k = L.k0 + line / n1, j = line - (line / n1) * n1;
+        const int cy = cnt1(j, n1), cz = cnt1(k, n1);
+        const bool inner_line = cy == 3 && cz == 3;
+        int64_t start = 9 * pairs_before(n1, 0, j, k) - base;  // entries before node (0, j, k)
+        for (int i = 0; i < n1; ++i) {
+            const int cx = cnt1(i, n1);
+            const int T = 3 * cx * cy * cz;
+            int32_t *dst = colind + start;
+            if (inner_line && cx == 3) {
+                const int32_t c0 = (int32_t)(L.lnode(i, j, k) * 3);
+#pragma unroll
+                for (int m = 0; m < 8; ++m)
+                    if (m < 7 || lane < 243 - 224) dst[lane + 32 * m] = c0 + rel[m];
+            } else {
+                const int i0 = i - (i > 0), j0 = j - (j > 0), kk0 = k - (k > 0);
+                for (int t = lane; t < 3 * T; t += 32) {
+                    const int s = t % T, q = s / 3, jj = s - 3 * q;
+                    const int ai = q % cx, aj = (q / cx) % cy, ak = q / (cx * cy);
+                    dst[t] = (int32_t)(L.lnode(i0 + ai, j0 + aj, kk0 + ak) * 3) + jj;
+                }
+            }
+            start += 3 * T;
+        }
+    }
+}
+
 static void matrix_alloc_pattern(smfem_matrix *K) {
     K->rowptr = dev_alloc<int64_t>(K->nrows_l + 1 + 8);  // +8: slack for 16 B-aligned bulk copies (TMA SpMV)
 }
@@ -776,13 +819,21 @@ void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Y
             return !(e && e[0] == '0');
         }();
         const bool side = fuse_pattern && side_ok && ready == nullptr && ctx->copy_stream && ctx->ev_fork && ctx->ev_check;
+        // SMFEM_COLIND_SIDE=1: the column indices come from the persistent side-stream kernel instead of the value kernel's output phase
+        const char *cs_env = std::getenv("SMFEM_COLIND_SIDE");
+        const bool colind_side = side && cs_env && cs_env[0] == '1';
         const unsigned rp_grid = (unsigned)((K->nrows_l + 1 + 255) / 256);
         if (fuse_pattern && !side) LAUNCH(ctx, k_struct_rowptr, rp_grid, 256, 0, mesh->lat, K->nDof, K->nrows_l, K->rowptr);
         if (side) {  // earlier work on the main stream may still read rowptr
             CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
             CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
         }
-        values_assemble_tile(ctx, mesh, K, mat, fuse_pattern, ready);  // writes every entry and the diagonal: no memset, no extract_diag
+        if (colind_side) {  // launched first: one small CTA per SM, the value kernel's CTAs fill the rest
+            k_struct_colind_side<<<ctx->sms, 64, 0, ctx->copy_stream>>>(mesh->lat, K->colind);
+            ctx->launches++;
+            CUDA_CHECK(cudaGetLastError());
+        }
+        values_assemble_tile(ctx, mesh, K, mat, fuse_pattern && !colind_side, ready);  // writes every entry and the diagonal: no memset, no extract_diag
         if (side) {
             k_struct_rowptr<<<rp_grid, 256, 0, ctx->copy_stream>>>(mesh->lat, K->nDof, K->nrows_l, K->rowptr);
             ctx->launches++;

@@ -334,10 +334,9 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_mma(const __grid_consta
 
 template <class T, int MINB>
 void launch_mma(smfem_ctx *ctx, TileArgs &A, int nown) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (first_use_on_device(attr_set)) {
         CUDA_CHECK(cudaFuncSetAttribute(k_values_mma<T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES));
-        attr_set = true;
     }
     A.tiles_x = (A.L.n1 + T::TX - 1) / T::TX;
     A.tiles_y = (A.L.n1 + T::TY - 1) / T::TY;

@@ -20,6 +20,7 @@
 #include <map>
 #include <queue>
 #include <tuple>
+#include <mutex>
 #include <vector>
 
 #include "smfem_internal.cuh"
@@ -435,6 +436,8 @@ std::vector<int> plan_chunks(int ntiles, int nown, int slots) {
         if (sum == nown && (int)len.size() <= MAX_CHUNKS) return len;
     }
     static std::map<std::tuple<int, int, int>, std::vector<int>> cache;
+    static std::mutex cache_mu;  // one process may assemble on several GPUs from several host threads (smfem_init_multi)
+    std::lock_guard<std::mutex> cache_lock(cache_mu);
     const auto key = std::make_tuple(ntiles, nown, slots);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
@@ -484,10 +487,9 @@ std::vector<int> plan_chunks(int ntiles, int nown, int slots) {
 
 template <class T, int MINB, int OUT>
 static void launch_tile(smfem_ctx *ctx, TileArgs &A, int nown) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (first_use_on_device(attr_set)) {
         CUDA_CHECK(cudaFuncSetAttribute(k_values_tile<T, MINB, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES));
-        attr_set = true;
     }
     A.tiles_x = (A.L.n1 + T::TX - 1) / T::TX;
     A.tiles_y = (A.L.n1 + T::TY - 1) / T::TY;

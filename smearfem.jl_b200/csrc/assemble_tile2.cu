@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "smfem_internal.cuh"
@@ -29,28 +30,49 @@
 
 namespace {
 
+// NTHv: threads per CTA (a warp owns 4 x 2 node columns: tile = 4 x 2 NTHv/32).  OPT bit 1: conflict-free shared-memory layout
+// (rows of the 4 nodes of a face padded so that the per-slot g_a loads of a half-warp hit 16 distinct bank pairs; Gauss-point
+// stride == 2 mod 16 and phase-1 tasks numbered element-major, so that the 8 Gauss points of an element read the same
+// coordinates (broadcast) and store to 8 distinct bank pairs); bit 2: compile-time section strides on interior planes.
+template <int NTHv, int OPTv>
 struct T2 {
-    static constexpr int TX = 4, TY = 8, NTH = 128;
-    static constexpr int EX = TX + 1, EY = TY + 1, NEL = EX * EY;  // 45 footprint elements per layer
-    static constexpr int NELP = NEL;                               // element stride of the ring
-    static constexpr int LAYER = 8 * 8 * 3 * NELP;                 // doubles: [gp][b][c][e]
+    static constexpr int TX = 4, NTH = NTHv, TY = 2 * (NTHv / 32), OPT = OPTv;
+    static constexpr int EX = TX + 1, EY = TY + 1, NEL = EX * EY;  // 45 footprint elements per layer (4 x 8 tile)
+    static constexpr int NELP = NEL;                               // element stride of a (b, c) row
+    // pads (doubles) in front of the rows of the face nodes q = 1, 2, 3: with them the addresses a half-warp uses for "its own
+    // node" (slot (sx, sy) -> node q(sx, sy) of element e - sx - EX sy) fall into 16 distinct bank pairs
+    static constexpr int P1 = (OPT & 1) ? 2 : 0, P2 = (OPT & 1) ? 4 : 0, P3 = (OPT & 1) ? (NELP == 45 ? 4 : 12) : 0;
+    static constexpr int FACE = 12 * NELP + P3;                    // doubles per face (4 nodes)
+    static constexpr int GS = (OPT & 1) ? ((2 * FACE + 15) / 16) * 16 + 2 : 2 * FACE;  // Gauss-point stride
+    static constexpr int LAYER = 8 * GS;                           // doubles: [gp][b][c][e]
     static constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY * 3;  // node-plane coordinate buffer (with halo)
     static constexpr int SN = 84;             // staging doubles per node and level (81 + pad; == 4 mod 16: see emit)
     static constexpr int STAGE_WARP = 8 * SN;  // a warp's 8 nodes
     static constexpr size_t SMEM_BYTES = sizeof(double) * (LAYER + (NTH / 32) * STAGE_WARP + 8 * 3 + 8 + 4 * PLANE);
+    // offset of the rows of local node b (reference numbering, b = 4 face + q) inside a Gauss point's block
+    __host__ __device__ static constexpr int boff(int b) {
+        return (b >> 2) * FACE + (b & 3) * 3 * NELP + ((b & 3) == 0 ? 0 : ((b & 3) == 1 ? P1 : ((b & 3) == 2 ? P2 : P3)));
+    }
+    // slots (0,0), (1,0), (1,1), (0,1) own q = 0, 1, 2, 3 at element offsets 0, -1, -EX-1, -EX
+    static constexpr int R1 = (boff(1) - 1) & 15, R2 = (boff(2) - EX - 1) & 15, R3 = (boff(3) - EX) & 15;
+    static_assert(!(OPT & 1) || (R1 % 4 == 0 && R2 % 4 == 0 && R3 % 4 == 0 && R1 && R2 && R3 && R1 != R2 && R1 != R3 && R2 != R3),
+                  "face-row pads do not give a conflict-free own-node load");
+    static_assert(!(OPT & 1) || (GS % 16 == 2), "Gauss-point stride");
 };
 
 // element layer `layer` of the footprint -> S.  Same arithmetic as phase1 of assemble_tile.cu (register-only Q1 gradients,
 // edge-form Jacobian, rsqrt overlapped with the unscaled gradients); src/fem.jl:192-196.
+template <class T>
 __device__ __forceinline__ void phase1_layer(const TileArgs &A, const double *s_gp, const double *s_sw, const double *s_xyz, double *S,
                                              int layer, int X0, int Y0) {
-    constexpr int NEL = T2::NEL, NELP = T2::NELP, EX = T2::EX, NTH = T2::NTH;
+    constexpr int NEL = T::NEL, NELP = T::NELP, EX = T::EX, NTH = T::NTH;
     const Lattice &L = A.L;
-    const double *P0 = s_xyz + (layer & 3) * T2::PLANE, *P1 = s_xyz + ((layer + 1) & 3) * T2::PLANE;
+    const double *P0 = s_xyz + (layer & 3) * T::PLANE, *P1 = s_xyz + ((layer + 1) & 3) * T::PLANE;
     // task = (element, Gauss point): 360 tasks on 128 threads = 3 rounds at 94 % lane use (pairs of Gauss points sharing the
-    // edge differences need 4 x 64 task slots: 70 %); consecutive lanes store consecutive e of one (gp, b, c) row
+    // edge differences need 4 x 64 task slots: 70 %).  OPT 1: the 8 Gauss points of an element sit in consecutive lanes (their
+    // coordinate loads are broadcasts, their stores go to 8 distinct bank pairs); else consecutive lanes = consecutive e
     for (int q = threadIdx.x; q < 8 * NEL; q += NTH) {
-        const int gp = q / NEL, e = q - gp * NEL;
+        const int gp = (T::OPT & 1) ? (q & 7) : q / NEL, e = (T::OPT & 1) ? (q >> 3) : q - gp * NEL;
         const int fy = e / EX, fx = e - fy * EX;
         const int ex = X0 - 1 + fx, ey = Y0 - 1 + fy;
         if (ex < 0 || ey < 0 || ex >= L.ne || ey >= L.ne) continue;
@@ -58,7 +80,7 @@ __device__ __forceinline__ void phase1_layer(const TileArgs &A, const double *s_
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int ox = u & 1, oy = (u >> 1) & 1, oz = u >> 2;
-            const double *p = (oz ? P1 : P0) + 3 * ((fy + oy) * T2::PX + fx + ox);
+            const double *p = (oz ? P1 : P0) + 3 * ((fy + oy) * T::PX + fx + ox);
             Xn[u][0] = p[0];
             Xn[u][1] = p[1];
             Xn[u][2] = p[2];
@@ -112,7 +134,7 @@ __device__ __forceinline__ void phase1_layer(const TileArgs &A, const double *s_
                 const int b = oz * 4 + (oy ? (ox ? 2 : 3) : (ox ? 1 : 0));  // reference local numbering (vector3D.jl:94-101)
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    S[((gp * 8 + b) * 3 + c) * NELP + e] = (d0 * adj[c] + d1 * adj[3 + c] + d2 * adj[6 + c]) * sc;
+                    S[gp * T::GS + T::boff(b) + c * NELP + e] = (d0 * adj[c] + d1 * adj[3 + c] + d2 * adj[6 + c]) * sc;
             }
         }
     }
@@ -126,21 +148,22 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int mask) { return __sh
 //                          the dz = 0 blocks of plane lay + face
 //   Other[q] += g_o g_b'   g_o = g_a of this column's node on the other face (loaded): the dz = 2 face - 1 blocks of
 //                          plane lay + 1 - face                                    (q = in-plane reference number of b)
+template <class T>
 __device__ __forceinline__ void sweep(const double *Sf, const double *So, int aq, double (&Same)[4][9], double (&Other)[4][9]) {
-    constexpr int NELP = T2::NELP;
+    constexpr int NELP = T::NELP;
 #pragma unroll 2
     for (int gp = 0; gp < 8; ++gp) {
-        const double *Sg = Sf + gp * (8 * 3 * NELP);
+        const double *Sg = Sf + gp * T::GS;
         double gb[4][3];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) gb[q][c] = Sg[(q * 3 + c) * NELP];
+            for (int c = 0; c < 3; ++c) gb[q][c] = Sg[T::boff(q) + c * NELP];
         double gs[3], go[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             gs[c] = (aq & 2) ? ((aq & 1) ? gb[3][c] : gb[2][c]) : ((aq & 1) ? gb[1][c] : gb[0][c]);
-            go[c] = So[gp * (8 * 3 * NELP) + c * NELP];
+            go[c] = So[gp * T::GS + c * NELP];
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -173,11 +196,12 @@ struct NodeGeo {
 // 3 rows a section of len = 3 cx cy consecutive entries at  rowstart + lz * len.
 // After the shuffles thread (sx, sy) holds   O0: (sy - sx, 0)  [not slot 3]   O1: (-sx, 1 - 2 sy)  [not slot 2]
 //                                            O2: (1 - sx, 1 - 2 sy)  [not slot 1]
+template <class T>
 __device__ __forceinline__ void emit_level(const TileArgs &A, const NodeGeo &G, double (&X)[4][9], double *stage_w, int lane, int ix, int iy,
                                            int k, int dz, int jx0, int jy0) {
     const int slot = lane & 3, sx = slot & 1, sy = slot >> 1, nwl = lane >> 2;
     const Lattice &L = A.L;
-    double *my = stage_w + nwl * T2::SN;
+    double *my = stage_w + nwl * T::SN;
     const int len = G.len_own;
 #pragma unroll
     for (int o = 0; o < 3; ++o) {
@@ -223,28 +247,37 @@ __device__ __forceinline__ void emit_level(const TileArgs &A, const NodeGeo &G, 
     const int64_t planeoff = 9 * (G.pre(k) * G.S1 * G.S1 - G.pairs_base);
     const bool collapse = (A.skip & 32) != 0;  // ablation: same stores onto a small cache-resident window
     if (G.fast && !collapse) {
-        // interior warp: 24 sections of 27 entries; all loads first, then the stores (the copy is latency-, not bandwidth-bound)
-        const int TR = 27 * cz;
+        // interior warp: 24 sections of 27 entries; all loads first, then the stores (the copy is latency-, not bandwidth-bound).
+        // Lanes >= 27 re-read lanes 11..15's words: a different bank pair than anything lanes 16..26 touch (index 0 was a 2-way conflict)
+        const int ll = (T::OPT & 1) ? (lane < 27 ? lane : lane - 16) : (lane < 27 ? lane : 0);
         double v[2][12];
 #pragma unroll
         for (int yrow = 0; yrow < 2; ++yrow)
 #pragma unroll
             for (int r = 0; r < 12; ++r)
-                v[yrow][r] = (A.skip & 64) ? 1.0 : stage_w[(yrow * 4 + r / 3) * T2::SN + (r % 3) * 27 + (lane < 27 ? lane : 0)];
+                v[yrow][r] = (A.skip & 64) ? 1.0 : stage_w[(yrow * 4 + r / 3) * T::SN + (r % 3) * 27 + ll];
         if (lane < 27 && !(A.skip & 128)) {
+            const int32_t colb = (int32_t)(L.lnode(jx0, jy0, nz) * 3) + G.crel27;
+            // TRc: section stride = entries per row; a compile-time constant on interior planes (all offsets become immediates)
+            auto copy_out = [&](auto trc) {
+                constexpr int TRC = decltype(trc)::value;
+                const int TR = TRC ? TRC : 27 * cz;
 #pragma unroll
-            for (int yrow = 0; yrow < 2; ++yrow) {
-                const int64_t g0 = planeoff + 9 * (int64_t)cz * G.rowc[yrow] + lz * 27 + lane;
-                double *vp = A.val + g0;
+                for (int yrow = 0; yrow < 2; ++yrow) {
+                    const int64_t g0 = planeoff + 9 * (int64_t)cz * G.rowc[yrow] + lz * 27 + lane;
+                    double *vp = A.val + g0;
 #pragma unroll
-                for (int r = 0; r < 12; ++r) vp[r * TR] = v[yrow][r];
-                if (A.colind) {
-                    int32_t *cp = A.colind + g0;
-                    const int32_t col0 = (int32_t)(L.lnode(jx0, jy0 + yrow, nz) * 3) + G.crel27;
+                    for (int r = 0; r < 12; ++r) vp[r * TR] = v[yrow][r];
+                    if (A.colind) {
+                        int32_t *cp = A.colind + g0;
+                        const int32_t col0 = colb + yrow * 3 * L.n1;
 #pragma unroll
-                    for (int r = 0; r < 12; ++r) cp[r * TR] = col0 + 3 * (r / 3);
+                        for (int r = 0; r < 12; ++r) cp[r * TR] = col0 + 3 * (r / 3);
+                    }
                 }
-            }
+            };
+            if ((T::OPT & 2) && cz == 3) copy_out(std::integral_constant<int, 81>());
+            else copy_out(std::integral_constant<int, 0>());
         }
     } else {
 #pragma unroll 1
@@ -263,7 +296,7 @@ __device__ __forceinline__ void emit_level(const TileArgs &A, const NodeGeo &G, 
                     const int dyr = cxn == 3 ? (blk * 11) >> 5 : blk >> 1;   // cxn is 2 or 3 (n1 >= 2)
                     const int dxr = blk - dyr * cxn;
                     const int32_t col = (int32_t)(L.lnode(jx + dxr - (jx > 0), jy + dyr - (jy > 0), nz) * 3) + j;
-                    const double *src = stage_w + (yrow * 4 + node) * T2::SN + lane;
+                    const double *src = stage_w + (yrow * 4 + node) * T::SN + lane;
                     const int64_t g0 = (collapse ? (base & 1023) + 2048 * (threadIdx.x >> 5) : base) + lz * lenn + lane;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
@@ -278,8 +311,9 @@ __device__ __forceinline__ void emit_level(const TileArgs &A, const NodeGeo &G, 
     __syncwarp();  // the staging area is rewritten by the next level
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(T2::NTH, MINB) k_values_tile2(const __grid_constant__ TileArgs A) {
+template <class T, int MINB>
+__global__ void __launch_bounds__(T::NTH, MINB) k_values_tile2(const __grid_constant__ TileArgs A) {
+    using T2 = T;
     constexpr int NTH = T2::NTH, EX = T2::EX, LAYER = T2::LAYER;
     extern __shared__ double smem[];
     double *S = smem;                               // [gp][b][c][e]: the resident element layer
@@ -310,6 +344,7 @@ __global__ void __launch_bounds__(T2::NTH, MINB) k_values_tile2(const __grid_con
     const int e = (ty - sy + 1) * EX + (tx - sx + 1);
     const int aq = sy ? (sx ? 2 : 3) : (sx ? 1 : 0);  // in-plane reference number of this node inside its element
     const double *Se = S + e;
+    const int boff_aq = aq == 0 ? T2::boff(0) : (aq == 1 ? T2::boff(1) : (aq == 2 ? T2::boff(2) : T2::boff(3)));
     double *stage_w = s_stage + warp * T2::STAGE_WARP;
     const int jx0 = X0, jy0 = Y0 + 2 * warp;
     NodeGeo G;
@@ -372,11 +407,11 @@ __global__ void __launch_bounds__(T2::NTH, MINB) k_values_tile2(const __grid_con
             __syncthreads();  // everybody is done with the previous layer in S; coordinate planes lay, lay + 1 have landed
             if (lay + 2 < L.n1 && lay + 2 <= L.k1) wait_plane(lay + 2);
             if (lay + 1 <= L1) stage_plane<T2>(A, s_xyz, lay + 2, X0, Y0);  // lands during this layer's sweeps
-            if (!(A.skip & 1)) phase1_layer(A, s_gp, s_w, s_xyz, S, lay, X0, Y0);
+            if (!(A.skip & 1)) phase1_layer<T2>(A, s_gp, s_w, s_xyz, S, lay, X0, Y0);
             __syncthreads();
         }
         if (real && el_ok && !(A.skip & 2))
-            sweep(Se + (4 * face) * 3 * T2::NELP, Se + (4 * (1 - face) + aq) * 3 * T2::NELP, aq, Same, Other);
+            sweep<T2>(Se + face * T2::FACE, Se + (1 - face) * T2::FACE + boff_aq, aq, Same, Other);
         // face 0: Other = dz -1 of plane lay + 1, then Same = dz 0 of plane lay (complete);  face 1: Other = dz +1 of plane lay
 #pragma unroll 1
         for (int rep = 0; rep < 2; ++rep) {
@@ -393,7 +428,7 @@ __global__ void __launch_bounds__(T2::NTH, MINB) k_values_tile2(const __grid_con
                         Same[q][m] = 0.0;
                     }
             }
-            if (p >= zs && p < ze) emit_level(A, G, Other, stage_w, lane, ix, iy, p, dz, jx0, jy0);
+            if (p >= zs && p < ze) emit_level<T2>(A, G, Other, stage_w, lane, ix, iy, p, dz, jx0, jy0);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -404,20 +439,16 @@ __global__ void __launch_bounds__(T2::NTH, MINB) k_values_tile2(const __grid_con
 
 }  // namespace
 
-// The default structured value kernel; SMFEM_TILE = 4x4 / 8x4 / mma* select the earlier kernels (returns false then)
-bool values_assemble_tile2(smfem_ctx *ctx, TileArgs &A, int nown) {
-    const char *sel = std::getenv("SMFEM_TILE");  // read per call: tests switch kernels inside one process
-    const bool mode = !sel || !sel[0] || std::string(sel) == "v2";
-    if (!mode) return false;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_values_tile2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T2::SMEM_BYTES));
-        attr_set = true;
+template <class T, int MINB>
+static void launch_tile2(smfem_ctx *ctx, TileArgs &A, int nown) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (first_use_on_device(attr_set)) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_values_tile2<T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES));
     }
-    A.tiles_x = (A.L.n1 + T2::TX - 1) / T2::TX;
-    A.tiles_y = (A.L.n1 + T2::TY - 1) / T2::TY;
+    A.tiles_x = (A.L.n1 + T::TX - 1) / T::TX;
+    A.tiles_y = (A.L.n1 + T::TY - 1) / T::TY;
     const int ntiles = A.tiles_x * A.tiles_y;
-    const std::vector<int> len = plan_chunks(ntiles, nown, ctx->sms * 2);
+    const std::vector<int> len = plan_chunks(ntiles, nown, ctx->sms * MINB);
     A.nchunks = (int)len.size();
     A.zb[0] = 0;
     for (int c = 0; c < A.nchunks; ++c) A.zb[c + 1] = A.zb[c] + len[c];
@@ -428,8 +459,22 @@ bool values_assemble_tile2(smfem_ctx *ctx, TileArgs &A, int nown) {
         CUDA_CHECK(cudaEventCreate(&ctx->asm_ev[2 * slot + 1]));
     }
     CUDA_CHECK(cudaEventRecord(ctx->asm_ev[2 * slot], ctx->stream));
-    LAUNCH(ctx, (k_values_tile2<2>), grid, T2::NTH, T2::SMEM_BYTES, A);
+    LAUNCH(ctx, (k_values_tile2<T, MINB>), grid, T::NTH, T::SMEM_BYTES, A);
     CUDA_CHECK(cudaEventRecord(ctx->asm_ev[2 * slot + 1], ctx->stream));
     ctx->asm_count++;
+}
+
+// The default structured value kernel; SMFEM_TILE = 4x4 / 8x4 / mma* select the earlier kernels (returns false then).
+// SMFEM_TILE = v2 (default: 128-thread CTAs, all layout / addressing optimisations), v2base (the first layer-march version),
+// v2l / v2i (one optimisation each), v2s (64-thread CTAs, 4 per SM): kept selectable for A/B timing (tools/time_tile2.py)
+bool values_assemble_tile2(smfem_ctx *ctx, TileArgs &A, int nown) {
+    const char *sel = std::getenv("SMFEM_TILE");  // read per call: tests switch kernels inside one process
+    const std::string m = (!sel || !sel[0]) ? "v2" : sel;
+    if (m == "v2") launch_tile2<T2<128, 3>, 2>(ctx, A, nown);
+    else if (m == "v2base") launch_tile2<T2<128, 0>, 2>(ctx, A, nown);
+    else if (m == "v2l") launch_tile2<T2<128, 1>, 2>(ctx, A, nown);
+    else if (m == "v2i") launch_tile2<T2<128, 2>, 2>(ctx, A, nown);
+    else if (m == "v2s") launch_tile2<T2<64, 3>, 4>(ctx, A, nown);
+    else return false;
     return true;
 }

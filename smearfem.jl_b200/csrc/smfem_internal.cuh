@@ -280,3 +280,15 @@ void gmg_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, cons
 void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *ms);
 void comm_export(smfem_ctx *ctx, smfem_matrix *K, void *handle_out);
 void comm_connect(smfem_ctx *ctx, smfem_matrix *K, const void *handles);
+void comm_connect_local(smfem_ctx *ctx, smfem_matrix *K, smfem_matrix *const *all_K, int n);  // same process: raw peer pointers
+void smfem_set_last_error(const char *msg);  // abi.cu: message for the calling thread's smfem_last_error()
+
+// true exactly once per (call site, device): per-function attributes (dynamic shared memory limits) are per device, and one
+// process may drive several GPUs (smfem_init_multi)
+#include <atomic>
+inline bool first_use_on_device(std::atomic<unsigned long long> &mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    return !(mask.fetch_or(bit) & bit);
+}

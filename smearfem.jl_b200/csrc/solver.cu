@@ -700,10 +700,9 @@ __global__ void __launch_bounds__(TMA_NT, 2) k_spmv_tma(SpmvArgs A, const int32_
 
 template <int MODE>
 static void launch_spmv_tma(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_set{0};
+    if (first_use_on_device(attr_set)) {
         CUDA_CHECK(cudaFuncSetAttribute(k_spmv_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaSmem)));
-        attr_set = true;
     }
     int grid = ctx->sms * 2;
     if (grid > K->nblk) grid = K->nblk;
@@ -1480,6 +1479,26 @@ void comm_connect(smfem_ctx *ctx, smfem_matrix *K, const void *handles) {
     K->comm_connected = true;
 }
 
+// The same connection inside ONE process (smfem_init_multi): the peers' windows are ordinary device pointers of this process;
+// the caller has enabled peer access between the devices.  all_K[q] = rank q's matrix (its window already allocated).
+void comm_connect_local(smfem_ctx *ctx, smfem_matrix *K, smfem_matrix *const *all_K, int n) {
+    solver_alloc(ctx, K);
+    REQUIRE(K->structured, SMFEM_ERR_UNSUPPORTED, "multi-GPU needs a structured (slab-partitioned) mesh");
+    REQUIRE(n == ctx->nranks && n <= SMFEM_MAX_RANKS, SMFEM_ERR_INVALID, "comm_connect_local: one matrix per rank");
+    for (int q = 0; q < n; ++q) {
+        REQUIRE(all_K[q] && all_K[q]->window, SMFEM_ERR_INVALID, "comm_connect_local: a peer has no window yet (smfem_comm_prepare)");
+        REQUIRE(all_K[q]->window_bytes >= sizeof(CommHeader), SMFEM_ERR_INVALID, "comm_connect_local: bad peer window");
+        void *base = all_K[q]->window;
+        K->comm.peer[q] = (CommHeader *)base;
+        K->comm.peer_p[q] = (double *)((char *)base + sizeof(CommHeader));
+    }
+    if (ctx->rank > 0) {
+        int k0, k1;
+        slab_range(K->lat.n1, ctx->rank - 1, ctx->nranks, k0, k1);
+        K->comm.lo_dst_off = (int64_t)(k1 - k0 + 1) * K->comm.plane_dofs;
+    }
+    K->comm_connected = true;
+}
 
 // y = K x without mask / fused dot.  halo: the rows of the first / last owned plane wait for the ghost planes pushed by the
 // neighbours.  For the row-group kernel the SpMV is split into an interior launch (no flag code at all: the halo variant

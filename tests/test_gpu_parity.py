@@ -82,6 +82,8 @@ def test_golden_fixtures_through_reference_api(golden_dir, name):
     assert np.array_equal(colptr, bo.colptr) and np.array_equal(rowval, bo.rowval)
     assert rel(nzval, bo.nzval) <= TOL
     K_bar = K + 100 * b  # examples/vector3D.jl:308
+    assert K_bar is not K
+    assert_csc_parity(K, _load_csc(g, "K"))  # K itself is untouched, as in the reference (K_bar is a device-side copy)
     q_d, C = sf.setboundaryCond(g["NodeList"], ne, 3, "Q1", 0.001, 3)
     q = sf.solve(K_bar, q_d, C, rtol=1e-13)
     assert rel(q, g["q"]) <= TOL
