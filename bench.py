@@ -354,11 +354,21 @@ def main():
                                      "frac_csr_algorithmic": b_spmv / (ms * 1e-3) / 1e9 / hbm_peak}
         ms4 = tried[names[4]]["ms"]
         gbs4 = b_spmv_real / (ms4 * 1e-3) / 1e9
+        # the same operator applied matrix-free from the coordinates (72 B per node of traffic, no CSR arrays)
+        matfree = None
+        try:
+            K.use_matrix_free(True).use_matrix_free(False)   # names the mesh; variant 5 of bench_spmv switches the operator
+            barrier()
+            ms5 = max_over_ranks(K.bench_spmv(reps=30, variant=5))
+            matfree = {"ms": ms5, "bytes_per_application_per_gpu": 72 * info["nrows_local"] // 3,
+                       "note": "y = (K + beta b) x per element from coordinates + x (8 colour passes, no atomics, bit-reproducible); fp64-bound"}
+        except Exception as exc:
+            matfree = {"error": str(exc)[:200]}
         # roofline of the SpMV the solver uses (always the library default, variant 4; not chosen by timing)
         spmv = {"bound": "hbm", "kernel": "k_spmv_group3", "achieved": gbs4, "peak": hbm_peak, "unit": "GB/s", "frac": gbs4 / hbm_peak,
                 "traffic": traffic.get("k_spmv_group3"), "traffic_source": "static: ncu --set full capture of the same kernel at this size, profiles/traffic.json (not re-measured in this run)",
                 "GB/s_per_gpu": gbs4, "ms": ms4, "variant": 4,
-                "bytes_per_spmv_per_gpu": b_spmv_real, "nnz_per_gpu": info["nnz_local"], "variants": tried,
+                "bytes_per_spmv_per_gpu": b_spmv_real, "nnz_per_gpu": info["nnz_local"], "variants": tried, "matrix_free": matfree,
                 "csr_algorithmic": {"bytes": b_spmv, "GB/s": b_spmv / (ms4 * 1e-3) / 1e9, "frac": b_spmv / (ms4 * 1e-3) / 1e9 / hbm_peak,
                                     "note": "BASELINE.md's 12 B/nnz + 24 B/row; exceeds 1.0 only because the kernel does not read colind for interior rows"},
                 "note": "achieved = bytes the kernel must really read / time: 8 B/nnz values, colind (4 B/nnz) once per row triple and only for "
@@ -371,6 +381,15 @@ def main():
         ms_tot = max_over_ranks(st["ms_total"])
         pcg = {"iters": it, "relres": relres, "ms_total": ms_tot, "ms_per_iter": ms_tot / max(it, 1),
                "spmv_GB/s_in_solve_per_gpu": b_spmv / (ms_tot / max(it, 1) * 1e-3) / 1e9, "rtol": 1e-10}
+        sd.barrier(ctx)
+        try:   # the same Jacobi-PCG with the matrix-free operator
+            K.use_matrix_free(True)
+            _, itf, relf = K.pcg_solve(rtol=1e-10, maxit=6000, want_q=False)
+            msf = max_over_ranks(K.pcg_stats()["ms_total"])
+            pcg["matrix_free"] = {"iters": itf, "relres": relf, "ms_total": msf, "ms_per_iter": msf / max(itf, 1)}
+        except Exception as exc:
+            pcg["matrix_free"] = {"error": str(exc)[:200]}
+        K.use_matrix_free(False)
         sd.barrier(ctx)
         # the same solve with the geometric-multigrid V-cycle as preconditioner (distributed fine
         # levels + replicated coarse hierarchy on several GPUs)

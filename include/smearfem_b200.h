@@ -220,6 +220,12 @@ int smfem_project_nodes(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, const
 int smfem_pcg_use_multigrid(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, int enable);
 /* z = M^-1 r: one application of the multigrid V-cycle to a host vector (this rank's rows in, this rank's rows out; constrained
  * rows are masked).  For tests of the preconditioner itself (linearity, symmetry, 1-GPU == N-GPU); collective over the ranks. */
+/* Opt-in (structured 3-D hex lattice, nDof 3): the following smfem_pcg_solve / smfem_spmv_host / multigrid
+ * fine-level products apply K_bar = K + beta*b MATRIX-FREE from `mesh`'s coordinates (72 B per node of traffic instead of 12 B per
+ * nonzero); K must have been assembled on that mesh (its diagonal is the Jacobi preconditioner, its material / beta define the
+ * operator).  Same vector layout, halo protocol and Dirichlet handling as the CSR SpMV; bit-reproducible (8 colour passes, no
+ * atomics).  smfem_bench_spmv variant 5 times it.  `mesh` must stay alive while the option is on. */
+int smfem_pcg_use_matrix_free(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, int enable);
 int smfem_pcg_apply_preconditioner(smfem_ctx *ctx, smfem_matrix *K, const double *r, double *z);
 /* Load stepping (examples/vector3D.jl:310-338: the same K̄ solved for 50 prescribed displacements d; q is exactly
  * linear in d): the NEXT smfem_pcg_solve on K starts from scale * (previous solution on the free dofs) instead of 0.

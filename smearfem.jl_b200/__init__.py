@@ -327,6 +327,11 @@ class SparseMatrixB200:
         call("smfem_pcg_use_multigrid", self.ctx.handle, self.handle, self.mesh.handle if self.mesh is not None else None, int(bool(enable)))
         return self
 
+    def use_matrix_free(self, enable=True):
+        """Opt-in: the solve's operator K + beta*b is applied matrix-free from the mesh coordinates (hex lattice, nDof 3)."""
+        call("smfem_pcg_use_matrix_free", self.ctx.handle, self.handle, self.mesh.handle if self.mesh is not None else None, int(bool(enable)))
+        return self
+
     def apply_preconditioner(self, r):
         """z = M^-1 r for the multigrid V-cycle (after use_multigrid(True)); this rank's rows."""
         r = np.ascontiguousarray(r, dtype=np.float64)

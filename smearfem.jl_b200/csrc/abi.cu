@@ -1047,6 +1047,24 @@ int smfem_comm_export(smfem_ctx *ctx, smfem_matrix *K, void *handle_out) {
     });
 }
 
+// SURVEY 8(f) row 3, second half: the solve's operator applied matrix-free (matfree.cu)
+int smfem_pcg_use_matrix_free(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, int enable) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(K);
+        if (enable) {
+            NOTNULL(mesh);
+            REQUIRE(mesh->structured && K->structured && K->ndim == 3 && K->nDof == 3, SMFEM_ERR_UNSUPPORTED,
+                    "matrix-free operator: structured 3-D hex lattice with nDof = 3 only");
+            REQUIRE(mesh->lat.n1 == K->lat.n1 && mesh->lat.k0 == K->lat.k0 && mesh->lat.k1 == K->lat.k1, SMFEM_ERR_INVALID,
+                    "matrix-free operator: the mesh is not the lattice K was assembled on");
+            REQUIRE(K->mat_known, SMFEM_ERR_INVALID, "matrix-free operator: assemble K first (material, diagonal for the preconditioner)");
+            K->mf_mesh = mesh;
+        }
+        K->matfree_on = enable != 0;
+    });
+}
+
 int smfem_comm_prepare(smfem_ctx *ctx, smfem_matrix *K) {
     return guarded([&] {
         NOTNULL(ctx);

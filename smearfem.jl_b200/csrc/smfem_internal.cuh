@@ -182,6 +182,8 @@ struct smfem_matrix {
     void *gmg = nullptr;            // Gmg* (gmg.cu), built at the first multigrid solve
     smfem_mesh *gmg_mesh = nullptr;  // not owned
     bool gmg_on = false, gmg_dirty = true;
+    bool matfree_on = false;          // the solve's operator is applied matrix-free from mf_mesh's coordinates (matfree.cu)
+    smfem_mesh *mf_mesh = nullptr;    // not owned
     bool gmg_coarse = false;          // a coarse-level operator owned by a multigrid hierarchy: no peer window region of its own
     int64_t gmg_region_doubles = 0;   // multi-GPU: doubles reserved behind p in the peer window for the hierarchy's exchanged vectors
     // Dirichlet
@@ -281,7 +283,9 @@ void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *m
 void comm_export(smfem_ctx *ctx, smfem_matrix *K, void *handle_out);
 void comm_connect(smfem_ctx *ctx, smfem_matrix *K, const void *handles);
 void comm_connect_local(smfem_ctx *ctx, smfem_matrix *K, smfem_matrix *const *all_K, int n);  // same process: raw peer pointers
-void smfem_set_last_error(const char *msg);  // abi.cu: message for the calling thread's smfem_last_error()
+void smfem_set_last_error(const char *msg);
+// matfree.cu: y = (K + beta b) x from the lattice coordinates (no CSR arrays read); same vector layout as the CSR SpMV
+void matfree_apply(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y, bool halo, bool check_done, unsigned long long halo_need);  // abi.cu: message for the calling thread's smfem_last_error()
 
 // true exactly once per (call site, device): per-function attributes (dynamic shared memory limits) are per device, and one
 // process may drive several GPUs (smfem_init_multi)

@@ -1506,6 +1506,10 @@ void comm_connect_local(smfem_ctx *ctx, smfem_matrix *K, smfem_matrix *const *al
 // NVLink transfer with the interior rows for free.  Other variants keep the single rotated launch.
 static void spmv_apply(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y, bool halo, bool check_done = false,
                        unsigned long long halo_need = 0) {
+    if (K->matfree_on) {  // the operator applied from the lattice coordinates (matfree.cu), same vector layout and halo protocol
+        matfree_apply(ctx, K, x, y, halo, check_done, halo_need);
+        return;
+    }
     SpmvArgs A = make_spmv_args(K, x, y);
     A.check_done = check_done ? 1 : 0;
     A.halo_need = halo_need;
@@ -1573,8 +1577,7 @@ void spmv_host(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y) {
         spmv_apply(ctx, K, K->p, K->Ap, true);
         LAUNCH(ctx, k_rank_barrier, 1, 1, 0, K->scal, K->comm);
     } else {
-        SpmvArgs A = make_spmv_args(K, K->p, K->Ap);
-        launch_spmv<0>(ctx, K, A, K->spmv_variant);
+        spmv_apply(ctx, K, K->p, K->Ap, false);
     }
     CUDA_CHECK(cudaMemcpyAsync(y, K->Ap, sizeof(double) * K->nrows_l, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -1600,7 +1603,14 @@ void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *m
     int dbg_mode = 0;  // experiments: SMFEM_BENCH_MODE = 1 mask, 2 dot, 3 mask|dot, 7 solve mode (single GPU only)
     if (const char *e = std::getenv("SMFEM_BENCH_MODE")) dbg_mode = std::atoi(e);
     const int saved_variant = K->spmv_variant;
-    K->spmv_variant = variant;
+    const bool saved_mf = K->matfree_on;
+    if (variant == 5) {  // the matrix-free operator (needs smfem_pcg_use_matrix_free to have named the mesh)
+        REQUIRE(K->mf_mesh != nullptr, SMFEM_ERR_INVALID, "bench_spmv variant 5: call smfem_pcg_use_matrix_free first");
+        K->matfree_on = true;
+    } else {
+        K->matfree_on = false;
+        K->spmv_variant = variant;
+    }
     int bench_seq = 0;
     auto one = [&](int j) {
         if (ctx->nranks == 1 && dbg_mode == 2) launch_spmv<2>(ctx, K, A, variant);
@@ -1626,6 +1636,7 @@ void bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, float *m
     CUDA_CHECK(cudaEventElapsedTime(&t, ctx->ev2, ctx->ev3));
     *ms = t / reps;
     K->spmv_variant = saved_variant;
+    K->matfree_on = saved_mf;
     if (ctx->nranks > 1) {  // later pushes (solver: it + 1) must use larger sequence numbers than the ones used here
         unsigned long long it_new = it0 + (unsigned long long)bench_seq + 1;
         CUDA_CHECK(cudaMemcpyAsync(&K->scal->it, &it_new, 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1672,7 +1683,7 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
     solver_alloc(ctx, K);
     REQUIRE(K->comm_connected, SMFEM_ERR_INVALID, "multi-GPU: call smfem_comm_connect first");
     const int64_t n = K->nrows_l;
-    const int variant = K->spmv_variant;
+    const int variant = K->matfree_on ? 5 : K->spmv_variant;  // also the key of the cached iteration graph
     double *extra = nullptr;
     if (rhs_extra) {
         extra = dev_alloc<double>(n);
@@ -1695,15 +1706,13 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
     K->warm_scale = 0.0;  // applies to one solve
     if (warm == 0.0) {
         // K q_d (unmasked rows; q_d's ghost entries are filled locally, no exchange needed)
-        SpmvArgs A = make_spmv_args(K, K->qd, K->Ap);
-        launch_spmv<0>(ctx, K, A, variant);
+        spmv_apply(ctx, K, K->qd, K->Ap, false);
     } else {
         // warm start (load stepping, examples/vector3D.jl:310-338: q is linear in d):  r0 = extra - K (q_d + warm x_prev)
         if (K->sol_x && K->sol_x != K->x)  // the previous solve was the multigrid one: its solution lives in its own buffer
             CUDA_CHECK(cudaMemcpyAsync(K->x, K->sol_x, 8 * n, cudaMemcpyDeviceToDevice, ctx->stream));
         {  // b = extra - K q_d is still needed for the stopping test: K q_d -> r (r is rewritten by k_pcg_init)
-            SpmvArgs A0 = make_spmv_args(K, K->qd, K->r);
-            launch_spmv<0>(ctx, K, A0, variant);
+            spmv_apply(ctx, K, K->qd, K->r, false);
         }
         LAUNCH(ctx, k_warm_vector, (unsigned)((K->ncols_l + 255) / 256), 256, 0, n, K->ghost_cols, K->ncols_l, (const double *)K->qd,
                (const double *)K->x, warm, K->p);

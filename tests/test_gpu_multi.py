@@ -162,6 +162,12 @@ def _worker_large(rank, ws, port, ne, q):
         out["gmg_iters_1gpu"] = itm1
         K.use_multigrid(False)
         K1.use_multigrid(False)
+        # the matrix-free operator on the N ranks (ghost element layer recomputed, same halo exchange of the search direction)
+        K.use_matrix_free(True)
+        qf, itf, relf = K.pcg_solve(rtol=1e-13, maxit=20000, rhs_extra=rhs[r0:r0 + nr])
+        out["mf_iters"], out["mf_relres"] = itf, relf
+        out["mf_rel_u"] = float(np.linalg.norm(qf - us[r0:r0 + nr]) / np.linalg.norm(us[r0:r0 + nr]))
+        K.use_matrix_free(False)
         # consecutive solves with NO host barrier between them (rank-dependent host delays provoke the race the protocol must survive)
         import time
         for rep in range(4):
@@ -210,6 +216,7 @@ def test_slab_partition_bit_equivalence_and_manufactured_solution(ws, ne):
         assert r["relres"] <= 1e-12 and r["rel_u"] <= 1e-10, r
         assert r["rel_vs_1gpu"] <= 1e-10 and abs(r["iters"] - r["iters_1gpu"]) <= 2, r
         assert r["gmg_rel_u"] <= 1e-10 and r["gmg_relres"] <= 1e-12 and r["gmg_iters"] <= 45 and r["gmg_iters"] <= r["gmg_iters_1gpu"] + 6, r
+        assert r["mf_rel_u"] <= 1e-10 and r["mf_relres"] <= 1e-12 and abs(r["mf_iters"] - r["iters"]) <= 2, r
 
 
 def _single_process_worker(ws, ne, q):

@@ -517,6 +517,55 @@ def test_side_stream_colind_kernel_same_pattern(monkeypatch, ne):
     mesh.free()
 
 
+@pytest.mark.parametrize("ne,beta", [(1, 100.0), (2, 0.0), (5, 100.0), (12, 100.0), (33, 7.5)])
+def test_matrix_free_operator_matches_assembled_spmv(ne, beta):
+    """SURVEY 8(f) row 3 (second half): y = (K + beta b) x applied matrix-free from the coordinates equals the CSR SpMV of the
+    assembled K_bar (<= 1e-13 relative, different summation order only), on an inflated + jittered lattice, and is bit-reproducible."""
+    ctx = sf.context()
+    NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.inflate_sphere(NL, 0, 1, 0, 1)
+    if ne > 1:
+        o.jitter_nodes(NL, ne, seed=3)
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).set_nodelist(NL)
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
+    if beta:
+        K.add_surface_mass(beta)
+    x = np.random.default_rng(ne).standard_normal(3 * (ne + 1) ** 3)
+    y_csr = K.spmv(x)
+    K.use_matrix_free(True)
+    y_mf = K.spmv(x)
+    assert rel(y_mf, y_csr) <= 1e-13
+    assert np.array_equal(K.spmv(x), y_mf)
+    K.use_matrix_free(False)
+    assert np.array_equal(K.spmv(x), y_csr)
+    K.free()
+    mesh.free()
+
+
+@pytest.mark.parametrize("ne", [6, 20])
+def test_matrix_free_pcg_matches_oracle(ne):
+    """The example problem solved with the matrix-free operator inside Jacobi-PCG and inside the multigrid-preconditioned CG:
+    ||u - u_ref|| / ||u_ref|| <= 1e-10 against the oracle's direct solve, same iteration counts (+-2) as with the assembled K."""
+    ctx = sf.context()
+    r = o.example_problem(ne)
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
+    K.add_surface_mass(100.0).set_dirichlet_zplanes(0.001)
+    q0, it0, _ = K.pcg_solve(rtol=1e-13, maxit=20000)
+    K.use_matrix_free(True)
+    q1, it1, rel1 = K.pcg_solve(rtol=1e-13, maxit=20000)
+    assert rel(q1, r["q"]) <= TOL and rel1 <= 1e-12 and abs(it1 - it0) <= 2
+    K.use_multigrid(True)
+    q2, it2, rel2 = K.pcg_solve(rtol=1e-13, maxit=200)
+    assert rel(q2, r["q"]) <= TOL and rel2 <= 1e-12 and it2 <= 40
+    K.use_multigrid(False)
+    K.use_matrix_free(False)
+    q3, it3, _ = K.pcg_solve(rtol=1e-13, maxit=20000)   # back on the assembled operator: the cached iteration graph is per operator
+    assert it3 == it0 and np.array_equal(q3, q0)
+    K.free()
+    mesh.free()
+
+
 def test_spmv_variants_and_host_spmv():
     ne = 9
     NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
