@@ -208,10 +208,21 @@ int smfem_pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, con
  * motion = q[ID]' taken from K's last smfem_pcg_solve (K = NULL or not solved yet: motion = 0), and its projection
  * back_project(NodeList_new[:, ids], CameraMatrix) (src/PostProcess.jl:131-152: R = [1 0 0; 0 0 1; 0 -1 0],
  * t = [0; -0.5; 2], perspective divide, CameraMatrix' * p, rows 1:2).  CameraMatrix: 3 x 3 column-major.  Outputs are
- * 3 x n and 2 x n column-major, either may be NULL.  One GPU.  The hull / spline / plotting steps of extract_borders
- * and fit_curve remain host code (PostProcess.jl unchanged). */
+ * 3 x n and 2 x n column-major, either may be NULL.  One GPU. */
 int smfem_project_nodes(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, const int64_t *node_ids, int64_t n,
                         const double *CameraMatrix, double *nodes3d_out, double *nodes2d_out);
+/* extract_borders(NodeList_new, CameraMatrix, BorderNodesList, state, ne) (src/PostProcess.jl:60-117) on the coordinates displaced by
+ * K's last solve: side_node_ids = BorderNodesList[1] (1-based, layer by layer as meshgrid lists them).  state 0 = "init": per layer
+ * the first node of minimal / maximal projected x, the top / bottom arcs above / below the left extreme sorted lexicographically
+ * (sortslices), BorderPoints = [Left | Top | reverse(Right) | reverse(Bottom)] -- all on the device, only the border crosses PCIe.
+ * state 1 = "update": convex hull of the projected side nodes in LazySets.convex_hull's convention (Andrew's monotone chain:
+ * counter-clockwise from the lexicographically smallest point, collinear points dropped; LazySets is not vendored with the
+ * reference, so this convention is restated from its documentation).  BorderPoints_out: 2 x capacity column-major (init needs
+ * 2 (ne + 1) + 2 n / (ne + 1) columns at most, update n); *nBorder_out = columns written; SideNodes2D_out (2 x n) may be NULL.
+ * fit_curve / plotting remain host code (PostProcess.jl unchanged).  One GPU. */
+int smfem_extract_borders(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, const int64_t *side_node_ids, int64_t n,
+                          const double *CameraMatrix, int state, int64_t ne, double *BorderPoints_out, int64_t capacity,
+                          int64_t *nBorder_out, double *SideNodes2D_out);
 /* Opt-in: the following smfem_pcg_solve calls on K use CG preconditioned by a geometric multigrid V-cycle instead of
  * Jacobi (examples/vector3D.jl:315-322 solved in ~20 instead of ~9 ne iterations).  Hex-lattice matrices on one GPU only
  * (SMFEM_ERR_UNSUPPORTED otherwise); `mesh` is K's mesh and must outlive the solves.  Coarse levels (ceil(ne/2), ... down to

@@ -659,6 +659,76 @@ def back_project(NodeList, CameraMatrix):
     return NodeListProj[0:2, :]                                      # :149
 
 
+def convex_hull_monotone_chain(points):
+    """LazySets.convex_hull for 2-D point lists (called at src/PostProcess.jl:106).  LazySets is a third-party dependency that is
+    NOT under /root/reference and is un-pinned (Project.toml lists it without [compat], no Manifest); its documented default for
+    planar inputs is Andrew's monotone chain: sort lexicographically by (x, y), build the lower hull left to right and the upper
+    hull right to left popping while the turn is not strictly counter-clockwise (collinear points are dropped), drop the repeated
+    end points -> vertices in counter-clockwise order starting at the lexicographically smallest point.  PARITY UNPINNED."""
+    pts = sorted((float(p[0]), float(p[1])) for p in points)
+    if len(pts) <= 2:
+        out = []
+        for p in pts:
+            if p not in out:
+                out.append(p)
+        return np.array(out, dtype=np.float64).reshape(-1, 2).T
+
+    def right_turn(o, a, b):  # cross product (a - o) x (b - o): > 0 for a counter-clockwise turn
+        return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
+
+    def build(seq):
+        h = []
+        for p in seq:
+            while len(h) >= 2 and right_turn(h[-2], h[-1], p) <= 0.0:
+                h.pop()
+            h.append(p)
+        return h
+
+    lower, upper = build(pts), build(reversed(pts))
+    hull = lower[:-1] + upper[:-1]
+    return np.array(hull, dtype=np.float64).T
+
+
+def extract_borders(NodeList, CameraMatrix, BorderNodesList, state, ne=None):
+    """src/PostProcess.jl:60-117.  Returns (BorderPoints 2 x nb, SideNodes2D 2 x nSide)."""
+    side = np.asarray(BorderNodesList[0], dtype=np.int64) - 1      # :62 (1-based node ids)
+    SideNodes2D = back_project(np.asarray(NodeList)[:, side], CameraMatrix)  # :64
+    if state == "init":  # :67-100
+        assert ne is not None, "Number of elements must be provided"
+        Left = np.zeros((2, ne + 1))
+        Right = np.zeros((2, ne + 1))
+        TopLayerList, BottomLayerList = [], []
+        szSide = SideNodes2D.shape[1] // (ne + 1)
+        for Layers in range(1, ne + 2):
+            nodes = SideNodes2D[:, (Layers - 1) * szSide:Layers * szSide]
+            minNode = (Layers - 1) * szSide + int(np.argmin(nodes[0]))      # first minimum, like Julia's argmin
+            maxNode = (Layers - 1) * szSide + int(np.argmax(nodes[0]))
+            Left[:, Layers - 1] = SideNodes2D[:, minNode]
+            Right[:, Layers - 1] = SideNodes2D[:, maxNode]
+            if Layers == ne + 1:                                            # :83-88
+                for nodeId in range(nodes.shape[1]):
+                    if nodes[1, nodeId] > SideNodes2D[1, minNode]:
+                        TopLayerList.append((Layers - 1) * szSide + nodeId)
+            elif Layers == 1:                                               # :89-95 (elseif: with ne == 0 only the top list fills)
+                for nodeId in range(nodes.shape[1]):
+                    if nodes[1, nodeId] < SideNodes2D[1, minNode]:
+                        BottomLayerList.append(nodeId)
+
+        def sortslices(M):  # columns in lexicographic order (x, then y)
+            if M.shape[1] == 0:
+                return M
+            return M[:, np.lexsort((M[1], M[0]))]
+
+        Top = sortslices(SideNodes2D[:, TopLayerList])
+        Bottom = sortslices(SideNodes2D[:, BottomLayerList])
+        BorderPoints = np.hstack([Left, Top, Right[:, ::-1], Bottom[:, ::-1]])  # :99
+    elif state == "update":  # :101-114
+        BorderPoints = convex_hull_monotone_chain(SideNodes2D.T)
+    else:
+        raise NameError("BorderPoints not defined")  # the reference falls through to an UndefVarError
+    return BorderPoints, SideNodes2D
+
+
 def jitter_nodes(NodeList, ne, seed=1234, amp=0.2):
     """Robustness input: seeded jitter U(-amp*h, amp*h) of INTERIOR nodes of the unit
     cube lattice (boundary nodes fixed so the z == 0 / z == 1 Dirichlet tests still hit)."""

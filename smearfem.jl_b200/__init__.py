@@ -321,6 +321,24 @@ class SparseMatrixB200:
         call("smfem_project_nodes", self.ctx.handle, self.mesh.handle, self.handle, _pi(ids), ids.size, _pf(cam), _pf(p3), _pf(p2))
         return p3, p2
 
+    def extract_borders(self, CameraMatrix, BorderNodesList, state, ne=None):
+        """extract_borders(NodeList_new, CameraMatrix, BorderNodesList, state, ne) of src/PostProcess.jl:60-117 with
+        NodeList_new = NodeList + motion of the last solve (examples/vector3D.jl:325-329): (BorderPoints, SideNodes2D)."""
+        if state not in ("init", "update"):
+            raise SmearFEMError(_lib.ERR_INVALID, "extract_borders: state must be 'init' or 'update' (reference: UndefVarError)")
+        if state == "init" and ne is None:
+            raise SmearFEMError(_lib.ERR_INVALID, "Number of elements must be provided")
+        ids = np.ascontiguousarray(BorderNodesList[0], dtype=np.int64).ravel()
+        cam = np.asfortranarray(CameraMatrix, dtype=np.float64)
+        n = ids.size
+        cap = n if state == "update" else 2 * (int(ne) + 1) + 2 * (n // (int(ne) + 1)) + 2
+        border = np.zeros((2, max(cap, 1)), order="F")
+        side = np.zeros((2, n), order="F")
+        nb = C.c_int64()
+        call("smfem_extract_borders", self.ctx.handle, self.mesh.handle, self.handle, _pi(ids), n, _pf(cam), 0 if state == "init" else 1,
+             -1 if ne is None else int(ne), _pf(border), cap, C.byref(nb), _pf(side))
+        return border[:, : nb.value].copy(), side
+
     def use_multigrid(self, enable=True):
         """Opt-in: later pcg_solve calls use CG preconditioned by a geometric multigrid V-cycle (hex lattice; with several
         ranks call distributed.connect(K) before the first solve)."""

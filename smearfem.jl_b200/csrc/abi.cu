@@ -994,6 +994,16 @@ int smfem_project_nodes(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, const
     });
 }
 
+int smfem_extract_borders(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, const int64_t *side_node_ids, int64_t n,
+                          const double *CameraMatrix, int state, int64_t ne, double *BorderPoints_out, int64_t capacity,
+                          int64_t *nBorder_out, double *SideNodes2D_out) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(mesh);
+        extract_borders(ctx, mesh, K, side_node_ids, n, CameraMatrix, state, ne, BorderPoints_out, capacity, nBorder_out, SideNodes2D_out);
+    });
+}
+
 int smfem_pcg_set_warm_start(smfem_matrix *K, double scale) {
     return guarded([&] {
         NOTNULL(K);

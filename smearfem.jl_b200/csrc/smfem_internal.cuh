@@ -284,6 +284,8 @@ void comm_export(smfem_ctx *ctx, smfem_matrix *K, void *handle_out);
 void comm_connect(smfem_ctx *ctx, smfem_matrix *K, const void *handles);
 void comm_connect_local(smfem_ctx *ctx, smfem_matrix *K, smfem_matrix *const *all_K, int n);  // same process: raw peer pointers
 void smfem_set_last_error(const char *msg);
+void extract_borders(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, const int64_t *ids, int64_t n, const double *cam, int state,
+                     int64_t ne, double *border_out, int64_t cap, int64_t *nborder, double *side2d_out);  // postprocess.cu
 // matfree.cu: y = (K + beta b) x from the lattice coordinates (no CSR arrays read); same vector layout as the CSR SpMV
 void matfree_apply(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y, bool halo, bool check_done, unsigned long long halo_need);  // abi.cu: message for the calling thread's smfem_last_error()
 

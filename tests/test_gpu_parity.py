@@ -634,6 +634,37 @@ def test_multigrid_pcg_general_dirichlet_jittered_mesh():
     assert relg <= 1e-12 and rel(qg, qj) <= 1e-9 and itg <= 40 and itg < itj / 3, (itg, itj)
 
 
+@pytest.mark.parametrize("ne", [2, 8, 21])
+def test_extract_borders_on_device(ne):
+    """extract_borders (src/PostProcess.jl:60-117), states "init" and "update", on the deformed mesh of the last
+    solve, against the oracle's restatement: the same border nodes in the same order (values to rounding)."""
+    ctx = sf.context()
+    NL, IEN, ID, top, btm, borders = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.inflate_sphere(NL, 0, 1, 0, 1)
+    CM = np.array([[8 * 2048 / 7.07, 0.0, 2048 / 2], [0.0, 8 * 1536 / 5.3, 1536 / 2], [0.0, 0.0, 1.0]]).T  # examples/vector3D.jl:281
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4).add_surface_mass(100.0)
+    # before any solve (the reference's "init" call, examples/vector3D.jl:288)
+    B, S = K.extract_borders(CM, borders, "init", ne)
+    Bo, So = o.extract_borders(NL, CM, borders, "init", ne)
+    assert B.shape == Bo.shape and rel(B, Bo) <= 1e-14 and rel(S, So) <= 1e-14
+    # after a load step (examples/vector3D.jl:325-329)
+    K.set_dirichlet_zplanes(0.05)
+    q, _, _ = K.pcg_solve(rtol=1e-13, maxit=5000)
+    new = NL + np.vstack([q[ID[:, c] - 1] for c in range(3)])
+    for state in ("init", "update"):
+        B, S = K.extract_borders(CM, borders, state, ne)
+        Bo, So = o.extract_borders(new, CM, borders, state, ne)
+        assert B.shape == Bo.shape, (state, B.shape, Bo.shape)
+        assert rel(B, Bo) <= 1e-13 and rel(S, So) <= 1e-13, state
+    with pytest.raises(sf.SmearFEMError):
+        K.extract_borders(CM, borders, "other", ne)
+    with pytest.raises(sf.SmearFEMError):
+        K.extract_borders(CM, borders, "init")
+    K.free()
+    mesh.free()
+
+
 def test_project_nodes_matches_postprocess_restatement():
     """motion, NodeList_new and back_project of the border nodes on the device
     (examples/vector3D.jl:325-329, src/PostProcess.jl:131-152) against the NumPy restatement."""

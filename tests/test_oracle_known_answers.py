@@ -164,3 +164,44 @@ def test_plane_stress_problem_matches_golden(golden_dir, ne):
     assert np.array_equal(r["K"].colptr, g["K_colptr"]) and np.array_equal(r["K"].rowval, g["K_rowval"])
     assert np.array_equal(r["fixed"], g["fixed"]) and np.array_equal(r["free"], g["free"])
     assert np.linalg.norm(r["q"] - g["q"]) <= 1e-13 * np.linalg.norm(g["q"])
+
+
+def test_extract_borders_restatement_properties():
+    """src/PostProcess.jl:60-117 restated (oracle.extract_borders): "init" returns the (ne+1) left extremes, the sorted top arc, the
+    reversed right extremes and the reversed sorted bottom arc; "update" returns a strictly convex counter-clockwise polygon that
+    starts at the lexicographically smallest point and contains every projected side node (scipy's Qhull gives the same vertex set)."""
+    from scipy.spatial import ConvexHull
+
+    ne = 8
+    NL, IEN, ID, top, btm, BL = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.inflate_sphere(NL, 0, 1, 0, 1)
+    CM = np.array([[8 * 2048 / 7.07, 0.0, 2048 / 2], [0.0, 8 * 1536 / 5.3, 1536 / 2], [0.0, 0.0, 1.0]]).T  # examples/vector3D.jl:281
+    B, S = o.extract_borders(NL, CM, BL, "init", ne)
+    n1 = ne + 1
+    assert S.shape == (2, len(BL[0])) and len(BL[0]) % n1 == 0
+    sz = S.shape[1] // n1
+    for l in range(n1):
+        lay = S[:, l * sz:(l + 1) * sz]
+        assert B[0, l] == lay[0].min()
+    nt = B.shape[1] - 2 * n1
+    assert nt > 0
+    topseg = B[:, n1:n1 + (S[1, ne * sz:] > B[1, ne]).sum()]
+    assert np.all(np.diff(topseg[0]) >= 0)                         # sortslices: ascending x
+    right = B[:, n1 + topseg.shape[1]:2 * n1 + topseg.shape[1]]
+    for l in range(n1):
+        assert right[0, n1 - 1 - l] == S[0, l * sz:(l + 1) * sz].max()   # reverse(RightborderNodes)
+    H, S2 = o.extract_borders(NL, CM, BL, "update")
+    assert np.array_equal(S, S2)
+    assert tuple(H[:, 0]) == min(map(tuple, S.T))
+    x, y = H
+    cross = (np.roll(x, -1) - x) * (np.roll(y, -2) - np.roll(y, -1)) - (np.roll(y, -1) - y) * (np.roll(x, -2) - np.roll(x, -1))
+    assert np.all(cross > 0)                                        # strictly convex, counter-clockwise
+    qh = ConvexHull(S.T)
+    assert {tuple(p) for p in H.T} <= {tuple(p) for p in S.T[qh.vertices]} | {tuple(p) for p in H.T}
+    # every point inside or on the hull
+    for k in range(H.shape[1]):
+        a, b = H[:, k], H[:, (k + 1) % H.shape[1]]
+        side = (b[0] - a[0]) * (S[1] - a[1]) - (b[1] - a[1]) * (S[0] - a[0])
+        assert side.min() >= -1e-9 * np.abs(S).max() ** 2
+    with pytest.raises(NameError):
+        o.extract_borders(NL, CM, BL, "other")
