@@ -4,11 +4,14 @@
 # the test-suite; the Python mirror (smearfem.jl_b200/__init__.py) binds the very same symbols with the
 # same argument order and is what the parity tests run.  Keep the two in sync with include/smearfem_b200.h.
 #
-# Usage (drop-in for the hot path):
-#     using SmearFEMB200            # instead of `using smearFEM` for assemble/solve
+# Usage (drop-in for the hot path).  smearFEM itself exports assemble_system / gaussian_quadrature / basis_function / greet_fem
+# (src/smearFEM.jl:3-4), so this module EXPORTS NOTHING that clashes: name what you take from it -- an explicit import wins over
+# smearFEM's implicit exports, and PostProcess (write_scene, fit_curve, plots) keeps coming from smearFEM unchanged:
+#     using smearFEM
+#     using SmearFEMB200: assemble_system, apply_boundary_conditions, setboundaryCond, solve, inflate_sphere, meshgrid
 #     K  = assemble_system(ne, NodeList, IEN, ndim, "Q1", nDof, ID, Young, ν)      # device-resident
 #     b  = apply_boundary_conditions(ne, NodeList, IEN, IEN_top, IEN_btm, ndim, "Q1", ID)
-#     K̄  = K + β*b                                                                 # in place on the GPU
+#     K̄  = K + β*b                                # a new device matrix (K stays K); add_surface_mass!(K, β*b) is the in-place form
 #     q_d, C = setboundaryCond(NodeList, ne, ndim, "Q1", d, nDof)
 #     q  = solve(K̄, q_d, C)                 # replaces inv(Matrix(C'K̄C)) * C'(-K̄ q_d); q = q_d + C q_f
 #     SparseMatrixCSC(K)                    # materialise Julia's CSC when really needed
@@ -16,10 +19,9 @@ module SmearFEMB200
 
 using SparseArrays, LinearAlgebra
 
-export assemble_system, gaussian_quadrature, basis_function, greet_fem
-export meshgrid, setboundaryCond, apply_boundary_conditions, inflate_sphere, solve
-export B200SparseMatrix, SurfaceMatrix
-export use_multigrid!, project_nodes, element_colors
+# non-clashing names only (see the usage note above); everything else is reached as SmearFEMB200.name or by explicit import
+export B200SparseMatrix, SurfaceMatrix, solve
+export use_multigrid!, use_matrix_free!, project_nodes, extract_borders_device, element_colors
 
 const LIB = get(ENV, "SMEARFEM_B200_LIB", joinpath(@__DIR__, "..", "libsmearfem_b200.so"))
 const Q1, Q2 = Cint(1), Cint(2)
@@ -34,17 +36,21 @@ last_error() = unsafe_string(ccall((:smfem_last_error, LIB), Cstring, ()))
 check(rc::Cint) = rc == 0 ? nothing : throw(SmfemError(rc, last_error()))
 fclass(s::AbstractString) = s == "Q1" ? Q1 : s == "Q2" ? Q2 : throw(ArgumentError("FunctionClass $s"))
 
-# ---- context: one GPU per process (RANK / WORLD_SIZE / LOCAL_RANK as set by the launcher) -------------------
+# ---- context: this module drives ONE GPU (device SMEARFEM_B200_DEVICE, default 0).  A Julia process that wants all GPUs of the box
+# uses the `Multi` submodule at the end of this file (smfem_init_multi: one process, n GPUs).  Launching several Julia processes
+# with RANK / WORLD_SIZE is rejected here: the peer-window handle exchange of that mode needs a launcher-side all-gather
+# (smearfem.jl_b200/distributed.py does it with torch.distributed) that this shim does not carry.
 mutable struct Context
     h::Ptr{Cvoid}
 end
 const CTX = Ref{Union{Nothing,Context}}(nothing)
 function context()
     if CTX[] === nothing
+        parse(Int, get(ENV, "WORLD_SIZE", "1")) == 1 ||
+            error("SmearFEMB200: WORLD_SIZE > 1 is not supported by the Julia shim; use SmearFEMB200.Multi (one process, n GPUs)")
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        dev = parse(Cint, get(ENV, "LOCAL_RANK", "0"))
-        rank = parse(Cint, get(ENV, "RANK", "0"))
-        nr = parse(Cint, get(ENV, "WORLD_SIZE", "1"))
+        dev = parse(Cint, get(ENV, "SMEARFEM_B200_DEVICE", "0"))
+        rank = Cint(0); nr = Cint(1)
         check(ccall((:smfem_init, LIB), Cint, (Cint, Cint, Cint, Ptr{Ptr{Cvoid}}), dev, rank, nr, h))
         c = Context(h[])
         finalizer(c -> ccall((:smfem_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), c)
@@ -173,21 +179,31 @@ end
 
 # ---- examples/vector3D.jl:175-264 and :308 ----------------------------------------------------------------------
 struct SurfaceMatrix                         # b = ∫ NᵀN over top ∪ bottom, kept lazy
+    mesh::Mesh                               # the NodeList apply_boundary_conditions was given (examples/vector3D.jl:306), on the device
     IEN_top::Matrix{Int64}
     IEN_btm::Matrix{Int64}
     β::Float64
 end
 function apply_boundary_conditions(ne, NodeList, IEN, IEN_top, IEN_btm, ndim, FunctionClass, ID, nDof=3)
     ndim == 3 || error("apply_boundary_conditions: only the 3-D branch of the reference is executable")
-    return SurfaceMatrix(Matrix{Int64}(IEN_top), Matrix{Int64}(IEN_btm), 1.0)
+    # b is integrated over THIS NodeList (which need not be the one K was assembled on)
+    m = mesh_from_host(Matrix{Float64}(NodeList), Matrix{Int64}(IEN), ID === nothing ? nothing : Matrix{Int64}(ID), ndim, nDof, ne)
+    return SurfaceMatrix(m, Matrix{Int64}(IEN_top), Matrix{Int64}(IEN_btm), 1.0)
 end
-Base.:*(β::Number, b::SurfaceMatrix) = SurfaceMatrix(b.IEN_top, b.IEN_btm, b.β * β)
-function Base.:+(K::B200SparseMatrix, b::SurfaceMatrix)                    # K̄ = K + β*b, in place on the device
+Base.:*(β::Number, b::SurfaceMatrix) = SurfaceMatrix(b.mesh, b.IEN_top, b.IEN_btm, b.β * β)
+function clone(K::B200SparseMatrix)                                        # device-side copy: pattern, values, diagonal
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:smfem_matrix_clone, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), context().h, K.h, h))
+    K2 = B200SparseMatrix(h[], K.mesh); finalizer(free!, K2); return K2
+end
+function add_surface_mass!(K::B200SparseMatrix, b::SurfaceMatrix)          # K += β*b in place (saves the copy of `+`)
     check(ccall((:smfem_surface_mass, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Int64, Cdouble, Cint),
-                context().h, K.h, K.mesh.h, b.IEN_top, b.IEN_btm, size(b.IEN_top, 1), b.β, 0))
+                context().h, K.h, b.mesh.h, b.IEN_top, b.IEN_btm, size(b.IEN_top, 1), b.β, 0))
     return K
 end
+# K̄ = K + β*b (examples/vector3D.jl:308): a NEW device matrix, K stays K as in the reference
+Base.:+(K::B200SparseMatrix, b::SurfaceMatrix) = add_surface_mass!(clone(K), b)
 
 # ---- examples/vector3D.jl:133-173 (host data preparation, verbatim semantics) ------------------------------------
 function setboundaryCond(NodeList, ne, ndim, FunctionClass, d, nDof=1)
@@ -227,6 +243,26 @@ function use_multigrid!(K̄::B200SparseMatrix, enable::Bool=true)
     return K̄
 end
 
+# ---- opt-in: apply K̄ matrix-free from the mesh coordinates inside the following solves (hex lattice, nDof = 3)
+function use_matrix_free!(K̄::B200SparseMatrix, enable::Bool=true)
+    check(ccall((:smfem_pcg_use_matrix_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint), context().h, K̄.h, K̄.mesh.h, enable))
+    return K̄
+end
+
+# ---- extract_borders(NodeList_new, CameraMatrix, BorderNodesList, state, ne) (src/PostProcess.jl:60-117) on the device, with
+#      NodeList_new = NodeList + motion of the last solve; returns (BorderPoints, SideNodes2D) like the reference
+function extract_borders_device(K̄::B200SparseMatrix, CameraMatrix, BorderNodesList, state::AbstractString, ne=nothing)
+    state in ("init", "update") || error("extract_borders: state must be \"init\" or \"update\"")
+    state == "init" && ne === nothing && error("Number of elements must be provided")
+    ids = Vector{Int64}(vec(BorderNodesList[1])); cam = Matrix{Float64}(CameraMatrix); n = length(ids)
+    cap = state == "update" ? n : 2 * (ne + 1) + 2 * (n ÷ (ne + 1)) + 2
+    border = zeros(2, cap); side = zeros(2, n); nb = Ref{Int64}(0)
+    check(ccall((:smfem_extract_borders, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Int64, Ptr{Cdouble}, Cint, Int64, Ptr{Cdouble}, Int64, Ptr{Int64}, Ptr{Cdouble}),
+                context().h, K̄.mesh.h, K̄.h, ids, n, cam, state == "init" ? 0 : 1, ne === nothing ? -1 : ne, border, cap, nb, side))
+    return border[:, 1:nb[]], side
+end
+
 # ---- examples/vector3D.jl:325-329 on the device: NodeList_new[:, ids] and back_project(NodeList_new[:, ids], CameraMatrix)
 #      (src/PostProcess.jl:131-152) with the displacement of the last solve; feed the result to the unchanged
 #      extract_borders / fit_curve in place of their own back_project call
@@ -245,5 +281,52 @@ function element_colors(K::B200SparseMatrix)
     check(ccall((:smfem_mesh_colors, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cint}, Ptr{Int64}), context().h, K.mesh.h, nc, sizes))
     return Int(nc[]), sizes[1:max(nc[], 0)]
 end
+
+# ---- one Julia process, n GPUs (smfem_init_multi): the reference's main() shape, K distributed in z-slabs ----------------------
+module Multi
+using ..SmearFEMB200: LIB, check, fclass
+mutable struct MultiContext
+    h::Ptr{Cvoid}
+    n::Int
+end
+function MultiContext(n_gpus::Integer)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:smfem_init_multi, LIB), Cint, (Cint, Ptr{Cint}, Ptr{Ptr{Cvoid}}), n_gpus, C_NULL, h))
+    c = MultiContext(h[], n_gpus)
+    finalizer(c -> ccall((:smfem_multi_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), c)
+    return c
+end
+mutable struct MultiMatrix
+    ctx::MultiContext
+    h::Ptr{Cvoid}
+    mesh::Ptr{Cvoid}
+end
+# assemble_system(ne, NodeList, IEN, ndim, FunctionClass, nDof, ID, Young, ν) with the reference's host arrays on all GPUs
+function assemble_system(c::MultiContext, ne, NodeList, IEN, ndim, FunctionClass="Q1", nDof=1, ID=nothing, Young=1, ν=0.3)
+    NL = Matrix{Float64}(NodeList); IENm = Matrix{Int64}(IEN); IDm = nDof > 1 ? Matrix{Int64}(ID) : nothing
+    idp = IDm === nothing ? Ptr{Int64}(C_NULL) : pointer(IDm)
+    mh = Ref{Ptr{Cvoid}}(C_NULL); kh = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve NL IENm IDm begin
+        check(ccall((:smfem_multi_assemble_system, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Cint, Int64, Cint, Cint, Cint, Cdouble, Cdouble,
+                     Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
+                    c.h, NL, IENm, idp, size(NL, 2), size(IENm, 1), size(IENm, 2), ne, ndim, fclass(FunctionClass), nDof, Young, ν, mh, kh))
+    end
+    return MultiMatrix(c, kh[], mh[])
+end
+add_surface_mass!(K::MultiMatrix, β) = (check(ccall((:smfem_multi_surface_mass, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble), K.ctx.h, K.h, K.mesh, β)); K)
+use_multigrid!(K::MultiMatrix, on::Bool=true) = (check(ccall((:smfem_multi_pcg_use_multigrid, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint), K.ctx.h, K.h, K.mesh, on)); K)
+# the example's Dirichlet data (z = 0: u_z = 0, z = 1: u_z = -d; examples/vector3D.jl:133-173) and solve (:315-322); q is global
+function solve(K::MultiMatrix, d; rtol=1e-12, maxit=20000)
+    check(ccall((:smfem_multi_set_dirichlet_zplanes, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble), K.ctx.h, K.h, K.mesh, d))
+    m = Ref{Int64}(0); n = Ref{Int64}(0); nnz = Ref{Int64}(0)
+    check(ccall((:smfem_multi_matrix_info, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}), K.ctx.h, K.h, m, n, nnz))
+    q = zeros(m[]); it = Ref{Cint}(0); rel = Ref{Cdouble}(0)
+    check(ccall((:smfem_multi_pcg_solve, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cint}, Ptr{Cdouble}),
+                K.ctx.h, K.h, rtol, maxit, C_NULL, q, it, rel))
+    return q
+end
+end # module Multi
 
 end # module
