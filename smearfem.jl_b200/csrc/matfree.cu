@@ -11,6 +11,7 @@
 // Several ranks: a rank applies the element layers [k0-1, k1) of its slab and keeps the rows of its owned node planes; x carries
 // the ghost planes exactly as for the CSR SpMV (same halo exchange), the ghost layer is recomputed instead of communicated.
 #include <cmath>
+#include <cstdlib>
 
 #include "smfem_internal.cuh"
 
@@ -126,6 +127,164 @@ __global__ void __launch_bounds__(128) k_matfree_color(const __grid_constant__ M
     }
 }
 
+// Second form of the element kernel: the trilinear maps in MONOMIAL coordinates.  With phi = {1, xi, eta, zeta, xi eta, xi zeta,
+// eta zeta, xi eta zeta} and c = W F / 8 (W = the 8 x 8 sign matrix of the corner shape functions, a 3-stage butterfly), the
+// reference gradient of a nodal field F is
+//     dF/dxi = c1 + c4 eta + c5 zeta + c7 eta zeta,   dF/deta = c2 + c4 xi + c6 zeta + c7 xi zeta,   dF/dzeta = c3 + c5 xi + c6 eta + c7 xi eta
+// i.e. 9 FMA per column instead of 24, for the Jacobian (F = coordinates) and for the displacement gradient (F = x) alike, and
+// the test side accumulates t_m += P[:, k] dphi_m/dxi_k in the same 7 monomials (36 instead of 72 operations per Gauss point),
+// transformed back to the 8 nodes once per element (y = W' t / 8).  63 persistent doubles (c for X and U, t) instead of 96.
+__device__ __forceinline__ void corner_to_monomial(const double (&F)[8][3], double (&c)[8][3]) {
+    // natural corner order u = ox + 2 oy + 4 oz; N_u = (1 + sx xi)(1 + sy eta)(1 + sz zeta) / 8
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = F[u][i];
+        // butterfly along x, y, z: sums -> even monomial power, differences -> odd
+        double b[8], d[8];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            b[2 * p] = a[2 * p + 1] + a[2 * p];
+            b[2 * p + 1] = a[2 * p + 1] - a[2 * p];
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                d[4 * p + x] = b[4 * p + 2 + x] + b[4 * p + x];
+                d[4 * p + 2 + x] = b[4 * p + 2 + x] - b[4 * p + x];
+            }
+        // index bits now: bit0 = x power, bit1 = y power; finish with z
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double lo = d[q], hi = d[4 + q];
+            const double sum = 0.125 * (hi + lo), dif = 0.125 * (hi - lo);
+            // monomial numbering m: 0:1 1:xi 2:eta 3:zeta 4:xi eta 5:xi zeta 6:eta zeta 7:xi eta zeta
+            const int m_sum = q == 0 ? 0 : (q == 1 ? 1 : (q == 2 ? 2 : 4));
+            const int m_dif = q == 0 ? 3 : (q == 1 ? 5 : (q == 2 ? 6 : 7));
+            c[m_sum][i] = sum;
+            c[m_dif][i] = dif;
+        }
+    }
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_matfree_color2(const __grid_constant__ MfArgs A) {
+    if (A.check_done && A.scal->done) return;
+    const Lattice &L = A.L;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)A.nx * A.ny * A.nz) return;
+    const int tx = (int)(t % A.nx), ty = (int)((t / A.nx) % A.ny), tz = (int)(t / ((int64_t)A.nx * A.ny));
+    const int ex = 2 * tx + A.cx, ey = 2 * ty + A.cy, ez = A.ez0 + 2 * tz;
+    const int64_t n0 = L.lnode(ex, ey, ez);
+    const int64_t sy = L.n1, sz = L.plane();
+    double cX[8][3], cU[8][3];
+    {
+        double F[8][3];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int64_t ln = n0 + (u & 1) + ((u >> 1) & 1) * sy + (u >> 2) * sz;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) F[u][c] = A.coords[3 * ln + c];
+        }
+        corner_to_monomial(F, cX);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int64_t ln = n0 + (u & 1) + ((u >> 1) & 1) * sy + (u >> 2) * sz;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) F[u][c] = A.x[3 * ln + c];
+        }
+        corner_to_monomial(F, cU);
+    }
+    double T[8][3];  // test-side accumulators in the monomials 1..7 (T[0] stays 0)
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) T[m][i] = 0.0;
+#pragma unroll 1
+    for (int gp = 0; gp < 8; ++gp) {
+        const double xi = (gp & 1) ? A.gpc : -A.gpc, eta = (gp & 2) ? A.gpc : -A.gpc, zeta = (gp & 4) ? A.gpc : -A.gpc;
+        const double xe = xi * eta, xz = xi * zeta, ez_ = eta * zeta;
+        double J[9], G[9];  // [r][k]: d x_r / d xi_k and d u_r / d xi_k
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            J[r * 3 + 0] = cX[1][r] + cX[4][r] * eta + cX[5][r] * zeta + cX[7][r] * ez_;
+            J[r * 3 + 1] = cX[2][r] + cX[4][r] * xi + cX[6][r] * zeta + cX[7][r] * xz;
+            J[r * 3 + 2] = cX[3][r] + cX[5][r] * xi + cX[6][r] * eta + cX[7][r] * xe;
+            G[r * 3 + 0] = cU[1][r] + cU[4][r] * eta + cU[5][r] * zeta + cU[7][r] * ez_;
+            G[r * 3 + 1] = cU[2][r] + cU[4][r] * xi + cU[6][r] * zeta + cU[7][r] * xz;
+            G[r * 3 + 2] = cU[3][r] + cU[5][r] * xi + cU[6][r] * eta + cU[7][r] * xe;
+        }
+        double adj[9];
+        adj[0] = J[4] * J[8] - J[5] * J[7];
+        adj[1] = J[2] * J[7] - J[1] * J[8];
+        adj[2] = J[1] * J[5] - J[2] * J[4];
+        adj[3] = J[5] * J[6] - J[3] * J[8];
+        adj[4] = J[0] * J[8] - J[2] * J[6];
+        adj[5] = J[2] * J[3] - J[0] * J[5];
+        adj[6] = J[3] * J[7] - J[4] * J[6];
+        adj[7] = J[1] * J[6] - J[0] * J[7];
+        adj[8] = J[0] * J[4] - J[1] * J[3];
+        const double det = J[0] * adj[0] + J[1] * adj[3] + J[2] * adj[6];
+        const double f = 1.0 / fabs(det);
+        double H[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) H[i * 3 + c] = G[i * 3] * adj[c] + G[i * 3 + 1] * adj[3 + c] + G[i * 3 + 2] * adj[6 + c];
+        const double tr = A.lam * (H[0] + H[4] + H[8]);
+        double S[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) S[i * 3 + c] = f * (A.mu * (H[i * 3 + c] + H[c * 3 + i]) + (i == c ? tr : 0.0));
+        double P[9];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) P[i * 3 + k] = S[i * 3] * adj[k * 3] + S[i * 3 + 1] * adj[k * 3 + 1] + S[i * 3 + 2] * adj[k * 3 + 2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double p0 = P[i * 3], p1 = P[i * 3 + 1], p2 = P[i * 3 + 2];
+            T[1][i] += p0;
+            T[2][i] += p1;
+            T[3][i] += p2;
+            T[4][i] += p0 * eta + p1 * xi;
+            T[5][i] += p0 * zeta + p2 * xi;
+            T[6][i] += p1 * zeta + p2 * eta;
+            T[7][i] += p0 * ez_ + p1 * xz + p2 * xe;
+        }
+    }
+    // y_u = sum_m W[u][m] T[m] / 8 with W[u][m] = the sign product of monomial m at corner u; the same butterfly, transposed
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        // z stage: (m_sum, m_dif) pairs as in corner_to_monomial
+        const double s0 = T[0][i], s1 = T[1][i], s2 = T[2][i], s3 = T[4][i];   // even in zeta: 1, xi, eta, xi eta
+        const double d0 = T[3][i], d1 = T[5][i], d2 = T[6][i], d3 = T[7][i];   // odd in zeta
+        double lo[4] = {s0 - d0, s1 - d1, s2 - d2, s3 - d3}, hi[4] = {s0 + d0, s1 + d1, s2 + d2, s3 + d3};
+        double yv[8];
+#pragma unroll
+        for (int oz = 0; oz < 2; ++oz) {
+            const double *v = oz ? hi : lo;  // [1, xi, eta, xi eta] coefficients on this z face
+            const double e0 = v[0] - v[2], e1 = v[1] - v[3], f0 = v[0] + v[2], f1 = v[1] + v[3];  // eta = -1 / +1
+            yv[4 * oz + 0] = e0 - e1;
+            yv[4 * oz + 1] = e0 + e1;
+            yv[4 * oz + 2] = f0 - f1;
+            yv[4 * oz + 3] = f0 + f1;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int k = ez + (u >> 2);
+            if (k < L.k0 || k >= L.k1) continue;
+            const int64_t ln = n0 + (u & 1) + ((u >> 1) & 1) * sy + (u >> 2) * sz;
+            // exactly one contribution per address and launch (same-colour elements share no node), launches are ordered: the
+            // reduction (RED.ADD.F64, no load, no wait) is as deterministic as a load-add-store and hides the latency of y
+            atomicAdd(A.y + 3 * (ln - sz) + i, 0.125 * yv[u]);
+        }
+    }
+}
+
 // y += beta b x on the z = 0 / z = 1 faces (examples/vector3D.jl:193-262): one thread per node of a boundary plane gathers from
 // its <= 4 faces; be = sum_g w_g |t1 x t2| N'N with the 2x2 rule, the same scalar mass for the three displacement components
 __global__ void k_matfree_surface(const __grid_constant__ MfArgs A, int do_bottom, int do_top) {
@@ -221,6 +380,9 @@ void matfree_apply(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y, 
     if (halo && ctx->nranks > 1) LAUNCH(ctx, k_matfree_wait_halo, 1, 1, 0, K->comm, K->scal, A.check_done, halo_need);
     CUDA_CHECK(cudaMemsetAsync(y, 0, sizeof(double) * K->nrows_l, ctx->stream));
     const int l0 = L.k0 > 0 ? L.k0 - 1 : 0, l1 = L.k1 - 1 < L.ne - 1 ? L.k1 - 1 : L.ne - 1;  // element layers [l0, l1] of this rank
+    const char *ver = std::getenv("SMFEM_MATFREE");  // "v1": the first (corner-form) element kernel, kept for A/B timing
+    const bool v1 = ver && ver[0] == 'v' && ver[1] == '1';
+    const int cfg = (ver && ver[0] == 'c') ? std::atoi(ver + 1) : 0;  // "c1".."c3": launch-shape experiments of the monomial kernel
     for (int c = 0; c < 8; ++c) {
         A.cx = c & 1;
         A.cy = (c >> 1) & 1;
@@ -232,7 +394,11 @@ void matfree_apply(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y, 
         A.nz = A.ez0 > l1 ? 0 : (l1 - A.ez0) / 2 + 1;
         const int64_t n = (int64_t)A.nx * A.ny * A.nz;
         if (n <= 0) continue;
-        LAUNCH(ctx, k_matfree_color, (unsigned)((n + 127) / 128), 128, 0, A);
+        if (v1) LAUNCH(ctx, k_matfree_color, (unsigned)((n + 127) / 128), 128, 0, A);
+        else if (cfg == 1) LAUNCH(ctx, (k_matfree_color2<128, 4>), (unsigned)((n + 127) / 128), 128, 0, A);
+        else if (cfg == 2) LAUNCH(ctx, (k_matfree_color2<64, 6>), (unsigned)((n + 63) / 64), 64, 0, A);
+        else if (cfg == 3) LAUNCH(ctx, (k_matfree_color2<64, 8>), (unsigned)((n + 63) / 64), 64, 0, A);
+        else LAUNCH(ctx, (k_matfree_color2<128, 3>), (unsigned)((n + 127) / 128), 128, 0, A);
     }
     const int bot = (L.k0 == 0), top = (L.k1 == L.n1);
     if (A.beta != 0.0 && (bot || top)) {

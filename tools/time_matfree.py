@@ -11,9 +11,15 @@ mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).inflate_sphere(0, 1, 0, 1)
 K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
 K.add_surface_mass(100.0).set_dirichlet_zplanes(0.001)
 K.use_matrix_free(True).use_matrix_free(False)   # names the mesh; bench_spmv variant 5 switches the operator itself
-for v, name in ((4, "CSR row-triple"), (5, "matrix-free")):
+for v, name, env in ((4, "CSR row-triple", None), (5, "matrix-free (corner form, v1)", "v1"), (5, "matrix-free (monomial form)", None),
+                     (5, "monomial, 128 thr x 4/SM (128 regs)", "c1"), (5, "monomial, 64 thr x 6/SM", "c2"), (5, "monomial, 64 thr x 8/SM", "c3")):
+    if env:
+        os.environ["SMFEM_MATFREE"] = env
+    else:
+        os.environ.pop("SMFEM_MATFREE", None)
     ms = K.bench_spmv(reps=30, variant=v)
-    print(f"{name:16s}: {ms:.4f} ms per application", flush=True)
+    print(f"{name:36s}: {ms:.4f} ms per application", flush=True)
+os.environ.pop("SMFEM_MATFREE", None)
 for mf in (False, True):
     K.use_matrix_free(mf)
     _, it, rr = K.pcg_solve(rtol=1e-10, maxit=20000, want_q=False)
