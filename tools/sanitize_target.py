@@ -23,7 +23,17 @@ for ne in (5, 9):
         K.reassemble(40, 0.4)
         nzm = K.to_csc()[2]
         assert np.linalg.norm(nzm - r["K"].nzval) <= 1e-12 * np.linalg.norm(nzm), tile
+    for tile in ("v2base", "v2l", "v2i", "v2s", "v2"):   # layer-march kernel: all instantiations (round 2)
+        os.environ["SMFEM_TILE"] = tile
+        K.reassemble(40, 0.4)
+        nzv = K.to_csc()[2]
+        assert np.linalg.norm(nzv - r["K"].nzval) <= 1e-12 * np.linalg.norm(nzv), tile
     os.environ.pop("SMFEM_TILE")
+    os.environ["SMFEM_COLIND_SIDE"] = "1"   # persistent closed-form colind kernel on the side stream beside the value kernel
+    K.reassemble(40, 0.4)
+    assert np.array_equal(K.to_csc()[2], nzv)
+    os.environ.pop("SMFEM_COLIND_SIDE")
+    nz = K.to_csc()[2]
     # the one-call host route: streamed NodeList (watermark polling), hybrid lattice check on the copy stream
     NLh, IENh, IDh, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
     o.inflate_sphere(NLh, 0, 1, 0, 1)
@@ -47,6 +57,28 @@ for ne in (5, 9):
     qg, itg, relg = K.pcg_solve(rtol=1e-12, maxit=200)
     assert np.linalg.norm(qg - 2 * r["q"]) <= 1e-9 * np.linalg.norm(qg) and itg < 60, itg
     K.use_multigrid(False)
+    # matrix-free operator (both element kernels), inside Jacobi-PCG and the multigrid cycle; clone; border extraction
+    for ver in ("v1", None):
+        if ver:
+            os.environ["SMFEM_MATFREE"] = ver
+        else:
+            os.environ.pop("SMFEM_MATFREE", None)
+        K.use_matrix_free(True)
+        qm, itm, relm = K.pcg_solve(rtol=1e-12, maxit=2000)
+        assert np.linalg.norm(qm - 2 * r["q"]) <= 1e-9 * np.linalg.norm(qm), ver
+        K.use_multigrid(True)
+        qm, itm, relm = K.pcg_solve(rtol=1e-12, maxit=200)
+        assert np.linalg.norm(qm - 2 * r["q"]) <= 1e-9 * np.linalg.norm(qm), ver
+        K.use_multigrid(False)
+        K.use_matrix_free(False)
+    Kc = K.clone()
+    assert np.array_equal(Kc.to_csc()[2], K.to_csc()[2])
+    Kc.free()
+    borders = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)[5]
+    CM = np.array([[8 * 2048 / 7.07, 0.0, 2048 / 2], [0.0, 8 * 1536 / 5.3, 1536 / 2], [0.0, 0.0, 1.0]]).T
+    for state in ("init", "update"):
+        B, S = K.extract_borders(CM, borders, state, ne)
+        assert B.shape[1] > 4
     K.free(); mesh.free()
 # general path (permuted ids), 2-D, scalar
 NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, 4, 3)
