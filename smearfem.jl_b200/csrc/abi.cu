@@ -385,7 +385,7 @@ int smfem_mesh_from_host(smfem_ctx *ctx, const double *NodeList, const int64_t *
                 LAUNCH(ctx, k_max_i64, (unsigned)((nNodes * nDof + 255) / 256), 256, 0, nNodes * nDof, (const int64_t *)d_id, d_max);
                 CUDA_CHECK(cudaMemcpyAsync(&m->ndof_id, d_max, 8, cudaMemcpyDeviceToHost, ctx->stream));
                 CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-                cudaFree(d_max);
+                dev_free(d_max);  // from dev_alloc: through the allocator (keeps its bookkeeping consistent)
             }
             if (ID && std_id) m->nDof_id = nDof;
             m->std_id = (ID == nullptr) || std_id;

@@ -55,20 +55,28 @@ void *dev_cache_alloc(size_t bytes) {
 
 void dev_cache_free(void *p) {
     size_t bytes = 0;
+    bool park = false;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto it = g_live.find(p);
         if (it != g_live.end()) {
             bytes = it->second;
             g_live.erase(it);
-            if (bytes >= CACHE_MIN && g_cached_bytes + bytes <= CACHE_MAX) {
-                g_free.emplace(cache_key(bytes), p);  // stream-ordered reuse is safe: the library uses ONE stream per context
-                g_cached_bytes += bytes;
-                return;
-            }
+            park = bytes >= CACHE_MIN && g_cached_bytes + bytes <= CACHE_MAX;
+            if (park) g_cached_bytes += bytes;  // reserve the room now, publish the block below
         }
     }
-    cudaFree(p);
+    if (!park) {
+        cudaFree(p);
+        return;
+    }
+    // A context has two streams (main + copy stream) and several contexts may share a device, so a parked block may be handed
+    // to a DIFFERENT stream than the one that last used it: drain the device first (what cudaFree would have done implicitly;
+    // big blocks are freed at the end of a step, after its results were read).  Outside the lock: another rank's host thread
+    // (smfem_init_multi) must be able to allocate while this device finishes.
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_free.emplace(cache_key(bytes), p);
 }
 
 void dev_cache_release() {
