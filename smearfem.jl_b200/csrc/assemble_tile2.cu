@@ -30,7 +30,10 @@
 
 namespace {
 
-// NTHv: threads per CTA (a warp owns 4 x 2 node columns: tile = 4 x 2 NTHv/32).  OPT bit 1: conflict-free shared-memory layout
+// NTHv: threads per CTA (a warp owns 4 x 2 node columns: tile = 4 x 2 NTHv/32).  OPT bit 4: the node's own gradient on the swept
+// face is loaded (conflict-free thanks to the pads) instead of selected out of the four loaded ones (18 selects per Gauss point);
+// bit 8: the words of a coordinate plane a thread stages are computed once per CTA; bit 16: no register copy of the carried blocks
+// before they are emitted (second instantiation of emit_level; costs registers, slower).  OPT bit 1: conflict-free shared-memory layout
 // (rows of the 4 nodes of a face padded so that the per-slot g_a loads of a half-warp hit 16 distinct bank pairs; Gauss-point
 // stride == 2 mod 16 and phase-1 tasks numbered element-major, so that the 8 Gauss points of an element read the same
 // coordinates (broadcast) and store to 8 distinct bank pairs); bit 2: compile-time section strides on interior planes.
@@ -149,7 +152,7 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int mask) { return __sh
 //   Other[q] += g_o g_b'   g_o = g_a of this column's node on the other face (loaded): the dz = 2 face - 1 blocks of
 //                          plane lay + 1 - face                                    (q = in-plane reference number of b)
 template <class T>
-__device__ __forceinline__ void sweep(const double *Sf, const double *So, int aq, double (&Same)[4][9], double (&Other)[4][9]) {
+__device__ __forceinline__ void sweep(const double *Sf, const double *So, const double *Ss, int aq, double (&Same)[4][9], double (&Other)[4][9]) {
     constexpr int NELP = T::NELP;
 #pragma unroll 2
     for (int gp = 0; gp < 8; ++gp) {
@@ -162,7 +165,8 @@ __device__ __forceinline__ void sweep(const double *Sf, const double *So, int aq
         double gs[3], go[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            gs[c] = (aq & 2) ? ((aq & 1) ? gb[3][c] : gb[2][c]) : ((aq & 1) ? gb[1][c] : gb[0][c]);
+            // g_a on the swept face: one of the loaded g_b (3 x 6 selects), or - OPT 4 - its own conflict-free load
+            gs[c] = (T::OPT & 4) ? Ss[gp * T::GS + c * NELP] : ((aq & 2) ? ((aq & 1) ? gb[3][c] : gb[2][c]) : ((aq & 1) ? gb[1][c] : gb[0][c]));
             go[c] = So[gp * T::GS + c * NELP];
         }
 #pragma unroll
@@ -385,10 +389,37 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile2(const __grid_cons
         }
     };
 
+    // coordinate staging: which words of a node plane this thread copies does not depend on the plane (OPT 8: computed once)
+    constexpr int NSTG = (T2::PLANE + NTH - 1) / NTH;
+    int stg_src[NSTG];
+    if (T2::OPT & 8) {
+#pragma unroll
+        for (int q = 0; q < NSTG; ++q) {
+            const int t = tid + q * NTH;
+            const int c = t % 3, n = t / 3, px = n % T2::PX, py = n / T2::PX;
+            const int gx = X0 - 1 + px, gy = Y0 - 1 + py;
+            stg_src[q] = (t < T2::PLANE && gx >= 0 && gy >= 0 && gx < L.n1 && gy < L.n1) ? 3 * (gy * L.n1 + gx) + c : -1;
+        }
+    }
+    auto stage = [&](int k) {
+        if (!(T2::OPT & 8)) {
+            stage_plane<T2>(A, s_xyz, k, X0, Y0);
+            return;
+        }
+        if (k < 0 || k >= L.n1 || k > L.k1) return;  // the slab holds planes k0-1 .. k1
+        const double *src = A.coords + 3 * (int64_t)(k - L.k0 + 1) * L.n1 * L.n1;
+        double *dst = s_xyz + (k & 3) * T2::PLANE + tid;
+#pragma unroll
+        for (int q = 0; q < NSTG; ++q)
+            if (stg_src[q] >= 0) {
+                unsigned d = (unsigned)__cvta_generic_to_shared(dst + q * NTH);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src + stg_src[q]) : "memory");
+            }
+    };
     const int L0 = max(zs - 1, 0), L1 = min(ze - 1, L.ne - 1);  // element layers this CTA sweeps (inclusive)
     wait_plane(min(L0 + 1, L.n1 - 1));
-    stage_plane<T2>(A, s_xyz, L0, X0, Y0);
-    stage_plane<T2>(A, s_xyz, L0 + 1, X0, Y0);
+    stage(L0);
+    stage(L0 + 1);
 
     double Same[4][9], Other[4][9];  // dz = 0 blocks (carried from a layer's top sweep into the next layer's bottom sweep) / dz = -+1 blocks
 #pragma unroll
@@ -406,13 +437,29 @@ __global__ void __launch_bounds__(T::NTH, MINB) k_values_tile2(const __grid_cons
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncthreads();  // everybody is done with the previous layer in S; coordinate planes lay, lay + 1 have landed
             if (lay + 2 < L.n1 && lay + 2 <= L.k1) wait_plane(lay + 2);
-            if (lay + 1 <= L1) stage_plane<T2>(A, s_xyz, lay + 2, X0, Y0);  // lands during this layer's sweeps
+            if (lay + 1 <= L1) stage(lay + 2);  // lands during this layer's sweeps
             if (!(A.skip & 1)) phase1_layer<T2>(A, s_gp, s_w, s_xyz, S, lay, X0, Y0);
             __syncthreads();
         }
         if (real && el_ok && !(A.skip & 2))
-            sweep<T2>(Se + face * T2::FACE, Se + (1 - face) * T2::FACE + boff_aq, aq, Same, Other);
+            sweep<T2>(Se + face * T2::FACE, Se + (1 - face) * T2::FACE + boff_aq, Se + face * T2::FACE + boff_aq, aq, Same, Other);
         // face 0: Other = dz -1 of plane lay + 1, then Same = dz 0 of plane lay (complete);  face 1: Other = dz +1 of plane lay
+        if (T2::OPT & 16) {  // the carried blocks are emitted from their own registers (no copy into Other; emit_level instantiated twice)
+            const int po = lay + 1 - face, dzo = 2 * face - 1;
+            if (po >= zs && po < ze) emit_level<T2>(A, G, Other, stage_w, lane, ix, iy, po, dzo, jx0, jy0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int m = 0; m < 9; ++m) Other[q][m] = 0.0;
+            if (face == 0) {
+                if (lay >= zs && lay < ze) emit_level<T2>(A, G, Same, stage_w, lane, ix, iy, lay, 0, jx0, jy0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int m = 0; m < 9; ++m) Same[q][m] = 0.0;
+            }
+            continue;
+        }
 #pragma unroll 1
         for (int rep = 0; rep < 2; ++rep) {
             int p = lay + 1 - face, dz = 2 * face - 1;
@@ -465,12 +512,19 @@ static void launch_tile2(smfem_ctx *ctx, TileArgs &A, int nown) {
 }
 
 // The default structured value kernel; SMFEM_TILE = 4x4 / 8x4 / mma* select the earlier kernels (returns false then).
-// SMFEM_TILE = v2 (default: 128-thread CTAs, all layout / addressing optimisations), v2base (the first layer-march version),
-// v2l / v2i (one optimisation each), v2s (64-thread CTAs, 4 per SM): kept selectable for A/B timing (tools/time_tile2.py)
+// SMFEM_TILE = v2 (default: 128-thread CTAs, OPT 15 = conflict-free layout + compile-time strides + own-gradient load + staging
+// plan), v2base (the first layer-march version), v2l / v2i / v2li / v2g / v2p (subsets), v2s (64-thread CTAs, 4 per SM),
+// v2e / v2all (carried blocks emitted from their own registers: 255 registers, slower): kept selectable for A/B timing
+// (tools/time_tile2.py, profiles/r2_tile2_variants.txt); all give the same bits
 bool values_assemble_tile2(smfem_ctx *ctx, TileArgs &A, int nown) {
     const char *sel = std::getenv("SMFEM_TILE");  // read per call: tests switch kernels inside one process
     const std::string m = (!sel || !sel[0]) ? "v2" : sel;
-    if (m == "v2") launch_tile2<T2<128, 3>, 2>(ctx, A, nown);
+    if (m == "v2") launch_tile2<T2<128, 15>, 2>(ctx, A, nown);
+    else if (m == "v2li") launch_tile2<T2<128, 3>, 2>(ctx, A, nown);
+    else if (m == "v2g") launch_tile2<T2<128, 7>, 2>(ctx, A, nown);
+    else if (m == "v2p") launch_tile2<T2<128, 11>, 2>(ctx, A, nown);
+    else if (m == "v2e") launch_tile2<T2<128, 19>, 2>(ctx, A, nown);
+    else if (m == "v2all") launch_tile2<T2<128, 31>, 2>(ctx, A, nown);
     else if (m == "v2base") launch_tile2<T2<128, 0>, 2>(ctx, A, nown);
     else if (m == "v2l") launch_tile2<T2<128, 1>, 2>(ctx, A, nown);
     else if (m == "v2i") launch_tile2<T2<128, 2>, 2>(ctx, A, nown);

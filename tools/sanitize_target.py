@@ -23,7 +23,7 @@ for ne in (5, 9):
         K.reassemble(40, 0.4)
         nzm = K.to_csc()[2]
         assert np.linalg.norm(nzm - r["K"].nzval) <= 1e-12 * np.linalg.norm(nzm), tile
-    for tile in ("v2base", "v2l", "v2i", "v2s", "v2"):   # layer-march kernel: all instantiations (round 2)
+    for tile in ("v2base", "v2l", "v2i", "v2s", "v2g", "v2p", "v2e", "v2all", "v2"):   # layer-march kernel: all instantiations (round 2)
         os.environ["SMFEM_TILE"] = tile
         K.reassemble(40, 0.4)
         nzv = K.to_csc()[2]
