@@ -510,7 +510,8 @@ def main():
            "trace_check": float(diag_h.sum())}
 
     # e2e leg 2: the whole reference pipeline through the C ABI with HOST arrays in and the SOLUTION on the host out
-    # (examples/vector3D.jl:302-322: assemble_system -> K + beta*b -> setboundaryCond -> solve), multigrid-PCG to rtol 1e-10
+    # (examples/vector3D.jl:302-322: assemble_system -> K + beta*b -> setboundaryCond -> solve), multigrid-PCG with the matrix-free
+    # fine-level operator (the fastest configuration) to rtol 1e-10
     pipe = None
     if not args.no_solve:
         q_h = torch.empty(nrows_local, dtype=torch.float64, pin_memory=True)
@@ -525,6 +526,7 @@ def main():
             sd.connect(Kp)
             Kp.set_dirichlet_zplanes(0.001)
             Kp.use_multigrid(True)
+            Kp.use_matrix_free(True)
             it, rel = C.c_int(), C.c_double()
             _lib.call("smfem_pcg_solve", ctx.handle, kh, 1e-10, 500, None, C.cast(q_h.data_ptr(), _f), C.byref(it), C.byref(rel))
             ctx.sync()
@@ -543,7 +545,7 @@ def main():
             pipe = {"ms_total": dt * 1e3, "elements_per_s": ne**3 / dt, "pcg_iters": itp, "relres": relp, "solve_ms": max_over_ranks(solve_ms),
                     "h2d_bytes": host_bytes, "d2h_bytes": int(q_h.numel() * 8 * world), "u_checksum": float(q_h.sum()),
                     "call": "smfem_assemble_system(host NodeList, IEN, ID) -> smfem_surface_mass -> smfem_set_dirichlet_zplanes -> "
-                            "smfem_pcg_use_multigrid -> smfem_pcg_solve(q on host); includes the multigrid hierarchy build"}
+                            "smfem_pcg_use_multigrid + smfem_pcg_use_matrix_free -> smfem_pcg_solve(q on host); includes the multigrid hierarchy build"}
         except Exception as exc:
             pipe = {"error": str(exc)[:300]}
         del q_h
