@@ -536,6 +536,9 @@ int smfem_mesh_free(smfem_mesh *mesh) {
         dev_free(mesh->ien);
         dev_free(mesh->id);
         dev_free(mesh->elist);
+        dev_free(mesh->g_ptr);
+        dev_free(mesh->g_ent);
+        dev_free(mesh->g_task_node);
         delete mesh;
     });
 }

@@ -785,6 +785,211 @@ k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Gather form of the value assembly for GENERAL 3-D hex meshes with the standard dof map: every entry of K is
+// written exactly once, by the warp that owns its row - no memset, no atomics, no colour passes (the scatter forms move each
+// entry of K through L2 / DRAM once per contributing element: 8x for interior nodes, and K >> L2).
+//   plan (once per mesh): the (element, local node) pairs of every node, sorted by element -> fold order = ascending element
+//       index, the order in which sparse(E,J,V) folds duplicates (src/fem.jl:253); nodes are cut into warp tasks of <= 32 pairs.
+//   kernel: lane = one (node a, element e) pair: the 8 blocks G_ab = sum_gp g_a g_b' of "its" element in registers (the same
+//       arithmetic as k_values_atomic); then, 4 nodes at a time, the pairs of a node add their blocks into the node's row
+//       buffer in shared memory, one pair per node and round (no two lanes touch the same block in a round), and the warp
+//       streams the node's 3 CSR rows out with the material applied - coalesced, contiguous (the rows of a node are adjacent).
+// ------------------------------------------------------------------------------------------------
+constexpr int GATHER_G = 4;  // nodes of a warp task accumulated at a time
+
+__global__ void k_max_rowlen_nodes(int64_t nNodes, const int64_t *__restrict__ rowptr, int *__restrict__ out) {
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < nNodes) atomicMax(out, (int)((rowptr[3 * n + 1] - rowptr[3 * n]) / 3));
+}
+
+__global__ void k_gather_fill(const int32_t *__restrict__ ien, int64_t nEl, int nn, const int64_t *__restrict__ ptr,
+                              int *__restrict__ cursor, int32_t *__restrict__ ent) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nEl * nn) return;
+    const int node = ien[t];
+    const int e = (int)(t % nEl), a = (int)(t / nEl);
+    const int slot = atomicAdd(&cursor[node], 1);
+    ent[ptr[node] + slot] = e * nn + a;
+}
+
+__global__ void k_gather_sort(int64_t nNodes, const int64_t *__restrict__ ptr, int32_t *__restrict__ ent, int *__restrict__ maxlen) {
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nNodes) return;
+    const int64_t b = ptr[n];
+    const int len = (int)(ptr[n + 1] - b);
+    for (int i = 1; i < len; ++i) {  // insertion sort: the lists are short (8 for an interior hex node)
+        const int32_t v = ent[b + i];
+        int j = i - 1;
+        while (j >= 0 && ent[b + j] > v) {
+            ent[b + j + 1] = ent[b + j];
+            --j;
+        }
+        ent[b + j + 1] = v;
+    }
+    atomicMax(maxlen, len);
+}
+
+void mesh_build_gather(smfem_ctx *ctx, smfem_mesh *mesh) {
+    if (mesh->g_state != 0) return;
+    const int64_t nNodes = mesh->nNodes_g, nEl = mesh->nEl_g;
+    const int nn = mesh->nn;
+    mesh->g_state = -1;
+    if (nEl * nn >= (int64_t)INT32_MAX) return;
+    int *cnt = dev_alloc<int>(nNodes + 1), *cursor = dev_alloc<int>(nNodes + 1), *d_max = dev_alloc<int>(1);
+    int64_t *ptr = dev_alloc<int64_t>(nNodes + 1);
+    int32_t *ent = dev_alloc<int32_t>(nEl * nn);
+    auto fail = [&] {
+        dev_free(cnt);
+        dev_free(cursor);
+        dev_free(d_max);
+        dev_free(ptr);
+        dev_free(ent);
+    };
+    try {
+        CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(int) * (nNodes + 1), ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(cursor, 0, sizeof(int) * (nNodes + 1), ctx->stream));
+        CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
+        const unsigned gE = (unsigned)((nEl * nn + 255) / 256);
+        LAUNCH(ctx, k_n2e_count, gE, 256, 0, (const int32_t *)mesh->ien, nEl, nn, cnt);
+        exclusive_scan_dev(ctx, cub::TransformInputIterator<int64_t, IntTo64, const int *>(cnt, IntTo64()), ptr, nNodes + 1);
+        LAUNCH(ctx, k_gather_fill, gE, 256, 0, (const int32_t *)mesh->ien, nEl, nn, (const int64_t *)ptr, cursor, ent);
+        LAUNCH(ctx, k_gather_sort, (unsigned)((nNodes + 127) / 128), 128, 0, nNodes, (const int64_t *)ptr, ent, d_max);
+        std::vector<int64_t> h_ptr((size_t)nNodes + 1);
+        int h_max = 0;
+        CUDA_CHECK(cudaMemcpyAsync(h_ptr.data(), ptr, sizeof(int64_t) * (nNodes + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (h_max > 32) {  // a node shared by more than 32 elements: the scatter forms handle it
+            fail();
+            return;
+        }
+        std::vector<int32_t> task;  // greedy: whole nodes, <= 32 pairs per warp task
+        task.push_back(0);
+        int64_t start = 0;
+        for (int64_t n = 0; n < nNodes; ++n)
+            if (h_ptr[n + 1] - start > 32) {
+                task.push_back((int32_t)n);
+                start = h_ptr[n];
+            }
+        task.push_back((int32_t)nNodes);
+        mesh->g_ntasks = (int)task.size() - 1;
+        mesh->g_task_node = dev_alloc<int32_t>(task.size());
+        CUDA_CHECK(cudaMemcpyAsync(mesh->g_task_node, task.data(), sizeof(int32_t) * task.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        fail();
+        throw;
+    }
+    dev_free(cnt);
+    dev_free(cursor);
+    dev_free(d_max);
+    mesh->g_ptr = ptr;
+    mesh->g_ent = ent;
+    mesh->g_state = 1;
+}
+
+__global__ void __launch_bounds__(128)
+k_values_gather(const int32_t *__restrict__ ien, int64_t nEl, const double *__restrict__ coords, const int64_t *__restrict__ rowptr,
+                const int32_t *__restrict__ colind, double *__restrict__ val, Material mat, const int64_t *__restrict__ g_ptr,
+                const int32_t *__restrict__ g_ent, const int32_t *__restrict__ task_node, int ntasks, int max_slots) {
+    constexpr int NN = 8, NGP = 8;
+    extern __shared__ double s_rows[];  // [warp][GATHER_G][max_slots][9]
+    __shared__ double s_dN[NGP][NN][3];
+    __shared__ double s_w[NGP];
+    for (int t = threadIdx.x; t < NGP * NN * 3; t += blockDim.x) s_dN[t / (NN * 3)][(t % (NN * 3)) / 3][t % 3] = c_dN3[t / (NN * 3)][(t % (NN * 3)) / 3][t % 3];
+    if (threadIdx.x < NGP) s_w[threadIdx.x] = c_w3[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int task = blockIdx.x * 4 + warp;
+    if (task >= ntasks) return;
+    double *buf = s_rows + (size_t)warp * GATHER_G * max_slots * 9;
+    const int n_first = task_node[task], n_last = task_node[task + 1];
+    const int64_t base = g_ptr[n_first];
+    const int cnt = (int)(g_ptr[n_last] - base);
+    const bool active = lane < cnt;
+    int node = -1, k = -1, slots[NN];
+    double G[NN][9];
+    if (active) {
+        const int32_t ent = g_ent[base + lane];
+        const int64_t e = ent / NN;
+        const int a = ent % NN;
+        int64_t nodes[NN];
+        double X[NN][3];
+#pragma unroll
+        for (int b = 0; b < NN; ++b) {
+            nodes[b] = ien[(int64_t)b * nEl + e];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) X[b][d] = coords[nodes[b] * 3 + d];
+        }
+        node = (int)nodes[a];
+        k = (int)(base + lane - g_ptr[node]);  // position inside the node's (sorted) list = its round
+#pragma unroll
+        for (int b = 0; b < NN; ++b)
+#pragma unroll
+            for (int m = 0; m < 9; ++m) G[b][m] = 0.0;
+#pragma unroll 1
+        for (int g = 0; g < NGP; ++g) {
+            double J[9], inv[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    double s = 0;
+#pragma unroll
+                    for (int b = 0; b < NN; ++b) s += X[b][r] * s_dN[g][b][c];  // Jac = coords*dN, src/fem.jl:192
+                    J[r * 3 + c] = s;
+                }
+            const double w = s_w[g] * fabs(jac_inv<3>(J, inv));  // :194-195
+            double ga[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) ga[c] = (s_dN[g][a][0] * inv[c] + s_dN[g][a][1] * inv[3 + c] + s_dN[g][a][2] * inv[6 + c]) * w;  // dNdX = dN*invJ, :196
+#pragma unroll
+            for (int b = 0; b < NN; ++b) {
+                double gb[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) gb[c] = s_dN[g][b][0] * inv[c] + s_dN[g][b][1] * inv[3 + c] + s_dN[g][b][2] * inv[6 + c];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) G[b][i * 3 + j] += ga[i] * gb[j];
+            }
+        }
+        const int64_t r0 = rowptr[3 * (int64_t)node];
+#pragma unroll
+        for (int b = 0; b < NN; ++b) slots[b] = (int)((csr_find(rowptr, colind, 3 * (int64_t)node, 3 * nodes[b]) - r0) / 3);
+    }
+    for (int g0 = n_first; g0 < n_last; g0 += GATHER_G) {
+        const int g1 = g0 + GATHER_G < n_last ? g0 + GATHER_G : n_last;
+        for (int t = lane; t < GATHER_G * max_slots * 9; t += 32) buf[t] = 0.0;
+        const bool mine = active && node >= g0 && node < g1;
+        const int rounds = __reduce_max_sync(0xffffffffu, mine ? k + 1 : 0);
+        __syncwarp();
+        for (int r = 0; r < rounds; ++r) {
+            if (mine && k == r) {
+                double *row = buf + (size_t)(node - g0) * max_slots * 9;
+#pragma unroll
+                for (int b = 0; b < NN; ++b)
+#pragma unroll
+                    for (int m = 0; m < 9; ++m) row[slots[b] * 9 + m] += G[b][m];
+            }
+            __syncwarp();
+        }
+        for (int n = g0; n < g1; ++n) {
+            const int64_t r0 = rowptr[3 * (int64_t)n];
+            const int T = (int)(rowptr[3 * (int64_t)n + 1] - r0);  // entries per row; the node's 3 rows are adjacent in K
+            const double *row = buf + (size_t)(n - g0) * max_slots * 9;
+            for (int t = lane; t < 3 * T; t += 32) {
+                const int c = t / T, s = t - c * T, slot = s / 3, j = s - 3 * slot;
+                const double *blk = row + slot * 9;
+                const double gij = blk[c * 3 + j], gji = blk[j * 3 + c], tr = blk[0] + blk[4] + blk[8];
+                val[r0 + t] = (c == j) ? mat.d11 * gij + mat.mu * (tr - gij) : mat.lam * gij + mat.mu * gji;  // src/fem.jl:236-249
+            }
+        }
+        __syncwarp();
+    }
+}
+
 void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind, const int *ready);  // assemble_tile.cu
 bool values_tile_enabled();
 
@@ -845,6 +1050,32 @@ void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Y
         return;
     } else {
         if (fuse_pattern) pattern_build_structured(ctx, mesh, K);  // no fused kernel for this element type: plain rebuild
+        const char *ev0 = std::getenv("SMFEM_VALUES");
+        if (!mesh->structured && mesh->ien && mesh->id == nullptr && ndim == 3 && nDof == 3 && mesh->nn == 8 && !(ev0 && ev0[0])) {
+            // general hex mesh, standard dof map: gather form (SMFEM_VALUES=colored / atomic select the scatter forms)
+            mesh_build_gather(ctx, mesh);
+            int max_slots = 0;
+            {
+                int *d_m = dev_alloc<int>(1);
+                CUDA_CHECK(cudaMemsetAsync(d_m, 0, sizeof(int), ctx->stream));
+                LAUNCH(ctx, k_max_rowlen_nodes, (unsigned)((K->nrows_l / 3 + 255) / 256), 256, 0, K->nrows_l / 3, (const int64_t *)K->rowptr, d_m);
+                CUDA_CHECK(cudaMemcpyAsync(&max_slots, d_m, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+                dev_free(d_m);
+            }
+            const size_t smem = sizeof(double) * 4 * GATHER_G * (size_t)max_slots * 9;
+            if (mesh->g_state == 1 && max_slots > 0 && smem <= 96 * 1024) {
+                static std::atomic<unsigned long long> attr_set{0};
+                if (first_use_on_device(attr_set))
+                    CUDA_CHECK(cudaFuncSetAttribute(k_values_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                LAUNCH(ctx, k_values_gather, (unsigned)((mesh->g_ntasks + 3) / 4), 128, smem, (const int32_t *)mesh->ien, mesh->nEl_g,
+                       (const double *)mesh->coords, (const int64_t *)K->rowptr, (const int32_t *)K->colind, K->val, mat,
+                       (const int64_t *)mesh->g_ptr, (const int32_t *)mesh->g_ent, (const int32_t *)mesh->g_task_node, mesh->g_ntasks, max_slots);
+                K->values_ready = true;
+                extract_diag(ctx, K);
+                return;
+            }
+        }
         CUDA_CHECK(cudaMemsetAsync(K->val, 0, sizeof(double) * K->nnz_l, ctx->stream));
         Conn C = make_conn(mesh);
         DofMap D = make_dofmap(mesh, K);

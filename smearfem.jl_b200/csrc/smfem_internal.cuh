@@ -121,6 +121,13 @@ struct smfem_mesh {
     int32_t *elist = nullptr;  // element ids sorted by colour
     int ncolors = 0;           // 0: not built, -1: not colourable with <= 64 colours (atomic scatter is used)
     int64_t color_off[65] = {};
+    // gather plan (general 3-D hex meshes with the standard dof map; built on first use by mesh_build_gather): the (element, local
+    // node) pairs of every node, sorted, and a partition of the nodes into warp tasks of <= 32 pairs
+    int64_t *g_ptr = nullptr;        // nNodes + 1
+    int32_t *g_ent = nullptr;        // nEl * nn entries  e * nn + a
+    int32_t *g_task_node = nullptr;  // g_ntasks + 1: first node of every warp task
+    int g_ntasks = 0;
+    int g_state = 0;                 // 0: not built, 1: usable, -1: not usable (a node with more than 32 elements)
     // surface faces for general meshes are passed to smfem_surface_mass directly
 };
 
