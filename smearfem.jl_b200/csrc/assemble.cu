@@ -792,11 +792,11 @@ k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64
 //   plan (once per mesh): the (element, local node) pairs of every node, sorted by element -> fold order = ascending element
 //       index, the order in which sparse(E,J,V) folds duplicates (src/fem.jl:253); nodes are cut into warp tasks of <= 32 pairs.
 //   kernel: lane = one (node a, element e) pair: the 8 blocks G_ab = sum_gp g_a g_b' of "its" element in registers (the same
-//       arithmetic as k_values_atomic); then, 4 nodes at a time, the pairs of a node add their blocks into the node's row
-//       buffer in shared memory, one pair per node and round (no two lanes touch the same block in a round), and the warp
-//       streams the node's 3 CSR rows out with the material applied - coalesced, contiguous (the rows of a node are adjacent).
+//       arithmetic as k_values_atomic), parked in a per-warp staging area; then, node by node, the warp loads the node's
+//       neighbour list (its row's columns) into shared memory, every pair looks up where its 8 nodes sit in that row, the 9
+//       entries of every neighbour block are summed over the pairs in element order by all 32 lanes, and the warp streams the
+//       node's 3 CSR rows out with the material applied - coalesced, contiguous (the rows of a node are adjacent).
 // ------------------------------------------------------------------------------------------------
-constexpr int GATHER_G = 4;  // nodes of a warp task accumulated at a time
 
 __global__ void k_max_rowlen_nodes(int64_t nNodes, const int64_t *__restrict__ rowptr, int *__restrict__ out) {
     int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -889,12 +889,19 @@ void mesh_build_gather(smfem_ctx *ctx, smfem_mesh *mesh) {
     mesh->g_state = 1;
 }
 
+constexpr int GATHER_STAGE = 73;  // doubles per lane in the staging area (72 + 1: odd stride, conflict-free)
+__host__ __device__ inline size_t gather_warp_bytes(int max_slots) {
+    // stage[32][73] f64 | xs[32][25] f64 | red[max_slots][9] f64 | adjn[max_slots] i32 | tab[32][max_slots] u8   (rounded to 16 bytes)
+    size_t b = sizeof(double) * (32 * GATHER_STAGE + 32 * 25 + (size_t)max_slots * 9) + 4 * (size_t)max_slots + 32 * (size_t)max_slots;
+    return (b + 15) & ~(size_t)15;
+}
+
 __global__ void __launch_bounds__(128)
 k_values_gather(const int32_t *__restrict__ ien, int64_t nEl, const double *__restrict__ coords, const int64_t *__restrict__ rowptr,
                 const int32_t *__restrict__ colind, double *__restrict__ val, Material mat, const int64_t *__restrict__ g_ptr,
                 const int32_t *__restrict__ g_ent, const int32_t *__restrict__ task_node, int ntasks, int max_slots) {
     constexpr int NN = 8, NGP = 8;
-    extern __shared__ double s_rows[];  // [warp][GATHER_G][max_slots][9]
+    extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ double s_dN[NGP][NN][3];
     __shared__ double s_w[NGP];
     for (int t = threadIdx.x; t < NGP * NN * 3; t += blockDim.x) s_dN[t / (NN * 3)][(t % (NN * 3)) / 3][t % 3] = c_dN3[t / (NN * 3)][(t % (NN * 3)) / 3][t % 3];
@@ -903,89 +910,129 @@ k_values_gather(const int32_t *__restrict__ ien, int64_t nEl, const double *__re
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int task = blockIdx.x * 4 + warp;
     if (task >= ntasks) return;
-    double *buf = s_rows + (size_t)warp * GATHER_G * max_slots * 9;
+    unsigned char *mine_smem = s_dyn + warp * gather_warp_bytes(max_slots);
+    double *stage = reinterpret_cast<double *>(mine_smem);
+    double *xs = stage + 32 * GATHER_STAGE;  // the 8 x 3 coordinates of each lane's element (odd lane stride): frees 48 registers
+    double *red = xs + 32 * 25;
+    int32_t *adjn = reinterpret_cast<int32_t *>(red + (size_t)max_slots * 9);
+    unsigned char *tab = reinterpret_cast<unsigned char *>(adjn + max_slots);
     const int n_first = task_node[task], n_last = task_node[task + 1];
     const int64_t base = g_ptr[n_first];
     const int cnt = (int)(g_ptr[n_last] - base);
     const bool active = lane < cnt;
-    int node = -1, k = -1, slots[NN];
-    double G[NN][9];
+    int32_t nodes[NN];
     if (active) {
         const int32_t ent = g_ent[base + lane];
         const int64_t e = ent / NN;
         const int a = ent % NN;
-        int64_t nodes[NN];
-        double X[NN][3];
+        double *X = xs + lane * 25;
 #pragma unroll
         for (int b = 0; b < NN; ++b) {
             nodes[b] = ien[(int64_t)b * nEl + e];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) X[b][d] = coords[nodes[b] * 3 + d];
+            for (int d = 0; d < 3; ++d) X[b * 3 + d] = coords[(int64_t)nodes[b] * 3 + d];
         }
-        node = (int)nodes[a];
-        k = (int)(base + lane - g_ptr[node]);  // position inside the node's (sorted) list = its round
-#pragma unroll
-        for (int b = 0; b < NN; ++b)
-#pragma unroll
-            for (int m = 0; m < 9; ++m) G[b][m] = 0.0;
+        // two passes over the Gauss points, 4 of the 8 blocks each: 36 accumulators instead of 72 keep the kernel free of register
+        // spills (the single-pass form spilled ~1.4 KB per thread) at the price of evaluating J^-1 twice
 #pragma unroll 1
-        for (int g = 0; g < NGP; ++g) {
-            double J[9], inv[9];
+        for (int half = 0; half < 2; ++half) {
+            double G[4][9];
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
+            for (int b = 0; b < 4; ++b)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    double s = 0;
+                for (int m = 0; m < 9; ++m) G[b][m] = 0.0;
+#pragma unroll 1
+            for (int g = 0; g < NGP; ++g) {
+                double J[9], inv[9];
 #pragma unroll
-                    for (int b = 0; b < NN; ++b) s += X[b][r] * s_dN[g][b][c];  // Jac = coords*dN, src/fem.jl:192
-                    J[r * 3 + c] = s;
+                for (int q = 0; q < 9; ++q) J[q] = 0.0;
+#pragma unroll
+                for (int b = 0; b < NN; ++b) {  // Jac = coords*dN, src/fem.jl:192 (same summation order over b as the scatter kernels)
+                    const double d0 = s_dN[g][b][0], d1 = s_dN[g][b][1], d2 = s_dN[g][b][2];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const double x = X[b * 3 + r];
+                        J[r * 3 + 0] += x * d0;
+                        J[r * 3 + 1] += x * d1;
+                        J[r * 3 + 2] += x * d2;
+                    }
                 }
-            const double w = s_w[g] * fabs(jac_inv<3>(J, inv));  // :194-195
-            double ga[3];
+                const double w = s_w[g] * fabs(jac_inv<3>(J, inv));  // :194-195
+                double ga[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) ga[c] = (s_dN[g][a][0] * inv[c] + s_dN[g][a][1] * inv[3 + c] + s_dN[g][a][2] * inv[6 + c]) * w;  // dNdX = dN*invJ, :196
+                for (int c = 0; c < 3; ++c) ga[c] = (s_dN[g][a][0] * inv[c] + s_dN[g][a][1] * inv[3 + c] + s_dN[g][a][2] * inv[6 + c]) * w;  // dNdX = dN*invJ, :196
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const double *dn = s_dN[g][4 * half + b];
+                    double gb[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) gb[c] = dn[0] * inv[c] + dn[1] * inv[3 + c] + dn[2] * inv[6 + c];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) G[b][i * 3 + j] += ga[i] * gb[j];
+                }
+            }
+            // park the blocks of this (node, element) pair: all lanes at once, odd lane stride
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int m = 0; m < 9; ++m) stage[lane * GATHER_STAGE + (4 * half + b) * 9 + m] = G[b][m];
+        }
+    }
+    __syncwarp();
+    for (int n = n_first; n < n_last; ++n) {
+        const int p0 = (int)(g_ptr[n] - base), p1 = (int)(g_ptr[n + 1] - base);  // this node's pairs = lanes [p0, p1)
+        const int64_t r0 = rowptr[3 * (int64_t)n];
+        const int T = (int)(rowptr[3 * (int64_t)n + 1] - r0);  // entries per row; the node's 3 rows are adjacent in K
+        const int nslots = T / 3;
+        // the node's neighbours in row order, and for every pair the local index of each neighbour inside its element
+        for (int sgm = lane; sgm < nslots; sgm += 32) adjn[sgm] = colind[r0 + 3 * sgm] / 3;
+        for (int t = lane; t < (p1 - p0) * max_slots; t += 32) tab[t] = 255;
+        __syncwarp();
+        if (lane >= p0 && lane < p1) {
 #pragma unroll
             for (int b = 0; b < NN; ++b) {
-                double gb[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) gb[c] = s_dN[g][b][0] * inv[c] + s_dN[g][b][1] * inv[3 + c] + s_dN[g][b][2] * inv[6 + c];
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) G[b][i * 3 + j] += ga[i] * gb[j];
+                int lo = 0, hi = nslots - 1;  // binary search in shared memory (the row is sorted)
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (adjn[mid] < nodes[b]) lo = mid + 1;
+                    else hi = mid;
+                }
+                tab[(lane - p0) * max_slots + lo] = (unsigned char)b;
             }
         }
-        const int64_t r0 = rowptr[3 * (int64_t)node];
-#pragma unroll
-        for (int b = 0; b < NN; ++b) slots[b] = (int)((csr_find(rowptr, colind, 3 * (int64_t)node, 3 * nodes[b]) - r0) / 3);
-    }
-    for (int g0 = n_first; g0 < n_last; g0 += GATHER_G) {
-        const int g1 = g0 + GATHER_G < n_last ? g0 + GATHER_G : n_last;
-        for (int t = lane; t < GATHER_G * max_slots * 9; t += 32) buf[t] = 0.0;
-        const bool mine = active && node >= g0 && node < g1;
-        const int rounds = __reduce_max_sync(0xffffffffu, mine ? k + 1 : 0);
         __syncwarp();
-        for (int r = 0; r < rounds; ++r) {
-            if (mine && k == r) {
-                double *row = buf + (size_t)(node - g0) * max_slots * 9;
+        // fold the pairs in ascending element order (= the order sparse(E,J,V) folds duplicates): item = (neighbour slot, block entry)
+        for (int sgm = lane; sgm < nslots; sgm += 32) {  // lane = neighbour slot: one table look-up per pair, 9 adds per hit
+            double acc[9];
 #pragma unroll
-                for (int b = 0; b < NN; ++b)
+            for (int m = 0; m < 9; ++m) acc[m] = 0.0;
+            for (int p = p0; p < p1; ++p) {
+                const int b = tab[(p - p0) * max_slots + sgm];
+                if (b != 255) {
+                    const double *src = stage + p * GATHER_STAGE + b * 9;
 #pragma unroll
-                    for (int m = 0; m < 9; ++m) row[slots[b] * 9 + m] += G[b][m];
+                    for (int m = 0; m < 9; ++m) acc[m] += src[m];
+                }
             }
-            __syncwarp();
+            // material on the summed block (src/fem.jl:236-249): red holds the 3 x 3 block of K for this neighbour
+            const double tr = acc[0] + acc[4] + acc[8];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const double gij = acc[c * 3 + j], gji = acc[j * 3 + c];
+                    red[sgm * 9 + c * 3 + j] = (c == j) ? mat.d11 * gij + mat.mu * (tr - gij) : mat.lam * gij + mat.mu * gji;
+                }
         }
-        for (int n = g0; n < g1; ++n) {
-            const int64_t r0 = rowptr[3 * (int64_t)n];
-            const int T = (int)(rowptr[3 * (int64_t)n + 1] - r0);  // entries per row; the node's 3 rows are adjacent in K
-            const double *row = buf + (size_t)(n - g0) * max_slots * 9;
-            for (int t = lane; t < 3 * T; t += 32) {
-                const int c = t / T, s = t - c * T, slot = s / 3, j = s - 3 * slot;
-                const double *blk = row + slot * 9;
-                const double gij = blk[c * 3 + j], gji = blk[j * 3 + c], tr = blk[0] + blk[4] + blk[8];
-                val[r0 + t] = (c == j) ? mat.d11 * gij + mat.mu * (tr - gij) : mat.lam * gij + mat.mu * gji;  // src/fem.jl:236-249
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 3; ++c)  // row c of the node: entry s = 3 slot + j  <-  block[slot][c][j]; coalesced
+            for (int sidx = lane; sidx < T; sidx += 32) {
+                const int slot = sidx / 3, j = sidx - 3 * slot;
+                val[r0 + (int64_t)c * T + sidx] = red[slot * 9 + c * 3 + j];
             }
-        }
         __syncwarp();
     }
 }
@@ -1063,11 +1110,11 @@ void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Y
                 CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
                 dev_free(d_m);
             }
-            const size_t smem = sizeof(double) * 4 * GATHER_G * (size_t)max_slots * 9;
-            if (mesh->g_state == 1 && max_slots > 0 && smem <= 96 * 1024) {
+            const size_t smem = 4 * gather_warp_bytes(max_slots);
+            if (mesh->g_state == 1 && max_slots > 0 && max_slots < 255 && smem <= 110 * 1024) {
                 static std::atomic<unsigned long long> attr_set{0};
                 if (first_use_on_device(attr_set))
-                    CUDA_CHECK(cudaFuncSetAttribute(k_values_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                    CUDA_CHECK(cudaFuncSetAttribute(k_values_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
                 LAUNCH(ctx, k_values_gather, (unsigned)((mesh->g_ntasks + 3) / 4), 128, smem, (const int32_t *)mesh->ien, mesh->nEl_g,
                        (const double *)mesh->coords, (const int64_t *)K->rowptr, (const int32_t *)K->colind, K->val, mat,
                        (const int64_t *)mesh->g_ptr, (const int32_t *)mesh->g_ent, (const int32_t *)mesh->g_task_node, mesh->g_ntasks, max_slots);
