@@ -791,8 +791,10 @@ k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64
 // entry of K through L2 / DRAM once per contributing element: 8x for interior nodes, and K >> L2).
 //   plan (once per mesh): the (element, local node) pairs of every node, sorted by element -> fold order = ascending element
 //       index, the order in which sparse(E,J,V) folds duplicates (src/fem.jl:253); nodes are cut into warp tasks of <= 32 pairs.
-//   kernel: lane = one (node a, element e) pair: the 8 blocks G_ab = sum_gp g_a g_b' of "its" element in registers (the same
-//       arithmetic as k_values_atomic), parked in a per-warp staging area; then, node by node, the warp loads the node's
+//   element pass: A = sqrt(w |det J|) J^-1 per (element, Gauss point) -> 576 B per element of scratch (k_gather_elem);
+//   kernel: lane = one (node a, element e) pair: the 8 blocks G_ab = sum_gp (dN_a A)(dN_b A)' of "its" element in registers (72
+//       accumulators, no coordinates, no Jacobian: the next Gauss point's A is loaded while this one's 153 FMAs run), parked in a
+//       per-warp staging area; then, node by node, the warp loads the node's
 //       neighbour list (its row's columns) into shared memory, every pair looks up where its 8 nodes sit in that row, the 9
 //       entries of every neighbour block are summed over the pairs in element order by all 32 lanes, and the warp streams the
 //       node's 3 CSR rows out with the material applied - coalesced, contiguous (the rows of a node are adjacent).
@@ -891,126 +893,155 @@ void mesh_build_gather(smfem_ctx *ctx, smfem_mesh *mesh) {
 
 constexpr int GATHER_STAGE = 73;  // doubles per lane in the staging area (72 + 1: odd stride, conflict-free)
 __host__ __device__ inline size_t gather_warp_bytes(int max_slots) {
-    // stage[32][73] f64 | xs[32][25] f64 | red[max_slots][9] f64 | adjn[max_slots] i32 | tab[32][max_slots] u8   (rounded to 16 bytes)
-    size_t b = sizeof(double) * (32 * GATHER_STAGE + 32 * 25 + (size_t)max_slots * 9) + 4 * (size_t)max_slots + 32 * (size_t)max_slots;
+    // stage[32][73] f64 | red[max_slots][9] f64 | adj_all[32][max_slots] i32 | pnodes[32][8] i32   (16-byte aligned pieces)
+    size_t b = sizeof(double) * (32 * GATHER_STAGE + (size_t)((max_slots + 1) & ~1) * 9) + 4 * 32 * (size_t)((max_slots + 3) & ~3) + 4 * 32 * 8;
     return (b + 15) & ~(size_t)15;
 }
 
-__global__ void __launch_bounds__(128)
-k_values_gather(const int32_t *__restrict__ ien, int64_t nEl, const double *__restrict__ coords, const int64_t *__restrict__ rowptr,
+// per (element, Gauss point): A = sqrt(w |det J|) J^-1 (src/fem.jl:192-196), so that g_a = dN_a A and G_ab += g_a g_b'.  The 8 (node,
+// element) pairs of an element read it instead of re-evaluating the Jacobian 8 times (and the gather kernel needs no coordinates).
+__global__ void __launch_bounds__(256) k_gather_elem(const int32_t *__restrict__ ien, int64_t nEl, const double *__restrict__ coords,
+                                                     double *__restrict__ Ainv) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nEl * 8) return;
+    const int64_t e = t >> 3;
+    const int g = (int)(t & 7);
+    double J[9], inv[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) J[q] = 0.0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {  // Jac = coords*dN, src/fem.jl:192
+        const int64_t nb = ien[(int64_t)b * nEl + e];
+        const double d0 = c_dN3[g][b][0], d1 = c_dN3[g][b][1], d2 = c_dN3[g][b][2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double x = coords[nb * 3 + r];
+            J[r * 3 + 0] += x * d0;
+            J[r * 3 + 1] += x * d1;
+            J[r * 3 + 2] += x * d2;
+        }
+    }
+    const double sw = sqrt(c_w3[g] * fabs(jac_inv<3>(J, inv)));  // :194-195
+#pragma unroll
+    for (int q = 0; q < 9; ++q) Ainv[t * 9 + q] = inv[q] * sw;
+}
+
+__global__ void __launch_bounds__(128, 2)
+k_values_gather(const int32_t *__restrict__ ien, int64_t nEl, const double *__restrict__ Ainv, const int64_t *__restrict__ rowptr,
                 const int32_t *__restrict__ colind, double *__restrict__ val, Material mat, const int64_t *__restrict__ g_ptr,
                 const int32_t *__restrict__ g_ent, const int32_t *__restrict__ task_node, int ntasks, int max_slots) {
     constexpr int NN = 8, NGP = 8;
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ double s_dN[NGP][NN][3];
-    __shared__ double s_w[NGP];
     for (int t = threadIdx.x; t < NGP * NN * 3; t += blockDim.x) s_dN[t / (NN * 3)][(t % (NN * 3)) / 3][t % 3] = c_dN3[t / (NN * 3)][(t % (NN * 3)) / 3][t % 3];
-    if (threadIdx.x < NGP) s_w[threadIdx.x] = c_w3[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int task = blockIdx.x * 4 + warp;
     if (task >= ntasks) return;
     unsigned char *mine_smem = s_dyn + warp * gather_warp_bytes(max_slots);
-    double *stage = reinterpret_cast<double *>(mine_smem);
-    double *xs = stage + 32 * GATHER_STAGE;  // the 8 x 3 coordinates of each lane's element (odd lane stride): frees 48 registers
-    double *red = xs + 32 * 25;
-    int32_t *adjn = reinterpret_cast<int32_t *>(red + (size_t)max_slots * 9);
-    unsigned char *tab = reinterpret_cast<unsigned char *>(adjn + max_slots);
-    const int n_first = task_node[task], n_last = task_node[task + 1];
+    double *stage = reinterpret_cast<double *>(mine_smem);        // [lane][73]: first the lane's 8 A matrices, then its 8 blocks
+    double *red = stage + 32 * GATHER_STAGE;                       // [slot][9]: the node's row blocks with the material applied
+    int32_t *adj_all = reinterpret_cast<int32_t *>(red + (size_t)((max_slots + 1) & ~1) * 9);  // [node of the task][slot]
+    int32_t *pnodes = adj_all + 32 * (size_t)((max_slots + 3) & ~3);  // [pair][8]: the node ids of every pair's element (16-byte aligned)
+    const int n_first = task_node[task], n_last = task_node[task + 1], nn_task = n_last - n_first;
     const int64_t base = g_ptr[n_first];
     const int cnt = (int)(g_ptr[n_last] - base);
     const bool active = lane < cnt;
-    int32_t nodes[NN];
+    // this lane's pair: element, local node; its element's 8 node ids and 8 A matrices go to shared memory (all loads of the
+    // task are requested before anything waits on them)
+    int a = 0;
+    int64_t e = 0;
     if (active) {
         const int32_t ent = g_ent[base + lane];
-        const int64_t e = ent / NN;
-        const int a = ent % NN;
-        double *X = xs + lane * 25;
-#pragma unroll
-        for (int b = 0; b < NN; ++b) {
-            nodes[b] = ien[(int64_t)b * nEl + e];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) X[b * 3 + d] = coords[(int64_t)nodes[b] * 3 + d];
-        }
-        // two passes over the Gauss points, 4 of the 8 blocks each: 36 accumulators instead of 72 keep the kernel free of register
-        // spills (the single-pass form spilled ~1.4 KB per thread) at the price of evaluating J^-1 twice
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            double G[4][9];
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-#pragma unroll
-                for (int m = 0; m < 9; ++m) G[b][m] = 0.0;
-#pragma unroll 1
-            for (int g = 0; g < NGP; ++g) {
-                double J[9], inv[9];
-#pragma unroll
-                for (int q = 0; q < 9; ++q) J[q] = 0.0;
-#pragma unroll
-                for (int b = 0; b < NN; ++b) {  // Jac = coords*dN, src/fem.jl:192 (same summation order over b as the scatter kernels)
-                    const double d0 = s_dN[g][b][0], d1 = s_dN[g][b][1], d2 = s_dN[g][b][2];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const double x = X[b * 3 + r];
-                        J[r * 3 + 0] += x * d0;
-                        J[r * 3 + 1] += x * d1;
-                        J[r * 3 + 2] += x * d2;
-                    }
-                }
-                const double w = s_w[g] * fabs(jac_inv<3>(J, inv));  // :194-195
-                double ga[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) ga[c] = (s_dN[g][a][0] * inv[c] + s_dN[g][a][1] * inv[3 + c] + s_dN[g][a][2] * inv[6 + c]) * w;  // dNdX = dN*invJ, :196
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const double *dn = s_dN[g][4 * half + b];
-                    double gb[3];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) gb[c] = dn[0] * inv[c] + dn[1] * inv[3 + c] + dn[2] * inv[6 + c];
-#pragma unroll
-                    for (int i = 0; i < 3; ++i)
-#pragma unroll
-                        for (int j = 0; j < 3; ++j) G[b][i * 3 + j] += ga[i] * gb[j];
-                }
-            }
-            // park the blocks of this (node, element) pair: all lanes at once, odd lane stride
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-#pragma unroll
-                for (int m = 0; m < 9; ++m) stage[lane * GATHER_STAGE + (4 * half + b) * 9 + m] = G[b][m];
-        }
+        e = ent / NN;
+        a = ent % NN;
     }
+    // row starts / lengths and list bounds of the task's nodes: lane i <-> node n_first + i
+    int64_t my_r0 = 0;
+    int my_T = 0, my_p0 = 0, my_p1 = 0;
+    if (lane < nn_task) {
+        const int64_t n = n_first + lane;
+        my_r0 = rowptr[3 * n];
+        my_T = (int)(rowptr[3 * n + 1] - my_r0);
+        my_p0 = (int)(g_ptr[n] - base);
+        my_p1 = (int)(g_ptr[n + 1] - base);
+    }
+    if (active) {
+#pragma unroll
+        for (int b = 0; b < NN; ++b) pnodes[lane * NN + b] = ien[(int64_t)b * nEl + e];
+        // the 8 A matrices: 72 asynchronous 8-byte copies per lane, all in flight at once (no register round trip)
+        const double *Ae = Ainv + e * 72;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + lane * GATHER_STAGE);
+#pragma unroll 8
+        for (int q = 0; q < 72; ++q) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * q), "l"(Ae + q) : "memory");
+    }
+    // the neighbour lists (= the columns of the nodes' first rows) of all nodes of the task, flattened over (node, slot)
+    for (int idx0 = 0; idx0 < nn_task * max_slots; idx0 += 32) {  // uniform trip count: the shuffles need all lanes
+        const int idx = idx0 + lane;
+        const bool ok = idx < nn_task * max_slots;
+        const int i = ok ? idx / max_slots : 0, sgm = idx - i * max_slots;
+        const int64_t r0 = __shfl_sync(0xffffffffu, my_r0, i);
+        const int nslots = __shfl_sync(0xffffffffu, my_T, i) / 3;
+        if (ok && sgm < nslots) adj_all[idx] = colind[r0 + 3 * sgm] / 3;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    for (int n = n_first; n < n_last; ++n) {
-        const int p0 = (int)(g_ptr[n] - base), p1 = (int)(g_ptr[n + 1] - base);  // this node's pairs = lanes [p0, p1)
-        const int64_t r0 = rowptr[3 * (int64_t)n];
-        const int T = (int)(rowptr[3 * (int64_t)n + 1] - r0);  // entries per row; the node's 3 rows are adjacent in K
-        const int nslots = T / 3;
-        // the node's neighbours in row order, and for every pair the local index of each neighbour inside its element
-        for (int sgm = lane; sgm < nslots; sgm += 32) adjn[sgm] = colind[r0 + 3 * sgm] / 3;
-        for (int t = lane; t < (p1 - p0) * max_slots; t += 32) tab[t] = 255;
-        __syncwarp();
-        if (lane >= p0 && lane < p1) {
+    if (active) {
+        double G[NN][9];
+#pragma unroll
+        for (int b = 0; b < NN; ++b)
+#pragma unroll
+            for (int m = 0; m < 9; ++m) G[b][m] = 0.0;
+#pragma unroll 1
+        for (int g = 0; g < NGP; ++g) {
+            double A[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) A[q] = stage[lane * GATHER_STAGE + g * 9 + q];
+            double ga[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) ga[c] = s_dN[g][a][0] * A[c] + s_dN[g][a][1] * A[3 + c] + s_dN[g][a][2] * A[6 + c];  // sqrt(w |det|) dNdX, :196
 #pragma unroll
             for (int b = 0; b < NN; ++b) {
-                int lo = 0, hi = nslots - 1;  // binary search in shared memory (the row is sorted)
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (adjn[mid] < nodes[b]) lo = mid + 1;
-                    else hi = mid;
-                }
-                tab[(lane - p0) * max_slots + lo] = (unsigned char)b;
+                double gb[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) gb[c] = s_dN[g][b][0] * A[c] + s_dN[g][b][1] * A[3 + c] + s_dN[g][b][2] * A[6 + c];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) G[b][i * 3 + j] += ga[i] * gb[j];
             }
         }
-        __syncwarp();
-        // fold the pairs in ascending element order (= the order sparse(E,J,V) folds duplicates): item = (neighbour slot, block entry)
-        for (int sgm = lane; sgm < nslots; sgm += 32) {  // lane = neighbour slot: one table look-up per pair, 9 adds per hit
+        // park the 8 blocks of this (node, element) pair over the consumed A matrices: all lanes at once, odd lane stride
+#pragma unroll
+        for (int b = 0; b < NN; ++b)
+#pragma unroll
+            for (int m = 0; m < 9; ++m) stage[lane * GATHER_STAGE + b * 9 + m] = G[b][m];
+    }
+    __syncwarp();
+    for (int i = 0; i < nn_task; ++i) {
+        const int p0 = __shfl_sync(0xffffffffu, my_p0, i), p1 = __shfl_sync(0xffffffffu, my_p1, i);  // this node's pairs = lanes [p0, p1)
+        const int64_t r0 = __shfl_sync(0xffffffffu, my_r0, i);
+        const int T = __shfl_sync(0xffffffffu, my_T, i);  // entries per row; the node's 3 rows are adjacent in K
+        const int nslots = T / 3;
+        // lane = neighbour slot: fold the blocks of the pairs whose element contains this neighbour, in ascending element order
+        // (= the order sparse(E,J,V) folds duplicates); which local node it is inside the element: 8 compares per pair
+        for (int sgm = lane; sgm < nslots; sgm += 32) {
+            const int32_t want = adj_all[i * max_slots + sgm];
             double acc[9];
 #pragma unroll
             for (int m = 0; m < 9; ++m) acc[m] = 0.0;
             for (int p = p0; p < p1; ++p) {
-                const int b = tab[(p - p0) * max_slots + sgm];
-                if (b != 255) {
+                const int4 lo4 = *reinterpret_cast<const int4 *>(pnodes + p * NN), hi4 = *reinterpret_cast<const int4 *>(pnodes + p * NN + 4);
+                int b = -1;
+                b = lo4.x == want ? 0 : b;
+                b = lo4.y == want ? 1 : b;
+                b = lo4.z == want ? 2 : b;
+                b = lo4.w == want ? 3 : b;
+                b = hi4.x == want ? 4 : b;
+                b = hi4.y == want ? 5 : b;
+                b = hi4.z == want ? 6 : b;
+                b = hi4.w == want ? 7 : b;
+                if (b >= 0) {
                     const double *src = stage + p * GATHER_STAGE + b * 9;
 #pragma unroll
                     for (int m = 0; m < 9; ++m) acc[m] += src[m];
@@ -1115,11 +1146,16 @@ void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Y
                 static std::atomic<unsigned long long> attr_set{0};
                 if (first_use_on_device(attr_set))
                     CUDA_CHECK(cudaFuncSetAttribute(k_values_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+                double *Ainv = dev_alloc<double>(mesh->nEl_g * 72);  // 576 B per element, read by its 8 (node, element) pairs
+                LAUNCH(ctx, k_gather_elem, (unsigned)((mesh->nEl_g * 8 + 255) / 256), 256, 0, (const int32_t *)mesh->ien, mesh->nEl_g,
+                       (const double *)mesh->coords, Ainv);
                 LAUNCH(ctx, k_values_gather, (unsigned)((mesh->g_ntasks + 3) / 4), 128, smem, (const int32_t *)mesh->ien, mesh->nEl_g,
-                       (const double *)mesh->coords, (const int64_t *)K->rowptr, (const int32_t *)K->colind, K->val, mat,
+                       (const double *)Ainv, (const int64_t *)K->rowptr, (const int32_t *)K->colind, K->val, mat,
                        (const int64_t *)mesh->g_ptr, (const int32_t *)mesh->g_ent, (const int32_t *)mesh->g_task_node, mesh->g_ntasks, max_slots);
                 K->values_ready = true;
                 extract_diag(ctx, K);
+                CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+                dev_free(Ainv);
                 return;
             }
         }
