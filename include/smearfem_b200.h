@@ -237,6 +237,14 @@ int smfem_pcg_use_multigrid(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, i
  * operator).  Same vector layout, halo protocol and Dirichlet handling as the CSR SpMV; bit-reproducible (8 colour passes, no
  * atomics).  smfem_bench_spmv variant 5 times it.  `mesh` must stay alive while the option is on. */
 int smfem_pcg_use_matrix_free(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, int enable);
+/* The same operator WITHOUT ever assembling K: a matrix handle that holds the slab layout, the material and diag(K) (computed
+ * from the coordinates, for the Jacobi preconditioner) but no rowptr / colind / val - 0 bytes per nonzero instead of 12, so one
+ * GPU solves meshes whose assembled matrix would not fit.  Accepted by smfem_surface_mass (lattice faces; the term enters the
+ * operator's beta and the diagonal), smfem_set_dirichlet[_zplanes], smfem_pcg_use_multigrid (coarse levels are assembled as usual),
+ * smfem_pcg_solve, smfem_spmv_host, smfem_bench_spmv (variant 5), smfem_comm_* / the multi layer, smfem_project_nodes,
+ * smfem_extract_borders, smfem_matrix_diag / _info / _clone; calls that need CSR arrays (export, reassemble, …) return
+ * SMFEM_ERR_UNSUPPORTED.  `mesh` must outlive the handle. */
+int smfem_matfree_operator(smfem_ctx *ctx, smfem_mesh *mesh, double Young, double nu, smfem_matrix **K_out);
 int smfem_pcg_apply_preconditioner(smfem_ctx *ctx, smfem_matrix *K, const double *r, double *z);
 /* Load stepping (examples/vector3D.jl:310-338: the same K̄ solved for 50 prescribed displacements d; q is exactly
  * linear in d): the NEXT smfem_pcg_solve on K starts from scale * (previous solution on the free dofs) instead of 0.

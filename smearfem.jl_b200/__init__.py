@@ -206,6 +206,14 @@ class SparseMatrixB200:
         return cls(ctx, h, mesh)
 
     @classmethod
+    def matrix_free(cls, ctx, mesh, Young, nu):
+        """The hex-lattice operator of assemble_system WITHOUT the assembled matrix (smfem_matfree_operator): solves, SpMVs and
+        the multigrid preconditioner work on it; anything that needs CSR arrays raises."""
+        h = C.c_void_p()
+        call("smfem_matfree_operator", ctx.handle, mesh.handle, float(Young), float(nu), C.byref(h))
+        return cls(ctx, h, mesh)
+
+    @classmethod
     def pattern(cls, ctx, mesh, ndim, nDof):
         h = C.c_void_p()
         call("smfem_pattern_build", ctx.handle, mesh.handle, int(ndim), int(nDof), C.byref(h))

@@ -65,6 +65,7 @@ SIGNATURES = {
     "smfem_mesh_colors": [_vp, _vp, C.POINTER(C.c_int), _i64p],
     "smfem_pcg_use_multigrid": [_vp, _vp, _vp, C.c_int],
     "smfem_pcg_use_matrix_free": [_vp, _vp, _vp, C.c_int],
+    "smfem_matfree_operator": [_vp, _vp, C.c_double, C.c_double, C.POINTER(_vp)],
     "smfem_pcg_apply_preconditioner": [_vp, _vp, _f64p, _f64p],
     "smfem_project_nodes": [_vp, _vp, _vp, _i64p, C.c_int64, _f64p, _f64p, _f64p],
     "smfem_extract_borders": [_vp, _vp, _vp, _i64p, C.c_int64, _f64p, C.c_int, C.c_int64, _f64p, C.c_int64, _i64p, _f64p],

@@ -594,6 +594,7 @@ int smfem_pattern_rebuild(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K) {
         NOTNULL(ctx);
         NOTNULL(mesh);
         NOTNULL(K);
+        REQUIRE(!K->csr_less, SMFEM_ERR_UNSUPPORTED, "this handle is a matrix-free operator without CSR arrays (smfem_matfree_operator)");
         REQUIRE(mesh->structured && K->structured, SMFEM_ERR_UNSUPPORTED, "pattern_rebuild: structured meshes only");
         pattern_build_structured(ctx, mesh, K);  // buffers exist: kernels only, no allocation, no host sync
     });
@@ -604,6 +605,7 @@ int smfem_reassemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Y
         NOTNULL(ctx);
         NOTNULL(mesh);
         NOTNULL(K);
+        REQUIRE(!K->csr_less, SMFEM_ERR_UNSUPPORTED, "this handle is a matrix-free operator without CSR arrays (smfem_matfree_operator)");
         REQUIRE(mesh->structured && K->structured, SMFEM_ERR_UNSUPPORTED, "reassemble: structured meshes only");
         if (const char *dbg = std::getenv("SMFEM_DEBUG_CLEAR"); dbg && dbg[0] == '1') {  // tests: prove every entry is rewritten
             CUDA_CHECK(cudaMemsetAsync(K->colind, 0xFF, sizeof(int32_t) * K->nnz_l, ctx->stream));
@@ -619,6 +621,7 @@ int smfem_assemble_values(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, dou
         NOTNULL(ctx);
         NOTNULL(mesh);
         NOTNULL(K);
+        REQUIRE(!K->csr_less, SMFEM_ERR_UNSUPPORTED, "this handle is a matrix-free operator without CSR arrays (smfem_matfree_operator)");
         int32_t *saved = mesh->id;
         if (K->nDof == 1) mesh->id = nullptr;
         try {
@@ -792,6 +795,7 @@ int smfem_matrix_export_csc(smfem_ctx *ctx, smfem_matrix *K, int which, int64_t 
     return guarded([&] {
         NOTNULL(ctx);
         NOTNULL(K);
+        REQUIRE(!K->csr_less, SMFEM_ERR_UNSUPPORTED, "this handle is a matrix-free operator without CSR arrays (smfem_matfree_operator)");
         export_csc(ctx, K, which, colptr, rowval, nzval);
     });
 }
@@ -842,8 +846,11 @@ int smfem_matrix_clone(smfem_ctx *ctx, smfem_matrix *K, smfem_matrix **out) {
         NOTNULL(ctx);
         NOTNULL(K);
         NOTNULL(out);
-        REQUIRE(K->rowptr && K->colind, SMFEM_ERR_INVALID, "matrix has no pattern yet");
+        REQUIRE(K->csr_less || (K->rowptr && K->colind), SMFEM_ERR_INVALID, "matrix has no pattern yet");
         smfem_matrix *C = new smfem_matrix();
+        C->csr_less = K->csr_less;
+        C->matfree_on = K->matfree_on;
+        C->mf_mesh = K->mf_mesh;
         C->ctx = ctx;
         C->ndim = K->ndim;
         C->nDof = K->nDof;
@@ -869,9 +876,11 @@ int smfem_matrix_clone(smfem_ctx *ctx, smfem_matrix *K, smfem_matrix **out) {
             dst = dev_alloc<T>(n);
             CUDA_CHECK(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
         };
-        dup(C->rowptr, (const int64_t *)K->rowptr, K->nrows_l + 1 + 8);
-        dup(C->colind, (const int32_t *)K->colind, K->nnz_l + 16);
-        dup(C->val, (const double *)K->val, K->nnz_l + 16);
+        if (!K->csr_less) {
+            dup(C->rowptr, (const int64_t *)K->rowptr, K->nrows_l + 1 + 8);
+            dup(C->colind, (const int32_t *)K->colind, K->nnz_l + 16);
+            dup(C->val, (const double *)K->val, K->nnz_l + 16);
+        }
         dup(C->bval, (const double *)K->bval, K->nnz_l);
         dup(C->diag, (const double *)K->diag, K->nrows_l);
         *out = C;
@@ -899,6 +908,12 @@ int smfem_surface_mass(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, const 
         NOTNULL(K);
         NOTNULL(mesh);
         REQUIRE(K->values_ready, SMFEM_ERR_INVALID, "assemble K before adding the surface term");
+        if (K->csr_less) {  // matrix-free operator: the term lives in the operator (beta) and in the diagonal
+            REQUIRE(!IEN_top && !IEN_btm && !keep_b && mesh->structured, SMFEM_ERR_UNSUPPORTED,
+                    "matrix-free operator: the surface term is the lattice's top / bottom faces (no explicit face lists, no stored b)");
+            matfree_add_surface(ctx, K, mesh, beta);
+            return;
+        }
         int32_t *faces = nullptr;
         int64_t nf = 0;
         if (IEN_top || IEN_btm) {
@@ -1060,11 +1075,52 @@ int smfem_comm_export(smfem_ctx *ctx, smfem_matrix *K, void *handle_out) {
     });
 }
 
+// The operator of assemble_system (src/fem.jl:135-256) for the hex lattice WITHOUT the assembled matrix: a handle that carries
+// the slab layout, the material, diag(K) (computed from the coordinates, for the Jacobi preconditioner) and nothing else.
+int smfem_matfree_operator(smfem_ctx *ctx, smfem_mesh *mesh, double Young, double nu, smfem_matrix **K_out) {
+    return guarded([&] {
+        NOTNULL(ctx);
+        NOTNULL(mesh);
+        NOTNULL(K_out);
+        CUDA_CHECK(cudaSetDevice(ctx->device));
+        REQUIRE(mesh->structured && mesh->ndim == 3, SMFEM_ERR_UNSUPPORTED, "matrix-free operator: structured 3-D hex lattice only");
+        smfem_matrix *K = new_matrix(ctx, mesh, 3, 3);
+        try {
+            const Lattice &L = mesh->lat;
+            K->structured = true;
+            K->csr_less = true;
+            K->lat = L;
+            K->m_g = 3 * mesh->nNodes_g;
+            const int64_t S1 = 3 * (int64_t)L.n1 - 2;
+            K->nnz_g = 9 * S1 * S1 * S1;  // what the assembled matrix would hold (reported by smfem_matrix_info; nnz_local = 0)
+            K->nnz_l = 0;
+            K->ghost_cols = L.plane() * 3;
+            K->nrows_l = (int64_t)L.nown() * L.plane() * 3;
+            K->ncols_l = K->nrows_l + 2 * K->ghost_cols;
+            K->row0 = (int64_t)L.k0 * L.plane() * 3;
+            REQUIRE(K->ncols_l < (int64_t)INT32_MAX, SMFEM_ERR_UNSUPPORTED, "local dof count exceeds int32 column indices");
+            K->Young = Young;
+            K->nu = nu;
+            K->beta_total = 0.0;
+            K->mat_known = true;
+            matfree_diag(ctx, K, mesh);
+            K->values_ready = true;
+            K->mf_mesh = mesh;
+            K->matfree_on = true;
+        } catch (...) {
+            smfem_matrix_free(K);
+            throw;
+        }
+        *K_out = K;
+    });
+}
+
 // SURVEY 8(f) row 3, second half: the solve's operator applied matrix-free (matfree.cu)
 int smfem_pcg_use_matrix_free(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, int enable) {
     return guarded([&] {
         NOTNULL(ctx);
         NOTNULL(K);
+        REQUIRE(enable || !K->csr_less, SMFEM_ERR_INVALID, "this operator has no assembled matrix to fall back to (smfem_matfree_operator)");
         if (enable) {
             NOTNULL(mesh);
             REQUIRE(mesh->structured && K->structured && K->ndim == 3 && K->nDof == 3, SMFEM_ERR_UNSUPPORTED,

@@ -341,6 +341,127 @@ __global__ void k_matfree_surface(const __grid_constant__ MfArgs A, int do_botto
     for (int c = 0; c < 3; ++c) dst[c] += A.beta * acc[c];
 }
 
+// diag(K) without K (the Jacobi preconditioner of a CSR-less operator): per element and Gauss point, with g_a = J^-T grad N_a,
+// K_aa[i][i] += w |det J| ((lam + mu) g_a,i^2 + mu |g_a|^2)   (= D11 g_i^2 + mu (|g|^2 - g_i^2), the diagonal of the assembly identity);
+// same colouring / reduction stores as the operator
+__global__ void __launch_bounds__(128) k_matfree_diag_color(const __grid_constant__ MfArgs A) {
+    const Lattice &L = A.L;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)A.nx * A.ny * A.nz) return;
+    const int tx = (int)(t % A.nx), ty = (int)((t / A.nx) % A.ny), tz = (int)(t / ((int64_t)A.nx * A.ny));
+    const int ex = 2 * tx + A.cx, ey = 2 * ty + A.cy, ez = A.ez0 + 2 * tz;
+    const int64_t n0 = L.lnode(ex, ey, ez);
+    const int64_t sy = L.n1, sz = L.plane();
+    double X[8][3], D[8][3];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int64_t ln = n0 + (u & 1) + ((u >> 1) & 1) * sy + (u >> 2) * sz;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            X[u][c] = A.coords[3 * ln + c];
+            D[u][c] = 0.0;
+        }
+    }
+#pragma unroll 1
+    for (int gp = 0; gp < 8; ++gp) {
+        const double xi = (gp & 1) ? A.gpc : -A.gpc, eta = (gp & 2) ? A.gpc : -A.gpc, zeta = (gp & 4) ? A.gpc : -A.gpc;
+        const double Xf[2] = {1.0 - xi, 1.0 + xi}, Yf[2] = {1.0 - eta, 1.0 + eta}, Zf[2] = {0.125 * (1.0 - zeta), 0.125 * (1.0 + zeta)};
+        double d[8][3];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int ox = u & 1, oy = (u >> 1) & 1, oz = u >> 2;
+            const double yz = Yf[oy] * Zf[oz], xz = Xf[ox] * Zf[oz], xy = 0.125 * Xf[ox] * Yf[oy];
+            d[u][0] = ox ? yz : -yz;
+            d[u][1] = oy ? xz : -xz;
+            d[u][2] = oz ? xy : -xy;
+        }
+        double J[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) J[q] = 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) J[r * 3 + k] += X[u][r] * d[u][k];
+        double adj[9];
+        adj[0] = J[4] * J[8] - J[5] * J[7];
+        adj[1] = J[2] * J[7] - J[1] * J[8];
+        adj[2] = J[1] * J[5] - J[2] * J[4];
+        adj[3] = J[5] * J[6] - J[3] * J[8];
+        adj[4] = J[0] * J[8] - J[2] * J[6];
+        adj[5] = J[2] * J[3] - J[0] * J[5];
+        adj[6] = J[3] * J[7] - J[4] * J[6];
+        adj[7] = J[1] * J[6] - J[0] * J[7];
+        adj[8] = J[0] * J[4] - J[1] * J[3];
+        const double det = J[0] * adj[0] + J[1] * adj[3] + J[2] * adj[6];
+        const double f = 1.0 / fabs(det);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            double g[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) g[c] = d[u][0] * adj[c] + d[u][1] * adj[3 + c] + d[u][2] * adj[6 + c];  // g_a det
+            const double n2 = A.mu * (g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) D[u][c] += f * ((A.lam + A.mu) * g[c] * g[c] + n2);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int k = ez + (u >> 2);
+        if (k < L.k0 || k >= L.k1) continue;
+        const int64_t ln = n0 + (u & 1) + ((u >> 1) & 1) * sy + (u >> 2) * sz;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) atomicAdd(A.y + 3 * (ln - sz) + c, D[u][c]);  // one contribution per address and launch
+    }
+}
+
+// diag += beta diag(b): one thread per node of a boundary plane, the same face integrals as k_matfree_surface
+__global__ void k_matfree_surface_diag(const __grid_constant__ MfArgs A, int do_bottom, int do_top) {
+    const Lattice &L = A.L;
+    const int n1 = L.n1;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t per = (int64_t)n1 * n1;
+    int k;
+    if (do_bottom && t < per) k = 0;
+    else {
+        if (do_bottom) t -= per;
+        if (!do_top || t >= per) return;
+        k = n1 - 1;
+    }
+    const int i = (int)(t % n1), j = (int)(t / n1);
+    double acc = 0.0;
+    for (int fy = j - 1; fy <= j; ++fy)
+        for (int fx = i - 1; fx <= i; ++fx) {
+            if (fx < 0 || fy < 0 || fx >= L.ne || fy >= L.ne) continue;
+            const int ox[4] = {0, 1, 1, 0}, oy[4] = {0, 0, 1, 1};
+            double Xf[4][3];
+            int a = 0;
+            for (int b = 0; b < 4; ++b) {
+                const int64_t nb = L.lnode(fx + ox[b], fy + oy[b], k);
+                for (int c = 0; c < 3; ++c) Xf[b][c] = A.coords[3 * nb + c];
+                if (fx + ox[b] == i && fy + oy[b] == j) a = b;
+            }
+            for (int g = 0; g < 4; ++g) {
+                const double xi = (ox[g] ? A.gpc : -A.gpc), eta = (oy[g] ? A.gpc : -A.gpc);
+                double t1[3] = {0, 0, 0}, t2[3] = {0, 0, 0}, Na = 0.0;
+                for (int b = 0; b < 4; ++b) {
+                    const double sx = ox[b] ? 1.0 : -1.0, sy = oy[b] ? 1.0 : -1.0;
+                    const double N = 0.25 * (1.0 + sx * xi) * (1.0 + sy * eta), dNx = 0.25 * sx * (1.0 + sy * eta), dNe = 0.25 * sy * (1.0 + sx * xi);
+                    if (b == a) Na = N;
+                    for (int c = 0; c < 3; ++c) {
+                        t1[c] += Xf[b][c] * dNx;
+                        t2[c] += Xf[b][c] * dNe;
+                    }
+                }
+                const double nx = t1[1] * t2[2] - t1[2] * t2[1], ny = t1[2] * t2[0] - t1[0] * t2[2], nz = t1[0] * t2[1] - t1[1] * t2[0];
+                acc += sqrt(nx * nx + ny * ny + nz * nz) * Na * Na;
+            }
+        }
+    double *dst = A.y + 3 * (L.lnode(i, j, k) - L.plane());
+    for (int c = 0; c < 3; ++c) dst[c] += A.beta * acc;
+}
+
 // the boundary-plane rows of a slab read ghost planes written by the neighbours: wait for the halo flags (one thread)
 __global__ void k_matfree_wait_halo(CommView cv, PcgScalars *scal, int check_done, unsigned long long halo_need) {
     if (check_done && scal->done) return;
@@ -405,4 +526,57 @@ void matfree_apply(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y, 
         const int64_t n = (int64_t)(bot + top) * L.n1 * L.n1;
         LAUNCH(ctx, k_matfree_surface, (unsigned)((n + 127) / 128), 128, 0, A, bot, top);
     }
+}
+
+// ---- the operator WITHOUT an assembled K (smfem_matfree_operator): only the diagonal is computed, for the Jacobi preconditioner
+static MfArgs matfree_args(smfem_matrix *K, smfem_mesh *mesh, double *y) {
+    MfArgs A;
+    A.L = K->lat;
+    A.coords = mesh->coords;
+    A.x = nullptr;
+    A.y = y;
+    const double f = K->Young / ((1 + K->nu) * (1 - 2 * K->nu));  // src/fem.jl:230
+    A.lam = K->nu * f;
+    A.mu = (1 - 2 * K->nu) / 2 * f;
+    A.beta = 0.0;
+    double xi[2], w[2];
+    smfem_host_gauss(-1, 1, 2, xi, w);
+    A.gpc = xi[1];
+    A.scal = nullptr;
+    A.check_done = 0;
+    return A;
+}
+
+void matfree_diag(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh) {
+    const Lattice &L = K->lat;
+    if (!K->diag) K->diag = dev_alloc<double>(K->nrows_l);
+    CUDA_CHECK(cudaMemsetAsync(K->diag, 0, sizeof(double) * K->nrows_l, ctx->stream));
+    MfArgs A = matfree_args(K, mesh, K->diag);
+    const int l0 = L.k0 > 0 ? L.k0 - 1 : 0, l1 = L.k1 - 1 < L.ne - 1 ? L.k1 - 1 : L.ne - 1;
+    for (int c = 0; c < 8; ++c) {
+        A.cx = c & 1;
+        A.cy = (c >> 1) & 1;
+        A.cz = c >> 2;
+        A.nx = (L.ne - A.cx + 1) / 2;
+        A.ny = (L.ne - A.cy + 1) / 2;
+        A.ez0 = l0 + (((l0 & 1) != A.cz) ? 1 : 0);
+        A.nz = A.ez0 > l1 ? 0 : (l1 - A.ez0) / 2 + 1;
+        const int64_t n = (int64_t)A.nx * A.ny * A.nz;
+        if (n <= 0) continue;
+        LAUNCH(ctx, k_matfree_diag_color, (unsigned)((n + 127) / 128), 128, 0, A);
+    }
+}
+
+// K_bar = K + beta b for a CSR-less operator: only the diagonal and the operator's beta change
+void matfree_add_surface(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, double beta) {
+    const Lattice &L = K->lat;
+    const int bot = (L.k0 == 0), top = (L.k1 == L.n1);
+    if (beta != 0.0 && (bot || top)) {
+        MfArgs A = matfree_args(K, mesh, K->diag);
+        A.beta = beta;
+        const int64_t n = (int64_t)(bot + top) * L.n1 * L.n1;
+        LAUNCH(ctx, k_matfree_surface_diag, (unsigned)((n + 127) / 128), 128, 0, A, bot, top);
+    }
+    K->beta_total += beta;
+    K->gmg_dirty = true;
 }

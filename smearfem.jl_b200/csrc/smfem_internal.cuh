@@ -189,6 +189,7 @@ struct smfem_matrix {
     void *gmg = nullptr;            // Gmg* (gmg.cu), built at the first multigrid solve
     smfem_mesh *gmg_mesh = nullptr;  // not owned
     bool gmg_on = false, gmg_dirty = true;
+    bool csr_less = false;            // smfem_matfree_operator: no rowptr / colind / val at all (the operator is applied matrix-free only)
     bool matfree_on = false;          // the solve's operator is applied matrix-free from mf_mesh's coordinates (matfree.cu)
     smfem_mesh *mf_mesh = nullptr;    // not owned
     bool gmg_coarse = false;          // a coarse-level operator owned by a multigrid hierarchy: no peer window region of its own
@@ -294,7 +295,9 @@ void smfem_set_last_error(const char *msg);
 void extract_borders(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, const int64_t *ids, int64_t n, const double *cam, int state,
                      int64_t ne, double *border_out, int64_t cap, int64_t *nborder, double *side2d_out);  // postprocess.cu
 // matfree.cu: y = (K + beta b) x from the lattice coordinates (no CSR arrays read); same vector layout as the CSR SpMV
-void matfree_apply(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y, bool halo, bool check_done, unsigned long long halo_need);  // abi.cu: message for the calling thread's smfem_last_error()
+void matfree_apply(smfem_ctx *ctx, smfem_matrix *K, const double *x, double *y, bool halo, bool check_done, unsigned long long halo_need);
+void matfree_diag(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh);                          // diag(K) from the coordinates
+void matfree_add_surface(smfem_ctx *ctx, smfem_matrix *K, smfem_mesh *mesh, double beta);      // CSR-less K += beta b  // abi.cu: message for the calling thread's smfem_last_error()
 
 // true exactly once per (call site, device): per-function attributes (dynamic shared memory limits) are per device, and one
 // process may drive several GPUs (smfem_init_multi)

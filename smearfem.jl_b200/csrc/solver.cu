@@ -945,7 +945,7 @@ static void launch_spmv_group(smfem_ctx *ctx, smfem_matrix *K, const SpmvArgs &A
 }
 
 static void spmv_stream_setup(smfem_ctx *ctx, smfem_matrix *K) {
-    if (K->blk_row) return;
+    if (K->blk_row || K->csr_less) return;  // a CSR-less operator has no rows to analyse
     int *d_max = dev_alloc<int>(1);
     CUDA_CHECK(cudaMemsetAsync(d_max, 0, sizeof(int), ctx->stream));
     LAUNCH(ctx, k_max_rowlen, (unsigned)((K->nrows_l + 255) / 256), 256, 0, K->nrows_l, (const int64_t *)K->rowptr, d_max);

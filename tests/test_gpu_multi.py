@@ -168,6 +168,16 @@ def _worker_large(rank, ws, port, ne, q):
         out["mf_iters"], out["mf_relres"] = itf, relf
         out["mf_rel_u"] = float(np.linalg.norm(qf - us[r0:r0 + nr]) / np.linalg.norm(us[r0:r0 + nr]))
         K.use_matrix_free(False)
+        # ... and the operator handle that never holds K (smfem_matfree_operator), Jacobi- and multigrid-preconditioned
+        F = sf.SparseMatrixB200.matrix_free(ctx, mesh, 40, 0.4).add_surface_mass(100.0)
+        sd.connect(F)
+        F.set_dirichlet_zplanes(0.001)
+        qh, ith, relh = F.pcg_solve(rtol=1e-13, maxit=20000, rhs_extra=rhs[r0:r0 + nr])
+        F.use_multigrid(True)
+        qk, itk, relk = F.pcg_solve(rtol=1e-13, maxit=200, rhs_extra=rhs[r0:r0 + nr])
+        out["csrless_rel_u"] = float(max(np.linalg.norm(v - us[r0:r0 + nr]) for v in (qh, qk)) / np.linalg.norm(us[r0:r0 + nr]))
+        out["csrless_iters"], out["csrless_gmg_iters"], out["csrless_relres"] = ith, itk, max(relh, relk)
+        F.free()
         # consecutive solves with NO host barrier between them (rank-dependent host delays provoke the race the protocol must survive)
         import time
         for rep in range(4):
@@ -216,7 +226,8 @@ def test_slab_partition_bit_equivalence_and_manufactured_solution(ws, ne):
         assert r["relres"] <= 1e-12 and r["rel_u"] <= 1e-10, r
         assert r["rel_vs_1gpu"] <= 1e-10 and abs(r["iters"] - r["iters_1gpu"]) <= 2, r
         assert r["gmg_rel_u"] <= 1e-10 and r["gmg_relres"] <= 1e-12 and r["gmg_iters"] <= 45 and r["gmg_iters"] <= r["gmg_iters_1gpu"] + 6, r
-        assert r["mf_rel_u"] <= 1e-10 and r["mf_relres"] <= 1e-12 and abs(r["mf_iters"] - r["iters"]) <= 2, r
+        assert r["mf_rel_u"] <= 1e-10 and r["mf_relres"] <= 1e-12 and abs(r["mf_iters"] - r["iters"]) <= max(2, r["iters"] // 100), r
+        assert r["csrless_rel_u"] <= 1e-10 and r["csrless_relres"] <= 1e-12 and abs(r["csrless_iters"] - r["iters"]) <= max(2, r["iters"] // 100) and r["csrless_gmg_iters"] <= 60, r
 
 
 def _single_process_worker(ws, ne, q):

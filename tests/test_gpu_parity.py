@@ -566,6 +566,43 @@ def test_matrix_free_pcg_matches_oracle(ne):
     mesh.free()
 
 
+@pytest.mark.parametrize("ne", [3, 12, 33])
+def test_matrix_free_operator_without_assembled_matrix(ne):
+    """smfem_matfree_operator: the operator handle that never holds K (no rowptr / colind / val).  Its diagonal, its products and the
+    solves through it (Jacobi-PCG and multigrid-PCG, incl. the surface term and the Dirichlet data) equal those of the assembled
+    K_bar / the oracle; calls that need CSR arrays fail loudly."""
+    ctx = sf.context()
+    NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
+    o.inflate_sphere(NL, 0, 1, 0, 1)
+    o.jitter_nodes(NL, ne, seed=4)
+    mesh = sf.Mesh.meshgrid(ctx, 0, 1, 0, 1, 0, 1, ne, 3).set_nodelist(NL)
+    K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4).add_surface_mass(100.0)
+    F = sf.SparseMatrixB200.matrix_free(ctx, mesh, 40, 0.4)
+    assert F.info()["nnz_local"] == 0 and F.info()["nnz"] == K.info()["nnz"] and F.shape == K.shape
+    F.add_surface_mass(100.0)
+    assert rel(F.diag(), K.diag()) <= 1e-13
+    x = np.random.default_rng(ne).standard_normal(3 * (ne + 1) ** 3)
+    assert rel(F.spmv(x), K.spmv(x)) <= 1e-13
+    for M in (K, F):
+        M.set_dirichlet_zplanes(0.001)
+    q0, it0, _ = K.pcg_solve(rtol=1e-13, maxit=20000)
+    q1, it1, rel1 = F.pcg_solve(rtol=1e-13, maxit=20000)
+    assert rel(q1, q0) <= 1e-10 and rel1 <= 1e-12 and abs(it1 - it0) <= max(2, it0 // 100)   # rtol 1e-13 sits at the rounding floor
+    F.use_multigrid(True)
+    q2, it2, rel2 = F.pcg_solve(rtol=1e-13, maxit=200)
+    assert rel(q2, q0) <= 1e-10 and rel2 <= 1e-12 and it2 <= 60   # jittered lattice, rtol 1e-13
+    F.use_multigrid(False)
+    C2 = F.clone()
+    assert np.array_equal(C2.diag(), F.diag())
+    C2.free()
+    for bad in (lambda: F.to_csc(), lambda: F.reassemble(40, 0.4), lambda: F.use_matrix_free(False)):
+        with pytest.raises(sf.SmearFEMError):
+            bad()
+    F.free()
+    K.free()
+    mesh.free()
+
+
 def test_spmv_variants_and_host_spmv():
     ne = 9
     NL, IEN, ID, *_ = o.meshgrid(0, 1, 0, 1, 0, 1, ne, 3)
