@@ -249,6 +249,14 @@ function use_matrix_free!(K̄::B200SparseMatrix, enable::Bool=true)
     return K̄
 end
 
+# ---- the lattice operator WITHOUT an assembled matrix (diag(K) only): solve / use_multigrid! / K + β*b work on it, SparseMatrixCSC does not
+function matrix_free_operator(NodeList, IEN, ID, ne, Young, ν)
+    mesh = mesh_from_host(Matrix{Float64}(NodeList), Matrix{Int64}(IEN), Matrix{Int64}(ID), 3, 3, ne)
+    kh = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:smfem_matfree_operator, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Ptr{Ptr{Cvoid}}), context().h, mesh.h, Young, ν, kh))
+    K = B200SparseMatrix(kh[], mesh); finalizer(free!, K); return K
+end
+
 # ---- extract_borders(NodeList_new, CameraMatrix, BorderNodesList, state, ne) (src/PostProcess.jl:60-117) on the device, with
 #      NodeList_new = NodeList + motion of the last solve; returns (BorderPoints, SideNodes2D) like the reference
 function extract_borders_device(K̄::B200SparseMatrix, CameraMatrix, BorderNodesList, state::AbstractString, ne=nothing)
