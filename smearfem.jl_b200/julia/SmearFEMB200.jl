@@ -202,6 +202,13 @@ function add_surface_mass!(K::B200SparseMatrix, b::SurfaceMatrix)          # K +
                 context().h, K.h, b.mesh.h, b.IEN_top, b.IEN_btm, size(b.IEN_top, 1), b.β, 0))
     return K
 end
+# K += β*b over the lattice's own top / bottom faces (no face lists; also valid for a matrix-free operator)
+function add_surface_mass!(K::B200SparseMatrix, β::Real)
+    check(ccall((:smfem_surface_mass, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Int64, Cdouble, Cint),
+                context().h, K.h, K.mesh.h, C_NULL, C_NULL, 0, Float64(β), 0))
+    return K
+end
 # K̄ = K + β*b (examples/vector3D.jl:308): a NEW device matrix, K stays K as in the reference
 Base.:+(K::B200SparseMatrix, b::SurfaceMatrix) = add_surface_mass!(clone(K), b)
 
@@ -249,7 +256,8 @@ function use_matrix_free!(K̄::B200SparseMatrix, enable::Bool=true)
     return K̄
 end
 
-# ---- the lattice operator WITHOUT an assembled matrix (diag(K) only): solve / use_multigrid! / K + β*b work on it, SparseMatrixCSC does not
+# ---- the lattice operator WITHOUT an assembled matrix (diag(K) only): solve / use_multigrid! / add_surface_mass!(K, β) work on it,
+#      SparseMatrixCSC(K) and K + β*b (explicit face lists) do not
 function matrix_free_operator(NodeList, IEN, ID, ne, Young, ν)
     mesh = mesh_from_host(Matrix{Float64}(NodeList), Matrix{Int64}(IEN), Matrix{Int64}(ID), 3, 3, ne)
     kh = Ref{Ptr{Cvoid}}(C_NULL)
