@@ -401,9 +401,16 @@ def main():
             pcg["multigrid"] = {"iters": itg, "relres": relg, "ms_total": max_over_ranks(K.pcg_stats()["ms_total"]),
                                 "ms_first_solve_with_hierarchy_build": ms_first,
                                 "note": "CG + V-cycle (re-assembled coarse levels, Chebyshev(2) smoothing); Jacobi-PCG above is the north-star path"}
+            # ... and with the matrix-free operator for the fine-level products of the cycle and of the outer CG
+            K.use_matrix_free(True)
+            K.pcg_solve(rtol=1e-10, maxit=500, want_q=False)
+            _, itf2, relf2 = K.pcg_solve(rtol=1e-10, maxit=500, want_q=False)
+            pcg["multigrid_matrix_free"] = {"iters": itf2, "relres": relf2, "ms_total": max_over_ranks(K.pcg_stats()["ms_total"])}
+            K.use_matrix_free(False)
             K.use_multigrid(False)
         except Exception as exc:  # never let the optional measurement take the bench line down
             pcg["multigrid"] = {"error": str(exc)[:200]}
+            K.use_matrix_free(False)
             K.use_multigrid(False)
         # solution check at the bench size: a smooth manufactured field u* through the example's boundary conditions
         # (u_z = 0 on z = 0, u_z = -d on z = 1); rhs = K_bar u* with the library's own (multi-rank) SpMV; ||u - u*|| / ||u*||

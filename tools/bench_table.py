@@ -15,6 +15,6 @@ for f in sys.argv[1:]:
     print(f"| {d['n_gpus']} | {d['config']['ne']}³ | {d['value'] / 1e6:.0f} M | {d['ms_per_step']:.3f} | {r['ms_per_launch']:.3f} ({r['achieved']:.0f}, {r['frac']:.3f}) | "
           f"{r['values_only']['ms_per_launch']:.3f} ({r['values_only']['frac']:.3f}) | {r['fp64']['frac']:.3f} | "
           f"{s['ms']:.3f} ({s['frac']:.2f}; {s['csr_algorithmic']['frac']:.2f}) | {mf.get('ms', float('nan')):.3f} | "
-          f"{p['iters']} × {p['ms_per_iter']:.3f} ({pm.get('ms_per_iter', float('nan')):.3f}) | {g.get('iters')} it, {g.get('ms_total', float('nan')):.0f} ms | "
+          f"{p['iters']} × {p['ms_per_iter']:.3f} ({pm.get('ms_per_iter', float('nan')):.3f}) | {g.get('iters')} it, {g.get('ms_total', float('nan')):.0f} ms ({(p.get('multigrid_matrix_free') or {}).get('ms_total', float('nan')):.0f} ms matrix-free) | "
           f"{m.get('jacobi_pcg', {}).get('rel_u', float('nan')):.1e} / {m.get('multigrid_pcg', {}).get('rel_u', float('nan')):.1e} | "
           f"{e['value'] / 1e6:.0f} M ({e['ms_per_step']:.2f}) | {pipe.get('ms_total', float('nan')):.0f} |")
