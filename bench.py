@@ -561,10 +561,8 @@ def main():
     # src/fem.jl:253) to host memory, at 50^3 (0.37 GB of CSC per call), one GPU
     if world == 1:
         try:
-            from oracle import fem_oracle as o50   # host mesh builder only (test infrastructure used to make INPUT arrays)
-
-            NL5, IEN5, ID5, *_ = o50.meshgrid(0, 1, 0, 1, 0, 1, 50, 3)
-            o50.inflate_sphere(NL5, 0, 1, 0, 1)
+            NL5, IEN5, ID5, *_ = sf.meshgrid(0, 1, 0, 1, 0, 1, 50, 3)   # the product's own meshgrid / inflate_sphere (host arrays out)
+            NL5 = sf.inflate_sphere(NL5, 0, 1, 0, 1)
             ts = []
             for _ in range(3):
                 t0 = time.perf_counter()

@@ -1142,7 +1142,8 @@ void values_assemble(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, double Y
                 dev_free(d_m);
             }
             const size_t smem = 4 * gather_warp_bytes(max_slots);
-            if (mesh->g_state == 1 && max_slots > 0 && max_slots < 255 && smem <= 110 * 1024) {
+            // (the per-element scratch is 576 B per element: beyond 8 GB the scatter forms take over)
+            if (mesh->g_state == 1 && max_slots > 0 && max_slots < 255 && smem <= 110 * 1024 && mesh->nEl_g * 576 <= ((int64_t)8 << 30)) {
                 static std::atomic<unsigned long long> attr_set{0};
                 if (first_use_on_device(attr_set))
                     CUDA_CHECK(cudaFuncSetAttribute(k_values_gather, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
