@@ -381,6 +381,10 @@ def main():
         ms_tot = max_over_ranks(st["ms_total"])
         pcg = {"iters": it, "relres": relres, "ms_total": ms_tot, "ms_per_iter": ms_tot / max(it, 1),
                "spmv_GB/s_in_solve_per_gpu": b_spmv / (ms_tot / max(it, 1) * 1e-3) / 1e9, "rtol": 1e-10}
+        ws = K.pcg_wait_stats()   # where an iteration waits for the other ranks (this rank's first CTA; max over ranks)
+        pcg["wait_us_per_iter"] = {k.replace("_us", ""): max_over_ranks(v) / max(it, 1) for k, v in ws.items()}
+        pcg["wait_us_per_iter"]["note"] = ("time the first CTA spins on the neighbours' halo flags (boundary-plane SpMV launches) and on the two "
+                                           "mailbox all-reduces per iteration; %globaltimer, summed over the solve / iterations, max over ranks")
         sd.barrier(ctx)
         try:   # the same Jacobi-PCG with the matrix-free operator
             K.use_matrix_free(True)

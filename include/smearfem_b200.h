@@ -262,6 +262,11 @@ int smfem_bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, flo
 int smfem_set_spmv_variant(smfem_matrix *K, int variant);
 /* statistics of the last smfem_pcg_solve on this matrix */
 int smfem_pcg_stats(smfem_matrix *K, float *ms_total, float *ms_spmv_est, int *iters);
+/* Wait accounting of the last Jacobi-PCG solve on K (several ranks): microseconds the first CTA spent spinning on the neighbours'
+ * halo flags (boundary-plane SpMV launches / the matrix-free operator's halo wait) and on the two mailbox all-reduces of an
+ * iteration (r'z, r'r before the search-direction update; p'Ap before the x / r update), summed over the solve (%globaltimer).
+ * Measurement only; any pointer may be NULL. */
+int smfem_pcg_wait_stats(smfem_matrix *K, double *halo_us, double *allreduce_rz_us, double *allreduce_pap_us);
 
 /* ---- multi-GPU peer window (one process per GPU) ----------------------------------------------
  * After smfem_pattern_build / smfem_assemble each rank creates its communication window (halo

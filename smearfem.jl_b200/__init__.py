@@ -370,6 +370,12 @@ class SparseMatrixB200:
         call("smfem_pcg_stats", self.handle, C.byref(ms), C.byref(ms2), C.byref(it))
         return dict(ms_total=float(ms.value), iters=int(it.value))
 
+    def pcg_wait_stats(self):
+        """us the first CTA spent waiting on halo flags / the r'z all-reduce / the p'Ap all-reduce during the last Jacobi-PCG solve."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        call("smfem_pcg_wait_stats", self.handle, C.byref(a), C.byref(b), C.byref(c))
+        return dict(halo_us=a.value, allreduce_rz_us=b.value, allreduce_pap_us=c.value)
+
     def spmv(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
         y = np.zeros_like(x)

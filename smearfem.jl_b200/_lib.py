@@ -80,6 +80,7 @@ SIGNATURES = {
     "smfem_bench_spmv": [_vp, _vp, C.c_int, C.c_int, C.POINTER(C.c_float)],
     "smfem_set_spmv_variant": [_vp, C.c_int],
     "smfem_pcg_stats": [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)],
+    "smfem_pcg_wait_stats": [_vp, _f64p, _f64p, _f64p],
     "smfem_comm_export": [_vp, _vp, _vp],
     "smfem_comm_connect": [_vp, _vp, _vp],
     "smfem_comm_prepare": [_vp, _vp],

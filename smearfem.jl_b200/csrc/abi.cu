@@ -1049,6 +1049,16 @@ int smfem_bench_spmv(smfem_ctx *ctx, smfem_matrix *K, int variant, int reps, flo
     });
 }
 
+// Jacobi-PCG of the last solve: microseconds CTA 0 spent waiting for the neighbours' halo flags and for the two all-reduces
+int smfem_pcg_wait_stats(smfem_matrix *K, double *halo_us, double *allreduce_rz_us, double *allreduce_pap_us) {
+    return guarded([&] {
+        NOTNULL(K);
+        if (halo_us) *halo_us = K->last_wait_us[0];
+        if (allreduce_rz_us) *allreduce_rz_us = K->last_wait_us[1];
+        if (allreduce_pap_us) *allreduce_pap_us = K->last_wait_us[2];
+    });
+}
+
 int smfem_set_spmv_variant(smfem_matrix *K, int variant) {
     return guarded([&] {
         NOTNULL(K);

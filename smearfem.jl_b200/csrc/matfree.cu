@@ -466,6 +466,7 @@ __global__ void k_matfree_surface_diag(const __grid_constant__ MfArgs A, int do_
 __global__ void k_matfree_wait_halo(CommView cv, PcgScalars *scal, int check_done, unsigned long long halo_need) {
     if (check_done && scal->done) return;
     const unsigned long long need = halo_need ? halo_need : scal->it + 1;
+    const unsigned long long t0 = global_timer_ns();
     unsigned spins = 0;
     if (cv.rank > 0)
         while (ld_acquire_sys(&cv.self->hflag[0]) < need)
@@ -473,6 +474,7 @@ __global__ void k_matfree_wait_halo(CommView cv, PcgScalars *scal, int check_don
     if (cv.rank < cv.nranks - 1)
         while (ld_acquire_sys(&cv.self->hflag[1]) < need)
             if (++spins > (1u << 28)) __trap();
+    scal->t_wait_halo += global_timer_ns() - t0;  // wait accounting (smfem_pcg_wait_stats)
 }
 
 }  // namespace

@@ -159,6 +159,10 @@ struct PcgScalars {
     double rtol2, rr_true;
     unsigned int iters, maxit, done, pad_;
     unsigned long long hseq, gseq, rseq;  // multigrid-PCG: halo pushes / all-gathers / all-reduces issued so far
+    // Jacobi-PCG wait accounting of the current solve (ns of %globaltimer, CTA 0 only): time spent spinning on the neighbours'
+    // halo flags inside the boundary-plane SpMV launches, and on the two all-reduce mailboxes (r'z / r'r before update_p, p'Ap
+    // before update_xr).  Reset by k_pcg_init; smfem_pcg_wait_stats reports them.
+    unsigned long long t_wait_halo, t_wait_rz, t_wait_pap;
 };
 
 struct CommView {  // passed by value to kernels
@@ -221,6 +225,7 @@ struct smfem_matrix {
     bool stream_ok = false, group3_ok = false;
     // stats
     float last_ms = 0, last_ms_spmv = 0;
+    double last_wait_us[3] = {0, 0, 0};  // halo flags, r'z all-reduce, p'Ap all-reduce (CTA 0, whole solve)
     int last_iters = 0;
 };
 
@@ -233,6 +238,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ double ld_volatile_f64(const double *p) {
     double v;

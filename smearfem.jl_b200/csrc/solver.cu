@@ -58,15 +58,18 @@ __device__ void allreduce_publish(const CommView &cv, unsigned long long seq, in
     for (int q = 0; q < cv.nranks; ++q) st_release_sys(&cv.peer[q]->mflag[slot][cv.rank], seq);
 }
 
-__device__ void allreduce_fetch(const CommView &cv, unsigned long long seq, int nv, double *out) {
+// wait_ns (optional): accumulates the time this call spent waiting for the peers' flags
+__device__ void allreduce_fetch(const CommView &cv, unsigned long long seq, int nv, double *out, unsigned long long *wait_ns = nullptr) {
     int slot = (int)(seq & 3ull);
     for (int v = 0; v < nv; ++v) out[v] = 0.0;
+    const unsigned long long t0 = wait_ns ? global_timer_ns() : 0ull;
     for (int q = 0; q < cv.nranks; ++q) {
         unsigned spins = 0;
         while (ld_acquire_sys(&cv.self->mflag[slot][q]) != seq)
             if (++spins > (1u << 26)) __trap();  // a peer that died must surface as an error, not as a hang
         for (int v = 0; v < nv; ++v) out[v] += ld_volatile_f64(&cv.self->mbox[slot][q][v]);
     }
+    if (wait_ns) *wait_ns += global_timer_ns() - t0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -801,12 +804,15 @@ __global__ void __launch_bounds__(256, 3) k_spmv_group(SpmvArgs A) {
             if (lo || hi) {
                 if (lane == 0) {
                     const unsigned long long need = SPMV_HALO_NEED(A);
+                    const bool rec = blockIdx.x == 0 && threadIdx.x == 0;  // wait accounting: the first warp of the launch
+                    const unsigned long long t0 = rec ? global_timer_ns() : 0ull;
                     if (lo)
                         while (ld_acquire_sys(&A.cv.self->hflag[0]) < need) {
                         }
                     if (hi)
                         while (ld_acquire_sys(&A.cv.self->hflag[1]) < need) {
                         }
+                    if (rec) A.scal->t_wait_halo += global_timer_ns() - t0;
                 }
                 __syncwarp();
             }
@@ -1065,7 +1071,7 @@ k_pcg_update_p(int64_t n, int64_t ghost_cols, const double *__restrict__ r, cons
     if (threadIdx.x == 0) {
         const bool first = scal->spare != 0.0;  // spare != 0 marks the first iteration of a solve
         double v[3];
-        allreduce_fetch(cv, 2ull * it, first ? 3 : 2, v);  // (rz_k, rr_k [, ||b||^2]) published by the previous C / init
+        allreduce_fetch(cv, 2ull * it, first ? 3 : 2, v, blockIdx.x == 0 ? &scal->t_wait_rz : nullptr);  // (rz_k, rr_k [, ||b||^2]) published by the previous C / init
         const double bn2 = first ? v[2] : scal->bnorm2;
         // the stopping test: every CTA of every rank evaluates it on bitwise identical numbers
         const bool stop = !(v[1] > scal->rtol2 * bn2) || scal->iters >= scal->maxit || scal->breakdown != 0;
@@ -1127,7 +1133,7 @@ k_pcg_update_xr(int64_t n, int64_t ghost_cols, const double *__restrict__ p, con
     const unsigned long long it = scal->it;
     if (threadIdx.x == 0) {
         double pAp;
-        allreduce_fetch(cv, 2ull * it + 1ull, 1, &pAp);
+        allreduce_fetch(cv, 2ull * it + 1ull, 1, &pAp, blockIdx.x == 0 ? &scal->t_wait_pap : nullptr);
         double rz = scal->rzs[it & 1ull];
         double alpha = 0.0;
         if (pAp > 0.0) alpha = rz / pAp;
@@ -1240,6 +1246,7 @@ k_pcg_init(int64_t n, const double *__restrict__ Kqd, const double *__restrict__
             scal->maxit = maxit;
             scal->iters = 0;
             scal->done = 0;
+            scal->t_wait_halo = scal->t_wait_rz = scal->t_wait_pap = 0ull;
             double v[3] = {t1, t2, t3};
             allreduce_publish(cv, 2ull * it + 2ull, 3, v);
             __threadfence();
@@ -1756,6 +1763,9 @@ void pcg_solve(smfem_ctx *ctx, smfem_matrix *K, double rtol, int maxit, const do
     CUDA_CHECK(cudaEventSynchronize(ctx->ev3));
     CUDA_CHECK(cudaEventElapsedTime(&K->last_ms, ctx->ev2, ctx->ev3));
     K->last_iters = it;
+    K->last_wait_us[0] = 1e-3 * (double)h->t_wait_halo;
+    K->last_wait_us[1] = 1e-3 * (double)h->t_wait_rz;
+    K->last_wait_us[2] = 1e-3 * (double)h->t_wait_pap;
     K->sol_x = K->x;
     K->last_relres_rec = bnorm2 > 0 ? std::sqrt(res2 / bnorm2) : 0.0;
     K->last_relres_true = bnorm2 > 0 ? std::sqrt(res2_true / bnorm2) : 0.0;
