@@ -790,7 +790,7 @@ k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64
 // written exactly once, by the warp that owns its row - no memset, no atomics, no colour passes (the scatter forms move each
 // entry of K through L2 / DRAM once per contributing element: 8x for interior nodes, and K >> L2).
 //   plan (once per mesh): the (element, local node) pairs of every node, sorted by element -> fold order = ascending element
-//       index, the order in which sparse(E,J,V) folds duplicates (src/fem.jl:253); nodes are cut into warp tasks of <= 32 pairs.
+//       index, the order in which sparse(E,J,V) folds duplicates (src/fem.jl:253); nodes are cut into warp tasks of <= 16 pairs.
 //   element pass: A = sqrt(w |det J|) J^-1 per (element, Gauss point) -> 576 B per element of scratch (k_gather_elem);
 //   kernel: lane = one (node a, element e) pair: the 8 blocks G_ab = sum_gp (dN_a A)(dN_b A)' of "its" element in registers (72
 //       accumulators, no coordinates, no Jacobian: the next Gauss point's A is loaded while this one's 153 FMAs run), parked in a
@@ -799,6 +799,8 @@ k_values_atomic(Conn C, DofMap D, const double *__restrict__ coords, const int64
 //       entries of every neighbour block are summed over the pairs in element order by all 32 lanes, and the warp streams the
 //       node's 3 CSR rows out with the material applied - coalesced, contiguous (the rows of a node are adjacent).
 // ------------------------------------------------------------------------------------------------
+
+constexpr int GATHER_PAIRS = 16;  // (node, element) pairs per warp task: TWO lanes per pair (4 of the 8 blocks each)
 
 __global__ void k_max_rowlen_nodes(int64_t nNodes, const int64_t *__restrict__ rowptr, int *__restrict__ out) {
     int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -862,15 +864,15 @@ void mesh_build_gather(smfem_ctx *ctx, smfem_mesh *mesh) {
         CUDA_CHECK(cudaMemcpyAsync(h_ptr.data(), ptr, sizeof(int64_t) * (nNodes + 1), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-        if (h_max > 32) {  // a node shared by more than 32 elements: the scatter forms handle it
+        if (h_max > GATHER_PAIRS) {  // a node shared by more elements than a warp task holds: the scatter forms handle it
             fail();
             return;
         }
-        std::vector<int32_t> task;  // greedy: whole nodes, <= 32 pairs per warp task
+        std::vector<int32_t> task;  // greedy: whole nodes, <= GATHER_PAIRS pairs per warp task
         task.push_back(0);
         int64_t start = 0;
         for (int64_t n = 0; n < nNodes; ++n)
-            if (h_ptr[n + 1] - start > 32) {
+            if (h_ptr[n + 1] - start > GATHER_PAIRS) {
                 task.push_back((int32_t)n);
                 start = h_ptr[n];
             }
@@ -893,8 +895,9 @@ void mesh_build_gather(smfem_ctx *ctx, smfem_mesh *mesh) {
 
 constexpr int GATHER_STAGE = 73;  // doubles per lane in the staging area (72 + 1: odd stride, conflict-free)
 __host__ __device__ inline size_t gather_warp_bytes(int max_slots) {
-    // stage[32][73] f64 | red[max_slots][9] f64 | adj_all[32][max_slots] i32 | pnodes[32][8] i32   (16-byte aligned pieces)
-    size_t b = sizeof(double) * (32 * GATHER_STAGE + (size_t)((max_slots + 1) & ~1) * 9) + 4 * 32 * (size_t)((max_slots + 3) & ~3) + 4 * 32 * 8;
+    // stage[16][73] f64 | red[max_slots][9] f64 | adj_all[16][max_slots] i32 | pnodes[16][8] i32   (16-byte aligned pieces)
+    size_t b = sizeof(double) * (GATHER_PAIRS * GATHER_STAGE + (size_t)((max_slots + 1) & ~1) * 9) + 4 * GATHER_PAIRS * (size_t)((max_slots + 3) & ~3) +
+               4 * GATHER_PAIRS * 8;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -926,7 +929,7 @@ __global__ void __launch_bounds__(256) k_gather_elem(const int32_t *__restrict__
     for (int q = 0; q < 9; ++q) Ainv[t * 9 + q] = inv[q] * sw;
 }
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, 4)
 k_values_gather(const int32_t *__restrict__ ien, int64_t nEl, const double *__restrict__ Ainv, const int64_t *__restrict__ rowptr,
                 const int32_t *__restrict__ colind, double *__restrict__ val, Material mat, const int64_t *__restrict__ g_ptr,
                 const int32_t *__restrict__ g_ent, const int32_t *__restrict__ task_node, int ntasks, int max_slots) {
@@ -939,20 +942,21 @@ k_values_gather(const int32_t *__restrict__ ien, int64_t nEl, const double *__re
     const int task = blockIdx.x * 4 + warp;
     if (task >= ntasks) return;
     unsigned char *mine_smem = s_dyn + warp * gather_warp_bytes(max_slots);
-    double *stage = reinterpret_cast<double *>(mine_smem);        // [lane][73]: first the lane's 8 A matrices, then its 8 blocks
-    double *red = stage + 32 * GATHER_STAGE;                       // [slot][9]: the node's row blocks with the material applied
+    double *stage = reinterpret_cast<double *>(mine_smem);        // [pair][73]: first the pair's 8 A matrices, then its 8 blocks
+    double *red = stage + GATHER_PAIRS * GATHER_STAGE;             // [slot][9]: the node's row blocks with the material applied
     int32_t *adj_all = reinterpret_cast<int32_t *>(red + (size_t)((max_slots + 1) & ~1) * 9);  // [node of the task][slot]
-    int32_t *pnodes = adj_all + 32 * (size_t)((max_slots + 3) & ~3);  // [pair][8]: the node ids of every pair's element (16-byte aligned)
+    int32_t *pnodes = adj_all + GATHER_PAIRS * (size_t)((max_slots + 3) & ~3);  // [pair][8]: node ids of every pair's element (16-byte aligned)
     const int n_first = task_node[task], n_last = task_node[task + 1], nn_task = n_last - n_first;
     const int64_t base = g_ptr[n_first];
     const int cnt = (int)(g_ptr[n_last] - base);
-    const bool active = lane < cnt;
-    // this lane's pair: element, local node; its element's 8 node ids and 8 A matrices go to shared memory (all loads of the
-    // task are requested before anything waits on them)
+    // two lanes per (node, element) pair: lane 2p + h accumulates the blocks b = 4h .. 4h + 3 of pair p (36 accumulators: ~120
+    // registers, 16 warps per SM instead of 8)
+    const int pair = lane >> 1, half = lane & 1;
+    const bool active = pair < cnt;
     int a = 0;
     int64_t e = 0;
     if (active) {
-        const int32_t ent = g_ent[base + lane];
+        const int32_t ent = g_ent[base + pair];
         e = ent / NN;
         a = ent % NN;
     }
@@ -967,13 +971,13 @@ k_values_gather(const int32_t *__restrict__ ien, int64_t nEl, const double *__re
         my_p1 = (int)(g_ptr[n + 1] - base);
     }
     if (active) {
+        // the element's node ids (4 per lane) and its 8 A matrices (36 doubles per lane): asynchronous copies, all in flight at once
 #pragma unroll
-        for (int b = 0; b < NN; ++b) pnodes[lane * NN + b] = ien[(int64_t)b * nEl + e];
-        // the 8 A matrices: 72 asynchronous 8-byte copies per lane, all in flight at once (no register round trip)
-        const double *Ae = Ainv + e * 72;
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + lane * GATHER_STAGE);
-#pragma unroll 8
-        for (int q = 0; q < 72; ++q) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * q), "l"(Ae + q) : "memory");
+        for (int b = 0; b < 4; ++b) pnodes[pair * NN + 4 * half + b] = ien[(int64_t)(4 * half + b) * nEl + e];
+        const double *Ae = Ainv + e * 72 + 36 * half;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + pair * GATHER_STAGE + 36 * half);
+#pragma unroll 6
+        for (int q = 0; q < 36; ++q) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * q), "l"(Ae + q) : "memory");
     }
     // the neighbour lists (= the columns of the nodes' first rows) of all nodes of the task, flattened over (node, slot)
     for (int idx0 = 0; idx0 < nn_task * max_slots; idx0 += 32) {  // uniform trip count: the shuffles need all lanes
@@ -986,40 +990,43 @@ k_values_gather(const int32_t *__restrict__ ien, int64_t nEl, const double *__re
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
+    double G[4][9];
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int m = 0; m < 9; ++m) G[b][m] = 0.0;
     if (active) {
-        double G[NN][9];
-#pragma unroll
-        for (int b = 0; b < NN; ++b)
-#pragma unroll
-            for (int m = 0; m < 9; ++m) G[b][m] = 0.0;
 #pragma unroll 1
         for (int g = 0; g < NGP; ++g) {
             double A[9];
 #pragma unroll
-            for (int q = 0; q < 9; ++q) A[q] = stage[lane * GATHER_STAGE + g * 9 + q];
+            for (int q = 0; q < 9; ++q) A[q] = stage[pair * GATHER_STAGE + g * 9 + q];
             double ga[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) ga[c] = s_dN[g][a][0] * A[c] + s_dN[g][a][1] * A[3 + c] + s_dN[g][a][2] * A[6 + c];  // sqrt(w |det|) dNdX, :196
 #pragma unroll
-            for (int b = 0; b < NN; ++b) {
+            for (int b = 0; b < 4; ++b) {
+                const double *dn = s_dN[g][4 * half + b];
                 double gb[3];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) gb[c] = s_dN[g][b][0] * A[c] + s_dN[g][b][1] * A[3 + c] + s_dN[g][b][2] * A[6 + c];
+                for (int c = 0; c < 3; ++c) gb[c] = dn[0] * A[c] + dn[1] * A[3 + c] + dn[2] * A[6 + c];
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
 #pragma unroll
                     for (int j = 0; j < 3; ++j) G[b][i * 3 + j] += ga[i] * gb[j];
             }
         }
-        // park the 8 blocks of this (node, element) pair over the consumed A matrices: all lanes at once, odd lane stride
+    }
+    __syncwarp();  // both lanes of every pair have read the A matrices: the blocks may overwrite them
+    if (active) {
 #pragma unroll
-        for (int b = 0; b < NN; ++b)
+        for (int b = 0; b < 4; ++b)
 #pragma unroll
-            for (int m = 0; m < 9; ++m) stage[lane * GATHER_STAGE + b * 9 + m] = G[b][m];
+            for (int m = 0; m < 9; ++m) stage[pair * GATHER_STAGE + (4 * half + b) * 9 + m] = G[b][m];
     }
     __syncwarp();
     for (int i = 0; i < nn_task; ++i) {
-        const int p0 = __shfl_sync(0xffffffffu, my_p0, i), p1 = __shfl_sync(0xffffffffu, my_p1, i);  // this node's pairs = lanes [p0, p1)
+        const int p0 = __shfl_sync(0xffffffffu, my_p0, i), p1 = __shfl_sync(0xffffffffu, my_p1, i);  // this node's pairs [p0, p1)
         const int64_t r0 = __shfl_sync(0xffffffffu, my_r0, i);
         const int T = __shfl_sync(0xffffffffu, my_T, i);  // entries per row; the node's 3 rows are adjacent in K
         const int nslots = T / 3;
