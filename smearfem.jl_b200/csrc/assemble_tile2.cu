@@ -505,8 +505,15 @@ static void launch_tile2(smfem_ctx *ctx, TileArgs &A, int nown) {
         CUDA_CHECK(cudaEventCreate(&ctx->asm_ev[2 * slot]));
         CUDA_CHECK(cudaEventCreate(&ctx->asm_ev[2 * slot + 1]));
     }
+    // experiment knob: SMFEM_TILE_SMEM_PAD=<bytes> of extra dynamic shared memory per CTA lowers the number of resident CTAs
+    // (occupancy sensitivity: how much slower is the kernel with 4 instead of 8 warps per SM?)
+    size_t smem = T::SMEM_BYTES;
+    if (const char *pad = std::getenv("SMFEM_TILE_SMEM_PAD")) {
+        smem += (size_t)std::atol(pad);
+        CUDA_CHECK(cudaFuncSetAttribute(k_values_tile2<T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     CUDA_CHECK(cudaEventRecord(ctx->asm_ev[2 * slot], ctx->stream));
-    LAUNCH(ctx, (k_values_tile2<T, MINB>), grid, T::NTH, T::SMEM_BYTES, A);
+    LAUNCH(ctx, (k_values_tile2<T, MINB>), grid, T::NTH, smem, A);
     CUDA_CHECK(cudaEventRecord(ctx->asm_ev[2 * slot + 1], ctx->stream));
     ctx->asm_count++;
 }

@@ -58,6 +58,14 @@ for variant in ("v2base", "v2", "v2s"):
     print(f"variant {variant:7s} + side-stream colind kernel: step {f:.3f} ms", flush=True)
 os.environ.pop("SMFEM_COLIND_SIDE")
 os.environ["SMFEM_TILE"] = "v2"
+# occupancy sensitivity: one CTA (4 warps) per SM instead of two
+os.environ["SMFEM_TILE_SMEM_PAD"] = "40000"
+print(f"v2 with ONE resident CTA per SM (4 warps): values {run(lambda: K.assemble_values(40.0, 0.4)):.3f} ms, fused {run(lambda: K.reassemble(40.0, 0.4)):.3f} ms", flush=True)
+os.environ["SMFEM_TILE"] = "v2s"
+os.environ["SMFEM_TILE_SMEM_PAD"] = "20000"
+print(f"v2s (64-thread CTAs) with TWO resident CTAs per SM (4 warps): fused {run(lambda: K.reassemble(40.0, 0.4)):.3f} ms", flush=True)
+os.environ.pop("SMFEM_TILE_SMEM_PAD")
+os.environ["SMFEM_TILE"] = "v2"
 for plan in sys.argv[2:]:
     os.environ["SMFEM_TILE_CHUNKS"] = plan
     print(f"v2 chunks={plan}: fused {run(lambda: K.reassemble(40.0, 0.4)):.3f} ms", flush=True)
