@@ -541,6 +541,7 @@ void tile_fill_args(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material 
 void values_assemble_tile(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind, const int *ready) {
     TileArgs A;
     tile_fill_args(ctx, mesh, K, mat, write_colind, ready, A);
+    if (values_assemble_tile3(ctx, A, A.L.nown())) return;  // split-role layer-march kernel (assemble_tile3.cu), SMFEM_TILE=v3
     if (values_assemble_tile2(ctx, A, A.L.nown())) return;  // layer-march kernel (assemble_tile2.cu)
     if (values_assemble_mma(ctx, A, A.L.nown())) return;  // DMMA kernel (assemble_mma.cu), selected by SMFEM_TILE=mma*
     const char *e = std::getenv("SMFEM_TILE");

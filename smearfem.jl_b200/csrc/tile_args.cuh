@@ -111,5 +111,7 @@ std::vector<int> plan_chunks(int ntiles, int nown, int slots);
 void tile_fill_args(smfem_ctx *ctx, smfem_mesh *mesh, smfem_matrix *K, Material mat, bool write_colind, const int *ready, TileArgs &A);
 // assemble_tile2.cu: the layer-march kernel; returns false when not selected (env SMFEM_TILE)
 bool values_assemble_tile2(smfem_ctx *ctx, TileArgs &A, int nown);
+// assemble_tile3.cu: the split-role layer-march kernel (SMFEM_TILE=v3)
+bool values_assemble_tile3(smfem_ctx *ctx, TileArgs &A, int nown);
 // assemble_mma.cu: returns false when the DMMA kernel is not selected (env SMFEM_TILE)
 bool values_assemble_mma(smfem_ctx *ctx, TileArgs &A, int nown);
