@@ -21,21 +21,32 @@
 
 namespace {
 
+// WPRv: warps per role (tile = 4 x 2 WPRv node columns, 64 WPRv threads).  FULLv: the staging area of a warp holds both of its
+// node rows (8 nodes, as in assemble_tile2.cu) instead of one at a time.
+//   <4, false>: 4 x 8 tile, 256 threads, 2 CTAs/SM = 16 warps/SM, <= 128 registers, half-size staging (shared memory is 6 KB short)
+//   <3, true> : 4 x 6 tile, 192 threads, 2 CTAs/SM = 12 warps/SM, <= 168 registers, full staging
+template <int WPRv, bool FULLv>
 struct T3 {
-    static constexpr int TX = 4, TY = 8, NTH = 256, OPT = 15;
-    static constexpr int EX = TX + 1, EY = TY + 1, NEL = EX * EY;  // 45 footprint elements per layer
+    static constexpr int TX = 4, WPR = WPRv, TY = 2 * WPRv, NTH = 64 * WPRv, OPT = 15;
+    static constexpr bool FULL = FULLv;
+    static constexpr int EX = TX + 1, EY = TY + 1, NEL = EX * EY;  // footprint elements per layer (45 / 35)
     static constexpr int NELP = NEL;
-    static constexpr int P1 = 2, P2 = 4, P3 = 4;                   // conflict-free own-node loads: see T2 in assemble_tile2.cu
+    // pads in front of the rows of the face nodes q = 1, 2, 3: conflict-free own-node loads (see T2 in assemble_tile2.cu)
+    static constexpr int P1 = NELP == 45 ? 2 : 0, P2 = NELP == 45 ? 4 : 0, P3 = NELP == 45 ? 4 : 14;
     static constexpr int FACE = 12 * NELP + P3;
     static constexpr int GS = ((2 * FACE + 15) / 16) * 16 + 2;
     static constexpr int LAYER = 8 * GS;
     static constexpr int PX = TX + 2, PY = TY + 2, PLANE = PX * PY * 3;
     static constexpr int SN = 84;
-    static constexpr int STAGE_WARP = 4 * SN;  // ONE row of 4 nodes per warp
+    static constexpr int STAGE_WARP = (FULLv ? 8 : 4) * SN;
     static constexpr size_t SMEM_BYTES = sizeof(double) * (LAYER + (NTH / 32) * STAGE_WARP + 8 * 3 + 8 + 4 * PLANE);
     __host__ __device__ static constexpr int boff(int b) {
         return (b >> 2) * FACE + (b & 3) * 3 * NELP + ((b & 3) == 0 ? 0 : ((b & 3) == 1 ? P1 : ((b & 3) == 2 ? P2 : P3)));
     }
+    static constexpr int R1 = (boff(1) - 1) & 15, R2 = (boff(2) - EX - 1) & 15, R3 = (boff(3) - EX) & 15;
+    static_assert(R1 % 4 == 0 && R2 % 4 == 0 && R3 % 4 == 0 && R1 && R2 && R3 && R1 != R2 && R1 != R3 && R2 != R3,
+                  "face-row pads do not give a conflict-free own-node load");
+    static_assert(NELP == 45 || NELP == 35, "pads are tabulated for these two tile heights");
 };
 
 template <class T>
@@ -121,6 +132,7 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int mask) { return __sh
 // One sweep over the 8 Gauss points: X[q] += g_a g_b(q)' for the 4 nodes b of one face of this thread's element (Sf points at the
 // face's g_b rows, Sa at the row of the node a this thread's role pairs them with: the column's node on the swept face for the
 // same-plane role, on the other face for the other-plane role)
+template <class T3>
 __device__ __forceinline__ void sweep1(const double *Sf, const double *Sa, double (&X)[4][9]) {
     constexpr int NELP = T3::NELP;
 #pragma unroll 2
@@ -161,12 +173,13 @@ struct NodeGeo {
 // out: for each node and each of its 3 rows a section of len = 3 cx cy consecutive entries at  rowstart + lz * len.
 // After the shuffles thread (sx, sy) holds   O0: (sy - sx, 0)  [not slot 3]   O1: (-sx, 1 - 2 sy)  [not slot 2]
 //                                            O2: (1 - sx, 1 - 2 sy)  [not slot 1]
+template <class T3>
 __device__ __forceinline__ void emit_level3(const TileArgs &A, const NodeGeo &G, double (&X)[4][9], double *stage_w, int lane, int ix, int iy,
                                             int k, int dz, int jx0, int jy0) {
     const int slot = lane & 3, sx = slot & 1, sy = slot >> 1, nwl = lane >> 2;
     const Lattice &L = A.L;
     const int len = G.len_own;
-    double V[3][9];  // the thread's three output blocks with the material applied (src/fem.jl:230-249)
+    double V[3][9];  // the thread's three output blocks with the material applied (src/fem.jl:230-249); FULL: stored at once
 #pragma unroll
     for (int o = 0; o < 3; ++o) {
         double g[9];
@@ -191,7 +204,11 @@ __device__ __forceinline__ void emit_level3(const TileArgs &A, const NodeGeo &G,
             for (int j = 0; j < 3; ++j) {
                 const double gij = g[c * 3 + j], gji = g[j * 3 + c];
                 const double v = (c == j) ? A.mat.d11 * gij + A.mat.mu * (tr - gij) : A.mat.lam * gij + A.mat.mu * gji;
-                V[o][c * 3 + j] = v;
+                if (T3::FULL) {
+                    if (G.soff[o] >= 0) stage_w[nwl * T3::SN + G.soff[o] + c * len + j] = v;
+                } else {
+                    V[o][c * 3 + j] = v;
+                }
                 if (o == 0 && c == j && dz == 0 && slot == 0 && G.soff[0] >= 0)
                     A.diag[(((int64_t)(k - L.k0) * L.n1 + iy) * L.n1 + ix) * 3 + c] = v;
             }
@@ -200,8 +217,10 @@ __device__ __forceinline__ void emit_level3(const TileArgs &A, const NodeGeo &G,
     const int64_t planeoff = 9 * (G.pre(k) * G.S1 * G.S1 - G.pairs_base);
     const int ll = lane < 27 ? lane : lane - 16;  // lanes >= 27 re-read lanes 11..15's words (no bank conflict with lanes 16..26)
 #pragma unroll 1
+    if (T3::FULL) __syncwarp();
     for (int yrow = 0; yrow < 2; ++yrow) {
-        if ((nwl >> 2) == yrow) {
+        const double *stage_r = stage_w + (T3::FULL ? yrow * 4 * T3::SN : 0);  // this node row's 4 staged nodes
+        if (!T3::FULL && (nwl >> 2) == yrow) {
             double *my = stage_w + (nwl & 3) * T3::SN;
 #pragma unroll
             for (int o = 0; o < 3; ++o)
@@ -213,13 +232,13 @@ __device__ __forceinline__ void emit_level3(const TileArgs &A, const NodeGeo &G,
                         for (int j = 0; j < 3; ++j) dst[c * len + j] = V[o][c * 3 + j];
                 }
         }
-        __syncwarp();
+        if (!T3::FULL) __syncwarp();
         const int jy = jy0 + yrow;
         if (G.fast) {
             // interior warp: 12 sections of 27 entries; all loads first, then the stores; lane = position inside the section
             double v[12];
 #pragma unroll
-            for (int r = 0; r < 12; ++r) v[r] = stage_w[(r / 3) * T3::SN + (r % 3) * 27 + ll];
+            for (int r = 0; r < 12; ++r) v[r] = stage_r[(r / 3) * T3::SN + (r % 3) * 27 + ll];
             if (lane < 27) {
                 const int32_t col0 = (int32_t)(L.lnode(jx0, jy, nz) * 3) + G.crel27;
                 const int64_t g0 = planeoff + 9 * (int64_t)cz * G.rowc[yrow] + lz * 27 + lane;
@@ -251,7 +270,7 @@ __device__ __forceinline__ void emit_level3(const TileArgs &A, const NodeGeo &G,
                     const int dyr = cxn == 3 ? (blk * 11) >> 5 : blk >> 1;   // cxn is 2 or 3 (n1 >= 2)
                     const int dxr = blk - dyr * cxn;
                     const int32_t col = (int32_t)(L.lnode(jx + dxr - (jx > 0), jy + dyr - (jy > 0), nz) * 3) + j;
-                    const double *src = stage_w + node * T3::SN + lane;
+                    const double *src = stage_r + node * T3::SN + lane;
                     const int64_t g0 = base + lz * lenn + lane;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
@@ -262,10 +281,12 @@ __device__ __forceinline__ void emit_level3(const TileArgs &A, const NodeGeo &G,
                 base += 3 * TR;
             }
         }
-        __syncwarp();  // the staging area is rewritten by the next node row / level
+        if (!T3::FULL) __syncwarp();  // the staging area is rewritten by the next node row
     }
+    if (T3::FULL) __syncwarp();  // ... by the next level
 }
 
+template <class T3>
 __global__ void __launch_bounds__(T3::NTH, 2) k_values_tile3(const __grid_constant__ TileArgs A) {
     constexpr int NTH = T3::NTH, EX = T3::EX, LAYER = T3::LAYER;
     extern __shared__ double smem[];
@@ -276,7 +297,7 @@ __global__ void __launch_bounds__(T3::NTH, 2) k_values_tile3(const __grid_consta
     double *s_xyz = s_w + 8;                        // [4][PLANE] node-plane coordinate ring
     const Lattice &L = A.L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int role = warp >> 2, wq = warp & 3;      // role 0: same-plane blocks (dz = 0), role 1: other-plane blocks (dz = -1, +1)
+    const int role = warp / T3::WPR, wq = warp - role * T3::WPR;  // role 0: same-plane blocks (dz = 0), role 1: other-plane blocks (dz = -1, +1)
     for (int t = tid; t < 8 * 3; t += NTH) s_gp[t] = (&A.gp[0][0])[t];
     if (tid < 8) s_w[tid] = sqrt(A.w[tid]);
 
@@ -379,35 +400,33 @@ __global__ void __launch_bounds__(T3::NTH, 2) k_values_tile3(const __grid_consta
         __syncthreads();
         if (role == 0) {
             // bottom face: a and b on plane lay -> its dz = 0 blocks are complete;  top face: a and b on plane lay + 1, carried
-            if (el_ok) sweep1(Se, Se + boff_aq, X);
-            if (lay >= zs && lay < ze) emit_level3(A, G, X, stage_w, lane, ix, iy, lay, 0, jx0, jy0);
+            if (el_ok) sweep1<T3>(Se, Se + boff_aq, X);
+            if (lay >= zs && lay < ze) emit_level3<T3>(A, G, X, stage_w, lane, ix, iy, lay, 0, jx0, jy0);
             zero();
-            if (el_ok) sweep1(Se + T3::FACE, Se + T3::FACE + boff_aq, X);
+            if (el_ok) sweep1<T3>(Se + T3::FACE, Se + T3::FACE + boff_aq, X);
         } else {
             // bottom face with a on the top face: dz = -1 blocks of plane lay + 1;  top face with a on the bottom face: dz = +1 of plane lay
-            if (el_ok) sweep1(Se, Se + T3::FACE + boff_aq, X);
-            if (lay + 1 >= zs && lay + 1 < ze) emit_level3(A, G, X, stage_w, lane, ix, iy, lay + 1, -1, jx0, jy0);
+            if (el_ok) sweep1<T3>(Se, Se + T3::FACE + boff_aq, X);
+            if (lay + 1 >= zs && lay + 1 < ze) emit_level3<T3>(A, G, X, stage_w, lane, ix, iy, lay + 1, -1, jx0, jy0);
             zero();
-            if (el_ok) sweep1(Se + T3::FACE, Se + boff_aq, X);
-            if (lay >= zs && lay < ze) emit_level3(A, G, X, stage_w, lane, ix, iy, lay, +1, jx0, jy0);
+            if (el_ok) sweep1<T3>(Se + T3::FACE, Se + boff_aq, X);
+            if (lay >= zs && lay < ze) emit_level3<T3>(A, G, X, stage_w, lane, ix, iy, lay, +1, jx0, jy0);
             zero();
         }
     }
     // the top plane of the lattice has no element layer above it: its dz = 0 level is what the last top sweep left
-    if (role == 0 && ze == L.n1 && L1 + 1 >= zs) emit_level3(A, G, X, stage_w, lane, ix, iy, L1 + 1, 0, jx0, jy0);
+    if (role == 0 && ze == L.n1 && L1 + 1 >= zs) emit_level3<T3>(A, G, X, stage_w, lane, ix, iy, L1 + 1, 0, jx0, jy0);
 }
 
 }  // namespace
 
-// SMFEM_TILE = v3: the split-role layer-march kernel (returns false when not selected)
-bool values_assemble_tile3(smfem_ctx *ctx, TileArgs &A, int nown) {
-    const char *sel = std::getenv("SMFEM_TILE");
-    if (!(sel && std::string(sel) == "v3")) return false;
+template <class T>
+static void launch_tile3(smfem_ctx *ctx, TileArgs &A, int nown) {
     static std::atomic<unsigned long long> attr_set{0};
     if (first_use_on_device(attr_set))
-        CUDA_CHECK(cudaFuncSetAttribute(k_values_tile3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3::SMEM_BYTES));
-    A.tiles_x = (A.L.n1 + T3::TX - 1) / T3::TX;
-    A.tiles_y = (A.L.n1 + T3::TY - 1) / T3::TY;
+        CUDA_CHECK(cudaFuncSetAttribute(k_values_tile3<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES));
+    A.tiles_x = (A.L.n1 + T::TX - 1) / T::TX;
+    A.tiles_y = (A.L.n1 + T::TY - 1) / T::TY;
     const int ntiles = A.tiles_x * A.tiles_y;
     const std::vector<int> len = plan_chunks(ntiles, nown, ctx->sms * 2);
     A.nchunks = (int)len.size();
@@ -420,8 +439,18 @@ bool values_assemble_tile3(smfem_ctx *ctx, TileArgs &A, int nown) {
         CUDA_CHECK(cudaEventCreate(&ctx->asm_ev[2 * slot + 1]));
     }
     CUDA_CHECK(cudaEventRecord(ctx->asm_ev[2 * slot], ctx->stream));
-    LAUNCH(ctx, k_values_tile3, grid, T3::NTH, T3::SMEM_BYTES, A);
+    LAUNCH(ctx, (k_values_tile3<T>), grid, T::NTH, T::SMEM_BYTES, A);
     CUDA_CHECK(cudaEventRecord(ctx->asm_ev[2 * slot + 1], ctx->stream));
     ctx->asm_count++;
+}
+
+// SMFEM_TILE = v3 (256 threads, 16 warps/SM, half staging) / v3b (192 threads, 12 warps/SM, full staging): the split-role
+// layer-march kernels (returns false when not selected)
+bool values_assemble_tile3(smfem_ctx *ctx, TileArgs &A, int nown) {
+    const char *sel = std::getenv("SMFEM_TILE");
+    const std::string m = sel ? sel : "";
+    if (m == "v3") launch_tile3<T3<4, false>>(ctx, A, nown);
+    else if (m == "v3b") launch_tile3<T3<3, true>>(ctx, A, nown);
+    else return false;
     return true;
 }

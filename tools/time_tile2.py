@@ -44,7 +44,7 @@ for skip, name in [(1, "no phase1"), (2, "no sweeps"), (4, "no shuffles"), (8, "
     t = run(lambda: K.reassemble(40.0, 0.4), 5)
     print(f"v2 skip={skip:2d} {name:16s}: fused {t:.3f} ms", flush=True)
 os.environ.pop("SMFEM_TILE_SKIP")
-for variant in ("v2base", "v2l", "v2i", "v2li", "v2s", "v2g", "v2p", "v2", "v2e", "v2all", "v3"):
+for variant in ("v2base", "v2l", "v2i", "v2li", "v2s", "v2g", "v2p", "v2", "v2e", "v2all", "v3", "v3b"):
     os.environ["SMFEM_TILE"] = variant
     K.reassemble(40.0, 0.4)
     ok = bool(np.array_equal(K.diag(), d2))
