@@ -107,6 +107,22 @@ def test_fails_loudly_without_gpu():
     assert ei.value.code == _lib.ERR_CUDA and "no CPU fallback" in str(ei.value)
 
 
+def test_multi_gpu_entry_point_fails_loudly_without_gpu():
+    """smfem_init_multi (one process, n GPUs) has no CPU fallback either, and rejects impossible rank counts before touching CUDA."""
+    import torch
+
+    with pytest.raises(sf.SmearFEMError) as ei:
+        sf.MultiContext(0)
+    assert ei.value.code == _lib.ERR_INVALID
+    with pytest.raises(sf.SmearFEMError):
+        sf.MultiContext(9)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(sf.SmearFEMError) as ei:
+        sf.MultiContext(2)
+    assert ei.value.code == _lib.ERR_CUDA and "no CPU fallback" in str(ei.value)
+
+
 def test_setboundarycond_host_prep_matches_oracle():
     from oracle import fem_oracle as o
 
@@ -125,3 +141,51 @@ def test_meshgrid_2d_host_matches_oracle():
         for u, v in zip(a[:5], b[:5]):
             assert np.array_equal(u, v)
         assert a[5][0] == b[5][0]
+
+
+def _header_param_counts():
+    src = open(os.path.join(ROOT, "include", "smearfem_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(smfem_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def test_julia_shim_ccalls_match_the_header():
+    """Julia is not installed, so the shim cannot be executed here; this is the static check that stands in for it: every
+    `ccall((:smfem_x, LIB), ret, (argument types...), ...)` names a function the header declares and passes exactly as many
+    argument types as the C prototype has parameters."""
+    shim = open(os.path.join(ROOT, "smearfem.jl_b200", "julia", "SmearFEMB200.jl")).read()
+    counts = _header_param_counts()
+    seen = 0
+    for m in re.finditer(r"ccall\(\(:(smfem_[a-z0-9_]+),\s*LIB\),\s*(\w+),\s*\(", shim):
+        name = m.group(1)
+        assert name in counts, f"{name} is not declared in include/smearfem_b200.h"
+        # the type tuple: balanced parentheses starting at the '(' the regex ended on
+        i = m.end() - 1
+        depth, j = 0, i
+        while True:
+            depth += shim[j] == "("
+            depth -= shim[j] == ")"
+            if depth == 0:
+                break
+            j += 1
+        tup = shim[i + 1:j]
+        # split on top-level commas (Ptr{Ptr{Cvoid}} contains braces, not commas; a trailing comma makes a 1-tuple)
+        parts, depth_b, cur = [], 0, ""
+        for ch in tup:
+            depth_b += ch in "{("
+            depth_b -= ch in "})"
+            if ch == "," and depth_b == 0:
+                parts.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        parts.append(cur)
+        ntypes = len([p for p in parts if p.strip()])
+        assert ntypes == counts[name], f"{name}: the shim passes {ntypes} argument types, the header declares {counts[name]} parameters"
+        assert (m.group(2) == "Cstring") == (name == "smfem_last_error")
+        seen += 1
+    assert seen >= 25
