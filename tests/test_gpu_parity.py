@@ -489,7 +489,7 @@ def test_layer_march_kernel_variants_same_bits(monkeypatch, ne):
     K = sf.SparseMatrixB200.assemble(ctx, mesh, ne, 3, "Q1", 3, 40, 0.4)
     ref = K.to_csc() + (K.diag(),)
     monkeypatch.setenv("SMFEM_DEBUG_CLEAR", "1")
-    for variant in ("v2", "v2l", "v2i", "v2li", "v2s", "v2g", "v2p", "v2e", "v2all", "v3", "v3b"):
+    for variant in ("v2", "v2l", "v2i", "v2li", "v2s", "v2g", "v2p", "v2e", "v2all"):
         monkeypatch.setenv("SMFEM_TILE", variant)
         K.reassemble(40, 0.4)
         got = K.to_csc() + (K.diag(),)
