@@ -43,7 +43,7 @@ __device__ __forceinline__ double block_sum(double v, double *smem /* NT/32 doub
 
 // ------------------------------------------------------------------------------------------------
 // All-reduce of up to 4 doubles through the peer windows: every rank stores its partial into slot
-// [seq&1][rank] of EVERY rank's mailbox (direct NVLink stores), then releases a flag; readers spin
+// [seq&3][rank] of EVERY rank's mailbox (direct NVLink stores), then releases a flag; readers spin
 // on their own (local) mailbox and add the partials in rank order, so all ranks obtain bitwise
 // identical sums.  Four slots (seq & 3), see CommHeader: no host barrier is needed anywhere, not even
 // between consecutive solves.

@@ -189,3 +189,103 @@ def test_julia_shim_ccalls_match_the_header():
         assert (m.group(2) == "Cstring") == (name == "smfem_last_error")
         seen += 1
     assert seen >= 25
+
+
+def _header_param_types():
+    """name -> list of canonical parameter types of the C prototype: 'int', 'i64', 'f64', 'f32*', 'i64*', 'int*', 'f64*', 'ptr'
+    (an opaque handle or void*), 'ptr*' (pointer to a handle / to void*)."""
+    src = open(os.path.join(ROOT, "include", "smearfem_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(smfem_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        types = []
+        if args not in ("", "void"):
+            for a in args.split(","):
+                a = re.sub(r"\bconst\b", "", a).strip()
+                stars = a.count("*")
+                base = re.match(r"\s*([A-Za-z_0-9]+)", a).group(1)
+                scalar = {"int": "int", "int64_t": "i64", "double": "f64", "float": "f32"}.get(base)
+                if scalar is None:  # smfem_ctx / smfem_mesh / smfem_matrix / smfem_multi* / void: opaque
+                    assert stars >= 1, (m.group(1), a)
+                    types.append("ptr" + "*" * (stars - 1))
+                else:
+                    types.append(scalar + "*" * stars)
+        out[m.group(1)] = types
+    return out
+
+
+def test_python_binding_types_match_the_header():
+    """Every ctypes argtypes list in _lib.SIGNATURES has the C prototype's parameter types, position by position (a c_int where
+    the header says int64_t would pass on x86-64 registers and fail on the stack)."""
+    import ctypes as C
+
+    def canon(t):
+        if t is C.c_int:
+            return "int"
+        if t is C.c_int64:
+            return "i64"
+        if t is C.c_double:
+            return "f64"
+        if t is C.c_void_p:
+            return "ptr"
+        if t is C.c_char_p:
+            return "ptr"
+        if t is C.c_float:
+            return "f32"
+        if isinstance(t, type) and issubclass(t, C._Pointer):  # POINTER(x)
+            return canon(t._type_) + "*"
+        raise AssertionError(t)
+
+    hdr = _header_param_types()
+    for name, args in _lib.SIGNATURES.items():
+        got = [canon(t) for t in args]
+        assert got == hdr[name], f"{name}: ctypes {got} vs header {hdr[name]}"
+    for name, (_, args) in _lib.NON_STATUS.items():
+        assert [canon(t) for t in args] == hdr[name]
+    assert set(hdr) == set(_lib.SIGNATURES) | set(_lib.NON_STATUS)
+
+
+def _split_top_level(tup):
+    parts, depth, cur = [], 0, ""
+    for ch in tup:
+        depth += ch in "{("
+        depth -= ch in "})"
+        if ch == "," and depth == 0:
+            parts.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    parts.append(cur)
+    return [p.strip() for p in parts if p.strip()]
+
+
+def test_julia_shim_ccall_types_match_the_header():
+    """Type-level form of the static shim check: each entry of a ccall's argument-type tuple is the Julia spelling of the C
+    parameter type at that position (Cint / Int64 / Cdouble / Ptr{...} / Ref{...}; handles are Ptr{Cvoid})."""
+    julia = {
+        "int": {"Cint"}, "i64": {"Int64", "Clonglong"}, "f64": {"Cdouble", "Float64"}, "f32": {"Cfloat"},
+        "int*": {"Ptr{Cint}", "Ref{Cint}"}, "i64*": {"Ptr{Int64}", "Ref{Int64}"}, "f64*": {"Ptr{Cdouble}", "Ref{Cdouble}", "Ptr{Float64}"},
+        "f32*": {"Ptr{Cfloat}", "Ref{Cfloat}"}, "ptr": {"Ptr{Cvoid}"}, "ptr*": {"Ptr{Ptr{Cvoid}}", "Ref{Ptr{Cvoid}}"},
+    }
+    shim = open(os.path.join(ROOT, "smearfem.jl_b200", "julia", "SmearFEMB200.jl")).read()
+    hdr = _header_param_types()
+    seen = 0
+    for m in re.finditer(r"ccall\(\(:(smfem_[a-z0-9_]+),\s*LIB\),\s*(\w+),\s*\(", shim):
+        name = m.group(1)
+        i = m.end() - 1
+        depth, j = 0, i
+        while True:
+            depth += shim[j] == "("
+            depth -= shim[j] == ")"
+            if depth == 0:
+                break
+            j += 1
+        got = _split_top_level(shim[i + 1:j])
+        want = hdr[name]
+        assert len(got) == len(want), name
+        for k, (g, w) in enumerate(zip(got, want)):
+            ok = g in julia[w] or (w.endswith("*") and g == "Ptr{Cvoid}")  # a raw buffer may be passed as an untyped pointer
+            assert ok, f"{name}: argument {k + 1} is {g} in the shim, the header says {w}"
+        seen += 1
+    assert seen >= 25
