@@ -161,10 +161,11 @@ function assemble_system(ne, NodeList, IEN, ndim, FunctionClass="Q1", nDof=1, ID
 end
 
 function info(K::B200SparseMatrix)
-    v = [Ref{Int64}(0) for _ in 1:6]
+    m = Ref{Int64}(0); n = Ref{Int64}(0); nz = Ref{Int64}(0); row0 = Ref{Int64}(0); nrl = Ref{Int64}(0); nzl = Ref{Int64}(0)
+    # (no splatting here: ccall is a special form, its argument count must be visible in the syntax)
     check(ccall((:smfem_matrix_info, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
-                K.h, v...))
-    return (m=v[1][], n=v[2][], nnz=v[3][], row0=v[4][], nrows_local=v[5][], nnz_local=v[6][])
+                K.h, m, n, nz, row0, nrl, nzl))
+    return (m=m[], n=n[], nnz=nz[], row0=row0[], nrows_local=nrl[], nnz_local=nzl[])
 end
 Base.size(K::B200SparseMatrix) = (i = info(K); (Int(i.m), Int(i.n)))
 SparseArrays.nnz(K::B200SparseMatrix) = Int(info(K).nnz)

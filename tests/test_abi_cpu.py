@@ -287,5 +287,14 @@ def test_julia_shim_ccall_types_match_the_header():
         for k, (g, w) in enumerate(zip(got, want)):
             ok = g in julia[w] or (w.endswith("*") and g == "Ptr{Cvoid}")  # a raw buffer may be passed as an untyped pointer
             assert ok, f"{name}: argument {k + 1} is {g} in the shim, the header says {w}"
+        # the values: ccall is a special form, so exactly one value per type must be spelled out (no splatting)
+        depth, e = 1, j + 1
+        while depth:
+            depth += shim[e] in "([{"
+            depth -= shim[e] in ")]}"
+            e += 1
+        values = _split_top_level(shim[j + 1:e - 1].replace("[", "(").replace("]", ")"))
+        assert len(values) == len(want), f"{name}: {len(values)} values for {len(want)} parameters"
+        assert not any(v.endswith("...") for v in values), f"{name}: splatted ccall argument"
         seen += 1
     assert seen >= 25
