@@ -3,13 +3,21 @@ these variants are recorded experiments (profiles/r2_tile2_variants.txt), and un
 cut short the parity tests of the kernels the library actually runs by default.
 
 Hardware record: the diagonal of K from v3 / v3b was bit-identical to the default kernel at 100^3 (tools/time_tile2.py, profiles/
-r2_tile2_variants.txt); this test is the stricter check (colptr / rowval / nzval / diagonal, every buffer cleared to 0xFF first)."""
+r2_tile2_variants.txt); this test is the stricter check (colptr / rowval / nzval / diagonal, every buffer cleared to 0xFF first).
+No log of THIS test on hardware exists (the round's GPU budget ended first), so it runs only on request
+(SMFEM_TEST_EXPERIMENTAL=1): the default `-m gpu` suite is exactly the set of tests that has been seen green on a B200."""
+import os
+
 import numpy as np
 import pytest
 
 import smearfem_b200 as sf
 
-pytestmark = pytest.mark.gpu
+pytestmark = [
+    pytest.mark.gpu,
+    pytest.mark.skipif(os.environ.get("SMFEM_TEST_EXPERIMENTAL") != "1",
+                       reason="opt-in experimental kernels: set SMFEM_TEST_EXPERIMENTAL=1 (no hardware log of this test yet)"),
+]
 
 
 @pytest.mark.parametrize("ne", [5, 22, 37])
