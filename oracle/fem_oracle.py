@@ -186,6 +186,12 @@ def julia_sparse(E, J, V):
     E = np.asarray(E, dtype=np.int64)
     J = np.asarray(J, dtype=np.int64)
     V = np.asarray(V, dtype=np.float64)
+    if not (E.shape == J.shape == V.shape):
+        raise ValueError("sparse(I, J, V): the three vectors must have the same length")  # Julia: ArgumentError
+    if E.size == 0:  # sparse(Int[], Int[], Float64[]) is the 0 x 0 matrix
+        return JuliaCSC(0, 0, np.ones(1, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0))
+    if E.min() < 1 or J.min() < 1:
+        raise ValueError("sparse(I, J, V): indices are 1-based")  # Julia: ArgumentError
     m, n = int(E.max()), int(J.max())
     key = (J - 1) * m + (E - 1)
     order = np.argsort(key, kind="stable")  # stable -> input order kept inside a duplicate group

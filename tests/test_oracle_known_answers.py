@@ -205,3 +205,38 @@ def test_extract_borders_restatement_properties():
         assert side.min() >= -1e-9 * np.abs(S).max() ** 2
     with pytest.raises(NameError):
         o.extract_borders(NL, CM, BL, "other")
+
+
+def test_julia_sparse_restatement_semantics():
+    """`sparse(I, J, V)` as the call sites src/fem.jl:253 and examples/vector3D.jl:262 rely on it (Julia stdlib SparseArrays, not
+    under /root/reference): dims = (max I, max J), duplicates folded with + in INPUT order, numerical zeros stay structural,
+    rows ascending per column, empty columns allowed, empty input = the 0 x 0 matrix."""
+    # a fold whose result depends on the order: ((1e16 + 1) - 1e16) = 0 in input order, (1e16 - 1e16) + 1 = 1 otherwise
+    E = [3, 1, 3, 3, 2, 5, 5]
+    J = [2, 1, 2, 2, 4, 4, 4]
+    V = [1e16, 7.0, 1.0, -1e16, 0.0, 2.5, -2.5]
+    A = o.julia_sparse(E, J, V)
+    assert (A.m, A.n) == (5, 4)
+    assert list(A.colptr) == [1, 2, 3, 3, 5]  # column 3 is empty
+    assert list(A.rowval) == [1, 3, 2, 5]
+    assert list(A.nzval) == [7.0, (1e16 + 1.0) - 1e16, 0.0, 0.0]  # explicit zero (2,4) and cancelled pair (5,4) are both stored
+    assert A.get(3, 2) == 0.0 and A.get(5, 4) == 0.0 and A.get(4, 4) == 0.0 and A.nnz == 4
+    # against a naive dictionary fold on random triplets with many duplicates
+    rng = np.random.default_rng(7)
+    E = rng.integers(1, 9, 400)
+    J = rng.integers(1, 7, 400)
+    V = rng.standard_normal(400) * 10.0 ** rng.integers(-8, 9, 400)
+    A = o.julia_sparse(E, J, V)
+    acc = {}
+    for e, j, v in zip(E, J, V):
+        acc[(j, e)] = acc.get((j, e), 0.0) + v  # left-to-right
+    keys = sorted(acc)
+    assert [k[1] for k in keys] == list(A.rowval)
+    assert [acc[k] for k in keys] == list(A.nzval)  # bitwise
+    assert all(A.colptr[j] - A.colptr[j - 1] == sum(1 for k in keys if k[0] == j) for j in range(1, A.n + 1))
+    Z = o.julia_sparse([], [], [])
+    assert (Z.m, Z.n, Z.nnz, list(Z.colptr)) == (0, 0, 0, [1])
+    with pytest.raises(ValueError):
+        o.julia_sparse([0, 1], [1, 1], [1.0, 2.0])
+    with pytest.raises(ValueError):
+        o.julia_sparse([1, 2], [1], [1.0, 2.0])
