@@ -298,3 +298,30 @@ def test_julia_shim_ccall_types_match_the_header():
         assert not any(v.endswith("...") for v in values), f"{name}: splatted ccall argument"
         seen += 1
     assert seen >= 25
+
+
+def test_every_entry_point_rejects_null_handles_without_crashing():
+    """Error behaviour at the boundary (the reference throws Julia exceptions; no exception, abort or segfault may cross the C ABI):
+    every exported function called with NULL pointers and zero scalars returns a status (free / destroy of NULL are no-ops that
+    return SMFEM_OK, everything else SMFEM_ERR_INVALID with a message).  Runs in a child process so that a crash is a test
+    failure, not the end of the test session.  No GPU is touched."""
+    import subprocess
+    import sys
+
+    code = r"""
+import ctypes as C, sys
+sys.path.insert(0, %r)
+from smearfem_b200 import _lib
+L = _lib.lib()
+noop_ok = {"smfem_destroy", "smfem_mesh_free", "smfem_matrix_free", "smfem_multi_destroy", "smfem_multi_matrix_free", "smfem_multi_mesh_free"}
+for name, types in _lib.SIGNATURES.items():
+    args = [0 if t in (C.c_int, C.c_int64) else 0.0 if t is C.c_double else None for t in types]
+    rc = getattr(L, name)(*args)
+    want = _lib.OK if name in noop_ok else _lib.ERR_INVALID
+    assert rc == want, (name, rc, L.smfem_last_error())
+    assert name in noop_ok or L.smfem_last_error(), name
+print("ok", len(_lib.SIGNATURES))
+""" % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().startswith("ok")
