@@ -1,5 +1,6 @@
 """Stall samples of an ncu SASS-source export grouped by line ranges of one source file.
-usage: ncu_regions.py <src.csv> <nvdisasm -g output> <kernel index> <file> name:lo-hi ..."""
+usage: ncu_regions.py <src.csv> <nvdisasm -g output of the kernel> <section index> <file> name:lo-hi ...
+(`ncu --page source --csv` prints TWO sections per launch: launch i is section 2 i)"""
 import csv
 import re
 import sys
